@@ -1,0 +1,224 @@
+/*
+ * mvmc.h — C-ABI of the B200-native capture hot path (libmvmc.so).
+ *
+ * The reference (khanhha/multiview_motion_capture) is pure Python and has no FFI; the seams this
+ * library replaces are plain Python calls, cited per entry point below as /root/reference paths.
+ * INTEGRATION.md shows the ctypes stubs a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - All array arguments of the *stage* and *clip-batch* entry points are DEVICE pointers owned by the
+ *     caller, contiguous, row-major, float64 unless stated. `stream` is a cudaStream_t passed as void*.
+ *     Calls only enqueue work on `stream`; the caller keeps the buffers alive until it synchronises.
+ *   - `*_host` entry points take HOST pointers and include the host<->device copies.
+ *   - Return value: 0 on success, a negative MVMC_ERR_* otherwise. Nothing throws. No CPU fallback.
+ *   - Index layout of the association problem ("global index"): [ T alive tracks | kept poses of view 0
+ *     (ascending pose id) | view 1 | ... ], n = T + sum P_v   (reference: motion_capture.py:658-667).
+ *   - Joint layouts: 2D poses are COCO-17 (x, y, score); 3D track poses are BASIC_18 (x, y, z).
+ *   - A pose parameter vector is 68 doubles: root(3) | euler XYZ (18*3) | side bone lengths (11)
+ *     (reference: inverse_kinematics.py:86-91 PoseShapeParam).
+ */
+#ifndef MVMC_H_
+#define MVMC_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVMC_OK 0
+#define MVMC_ERR_INVALID (-1)   /* bad argument (null pointer, size out of range) */
+#define MVMC_ERR_CUDA (-2)      /* a CUDA call failed; see mvmc_last_cuda_error() */
+#define MVMC_ERR_CAPACITY (-3)  /* a per-clip capacity (tracks, births, views per match) overflowed */
+#define MVMC_ERR_NO_DEVICE (-4)
+
+#define MVMC_MAX_VIEWS 8        /* cameras per clip */
+#define MVMC_MAX_POSES 32       /* 2D poses per view */
+#define MVMC_MAX_TRACKS 64      /* alive tracks per clip */
+#define MVMC_N_COCO 17
+#define MVMC_N_B18 18
+#define MVMC_N_PARAM 68
+#define MVMC_MAX_SEL 8          /* 2D poses that can feed one IK solve */
+
+int mvmc_version(void);
+const char* mvmc_error_string(int code);
+const char* mvmc_last_cuda_error(void);
+
+/* First n doubles of numpy.random.RandomState(0).rand(...) (MT19937, 53-bit) — the ALS initial factor
+ * A0[i][j] = stream[i*r + j] (reference: mv_association.py:271). HOST pointer. */
+int mvmc_rand_stream_host(double* out, int n);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage entry points (one per reference seam). B = number of independent instances ("clips").
+ * ---------------------------------------------------------------------------------------------- */
+
+/* A1 — mv_math_util.py:57-77 get_fundamental_matrix for every ordered camera pair.
+ * P [B,C,3,4] -> F [B,C,C,3,3] with x_j^T F[i][j] x_i = 0. */
+int mvmc_fundamental(const double* P, double* F, int B, int C, void* stream);
+
+/* A7 helper — mv_math_util.py:267-285 calc_pairwise_f_mats: F from (K, R|t), float64 math stored as
+ * float32. K [B,C,3,3], Rt [B,C,3,4] -> F32 [B,C,C,3,3] (float). */
+int mvmc_fundamental_krt(const double* K, const double* Rt, float* F32, int B, int C, void* stream);
+
+/* A0 + A4 index layout — motion_capture.py:1023-1043 filter_bad_pose and :643-667.
+ * kps [B,C,Pmax,17,3], n_pose [B,C], n_trk [B] ->
+ * keep [B,C,Pmax] (u8), dim_groups [B,C+2], idx_view [B,N] (-1 for tracks), idx_pose [B,N] (pose id /
+ * track slot), N = Tmax + C*Pmax. */
+int mvmc_prepare(const double* kps, const int* n_pose, const int* n_trk, int B, int C, int Pmax, int Tmax,
+                 uint8_t* keep, int* dim_groups, int* idx_view, int* idx_pose, void* stream);
+
+/* A2 + A3 + A4 (+ A7 when n_trk[b] == 0) — motion_capture.py:634-756, :597-631;
+ * mv_math_util.py:80-115, :288-351. Needs mvmc_prepare's outputs.
+ * trk_joints [B,Tmax,18,3]; F [B,C,C,3,3]; F32 [B,C,C,3,3] float; dst, sim [B,N,N] (only the leading
+ * n x n block of each instance, leading dimension N, is written). */
+int mvmc_affinity(const double* kps, const double* P, const double* F, const float* F32,
+                  const double* trk_joints, const int* n_trk, const int* dim_groups, const int* idx_view,
+                  const int* idx_pose, int B, int C, int Pmax, int Tmax, double* dst, double* sim,
+                  void* stream);
+
+/* A5 — mv_association.py:222-318 match_als. sim [B,N,N] (ld N), dim_groups [B,G+1] with G = n_groups.
+ * f32_first_iter [B] (may be NULL): 1 where `sim` came from the float32 no-track path (A7).
+ * rand_stream: device copy of mvmc_rand_stream_host with at least N*rmax entries.
+ * workspace: mvmc_match_als_workspace_bytes(B, N, rmax) bytes of device memory.
+ * xbin [B,N,N/32 words] row bitmasks of X_bin; n_iter [B]. N must be a multiple of 32. */
+size_t mvmc_match_als_workspace_bytes(int B, int N, int rmax);
+int mvmc_match_als(const double* sim, const int* dim_groups, int n_groups, const int* f32_first_iter,
+                   const double* rand_stream, int B, int N, int rmax, void* workspace, uint32_t* xbin,
+                   int* n_iter, void* stream);
+
+/* A6 — mv_association.py:99-121 transform_closure, motion_capture.py:417-446 parse_match_result and
+ * :762-808 / :618-624 group decoding. Outputs, per instance:
+ *   trk_nsel [B,Tmax]: -1 = track absent from spatial_time_matches, else number of (view,pose) pairs;
+ *   trk_sel  [B,Tmax,MVMC_MAX_SEL,2]: (view, pose id);
+ *   new_n [B]; new_nsel [B,Nb]; new_sel [B,Nb,MVMC_MAX_SEL,2] for 2D-only groups (ALL of them, in
+ *   reference order, including single-view ones), Nb = max_new;
+ *   n_dup [B]: how often the "more than one pose per view" hack fired; err [B]: 0 or MVMC_ERR_CAPACITY. */
+int mvmc_assign(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose,
+                const int* n_trk, int B, int C, int N, int Tmax, int max_new, int* trk_nsel, int* trk_sel,
+                int* new_n, int* new_nsel, int* new_sel, int* n_dup, int* err, void* stream);
+
+/* B1 + B2 — mv_math_util.py:152-240 (DLT per joint + optional 2-nfev TRF refine).
+ * obs [M,V,K,3] (x,y,score), Psel [M,V,3,4], n_views [M] (<= V <= MVMC_MAX_SEL), K <= 18 joints.
+ * out [M,K,4] = (x,y,z,mean score). refine_nfev = 0 disables the refine. */
+int mvmc_triangulate(const double* obs, const double* Psel, const int* n_views, int M, int V, int K,
+                     double min_score, int refine_nfev, double* out, void* stream);
+
+/* I1 — inverse_kinematics.py:176-199 foward_kinematics on the BASIC_18 skeleton.
+ * params [M,68] -> joints [M,18,3]. */
+int mvmc_fk(const double* params, int M, double* joints, void* stream);
+
+/* I1/I6 generic chain — kinematics.py:18-31 without its two quirks.
+ * rot [M,J,3,3] local rotations, offsets [J,3], parents [J] (parent index < child index, -1 = root),
+ * root [M,3] or NULL -> joints [M,J,3]. J <= 64. */
+int mvmc_fk_chain(const double* rot, const double* offsets, const int* parents, const double* root, int M,
+                  int J, double* joints, void* stream);
+
+/* I0 + I2 + I3 + I4 + I5 — inverse_kinematics.py:202-277,339-433 PoseSolver.solve, with
+ * scipy.optimize.least_squares(method='trf', jac='2-point') restated on the device.
+ * kps2d [M,V,17,3] COCO poses feeding each solve, Psel [M,V,3,4], n_views [M];
+ * x0 [M,68] warm start (ignored where birth[m] != 0: triangulate -> root = mid hip, zero angles,
+ * reference bone lengths); max_nfev [M] (reference: 5 for updates, 50 for births);
+ * free_mask [68] u8 or NULL: 1 = parameter is optimised (NULL = all; the reference optimises all).
+ * Outputs: x_out [M,68], joints [M,18,3], info [M,2,4] = per solve (nfev, njev, status, n_free),
+ * cost [M,2]. workspace: mvmc_ik_workspace_bytes(M, V). */
+size_t mvmc_ik_workspace_bytes(int M, int V);
+int mvmc_ik_solve(const double* kps2d, const double* Psel, const int* n_views, const double* x0,
+                  const uint8_t* birth, const int* max_nfev, const uint8_t* free_mask, int M, int V,
+                  void* workspace, double* x_out, double* joints, int* info, double* cost, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Clip-batch pipeline: B independent clips advance one frame per step
+ * (reference: MvTracker.update_4d, motion_capture.py:873-963, one call per clip and frame).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mvmc_clips mvmc_clips;
+
+typedef struct mvmc_config {
+    int n_clips;      /* B */
+    int n_views;      /* C <= MVMC_MAX_VIEWS */
+    int max_poses;    /* Pmax <= MVMC_MAX_POSES */
+    int max_tracks;   /* Tmax <= MVMC_MAX_TRACKS */
+    int max_new;      /* births per clip per frame that can be solved (<= 32) */
+    int n_inits;      /* hits to confirm a track (reference: 3) */
+    int max_age;      /* misses tolerated by a confirmed track (reference: 0) */
+    int nfev_update;  /* reference: 5 */
+    int nfev_birth;   /* reference: 50 */
+    int keep_matrices;/* 1: keep dst/sim/xbin readable after a step (debug/parity) */
+} mvmc_config;
+
+void mvmc_default_config(mvmc_config* cfg);
+int mvmc_clips_create(const mvmc_config* cfg, mvmc_clips** out);
+void mvmc_clips_destroy(mvmc_clips* h);
+/* bytes of device memory held by the handle */
+size_t mvmc_clips_device_bytes(const mvmc_clips* h);
+
+/* K [B,C,3,3], Rt [B,C,3,4], P [B,C,3,4] (= K·Rt as the host computed it; reference:
+ * motion_capture.py:250-272 load_calib). Host or device pointers (copied with cudaMemcpyDefault);
+ * both fundamental-matrix tables are derived on the device. */
+int mvmc_clips_set_calib(mvmc_clips* h, const double* K, const double* Rt, const double* P, void* stream);
+/* forget all tracks of all clips */
+int mvmc_clips_reset(mvmc_clips* h, void* stream);
+
+/* Advance every clip by one frame. kps [B,C,Pmax,17,3], n_pose [B,C] DEVICE pointers.
+ * frame_idx is recorded in the outputs only. */
+int mvmc_clips_step(mvmc_clips* h, const double* kps, const int* n_pose, int frame_idx, void* stream);
+
+/* Per-step result record, one per clip (device layout == host layout). */
+typedef struct mvmc_track_out {
+    int32_t track_id;                 /* creation order within the clip (reference: append order) */
+    int32_t state;                    /* 1 tentative, 2 confirmed (dead tracks are not listed) */
+    int32_t hits;
+    int32_t time_since_update;
+    int32_t length;                   /* frames in which the track was solved */
+    int32_t updated;                  /* 1 = solved this frame (update or birth), 2 = born this frame */
+    int32_t n_sel;                    /* (view, pose) pairs used this frame */
+    int32_t sel[MVMC_MAX_SEL][2];
+    int32_t nfev[2], njev[2], status[2];
+    int32_t pad_;
+    double cost[2];
+    double param[MVMC_N_PARAM];
+    double joints[MVMC_N_B18 * 3];
+} mvmc_track_out;
+
+typedef struct mvmc_step_out {
+    int32_t frame_idx;
+    int32_t n_alive;                  /* tracks alive after the step */
+    int32_t n_died;                   /* tracks that died in this step */
+    int32_t died_ids[MVMC_MAX_TRACKS];
+    int32_t n_total;                  /* n of the association problem */
+    int32_t als_iters;
+    int32_t n_dup_view;
+    int32_t error;                    /* 0 or MVMC_ERR_CAPACITY */
+    mvmc_track_out tracks[MVMC_MAX_TRACKS];
+} mvmc_step_out;
+
+/* sizeof(mvmc_step_out) as compiled into the library (binding sanity check) */
+size_t mvmc_sizeof_step_out(void);
+
+/* DEVICE pointer to the B records written by the last step (valid until the next step). */
+const mvmc_step_out* mvmc_clips_last_out(const mvmc_clips* h);
+
+/* Same step with HOST buffers: copies kps/n_pose host->device, steps, copies the B records back and
+ * synchronises the stream. out_host may be NULL (then only `n_alive`-sized summaries stay on device). */
+int mvmc_clips_step_host(mvmc_clips* h, const double* kps_host, const int* n_pose_host, int frame_idx,
+                         mvmc_step_out* out_host, void* stream);
+
+/* Teacher forcing / checkpoint-resume: overwrite the alive-track table of every clip.
+ * n_trk [B]; ids, state, hits, tsu, length [B,Tmax]; param [B,Tmax,68]; joints [B,Tmax,18,3];
+ * next_id [B]. HOST pointers. */
+int mvmc_clips_set_tracks_host(mvmc_clips* h, const int* n_trk, const int* ids, const int* state,
+                               const int* hits, const int* tsu, const int* length, const double* param,
+                               const double* joints, const int* next_id, void* stream);
+
+/* Debug/parity read-back of the last step's association matrices of clip b (HOST pointers, sized n*n
+ * with n = n_total of that clip; xbin as bytes). Requires keep_matrices=1. */
+int mvmc_clips_read_matrices_host(mvmc_clips* h, int b, double* dst, double* sim, uint8_t* xbin, int* n,
+                                  int* dim_groups, void* stream);
+
+/* number of kernel launches enqueued by this library since load (for bench.py's gpu_launches) */
+unsigned long long mvmc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVMC_H_ */

@@ -1,0 +1,72 @@
+"""Builds libmvmc.so (the sm_100a CUDA kernels + C-ABI) in-tree with nvcc, and the oracle's C pieces.
+
+    python -m multiview_motion_capture_b200.build          # build if stale
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libmvmc.so")
+SOURCES = ["affinity.cu", "als.cu", "ik.cu", "pipeline.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+              "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_cuda(force=False, verbose=True):
+    os.makedirs(LIBDIR, exist_ok=True)
+    headers = [os.path.join(ROOT, "include", "mvmc.h"), os.path.join(CSRC, "mvmc_common.cuh")]
+    nvcc = _nvcc()
+    objs = []
+    jobs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(LIBDIR, s.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _stale(obj, [src] + headers):
+            jobs.append([nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj])
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        list(ex.map(run, jobs))
+    if force or jobs or _stale(LIB, objs):
+        run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return LIB
+
+
+def build_emulator(verbose=False):
+    """TEST INFRASTRUCTURE: the CPU kernel-emulator build used by the `-m "not gpu"` tier."""
+    script = os.path.join(ROOT, "tests", "emu", "build_emu.sh")
+    out = os.path.join(ROOT, "tests", "emu", "libmvmc_emu.so")
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "mvmc_common.cuh"),
+                                                        os.path.join(ROOT, "include", "mvmc.h"),
+                                                        os.path.join(ROOT, "tests", "emu", "cuda_emu.h")]
+    if _stale(out, deps):
+        subprocess.run(["bash", script], check=True, stdout=None if verbose else subprocess.DEVNULL)
+    return out
+
+
+if __name__ == "__main__":
+    print(build_cuda(force="--force" in sys.argv))

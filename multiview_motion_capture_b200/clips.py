@@ -1,0 +1,141 @@
+"""Clip-batch pipeline handle (mvmc_clips): B independent clips advance one frame per step.
+Mirrors MvTracker.update_4d (reference: src/motion_capture.py:873-963) for a batch of clips."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Config, N_COCO, STEP_OUT_DTYPE, check, ptr
+
+
+class ClipBatch:
+    def __init__(self, n_clips, n_views, max_poses, max_tracks=None, max_new=None, device=None, n_inits=3, max_age=0,
+                 nfev_update=5, nfev_birth=50):
+        lib = _lib.get_lib()
+        self.lib = lib
+        if device is None:
+            device = "cpu" if _lib.is_emulator() else "cuda"
+        self.device = torch.device(device)
+        if self.device.type == "cuda":
+            torch.cuda.set_device(self.device)
+        cfg = Config()
+        lib.mvmc_default_config(ctypes.byref(cfg))
+        cfg.n_clips, cfg.n_views, cfg.max_poses = n_clips, n_views, max_poses
+        cfg.max_tracks = max_tracks if max_tracks is not None else min(64, 2 * max_poses)
+        cfg.max_new = max_new if max_new is not None else min(32, max(4, max_poses))
+        cfg.n_inits, cfg.max_age, cfg.nfev_update, cfg.nfev_birth = n_inits, max_age, nfev_update, nfev_birth
+        self.cfg = cfg
+        self.B, self.C, self.Pmax, self.Tmax = n_clips, n_views, max_poses, cfg.max_tracks
+        self._h = ctypes.c_void_p()
+        check(lib.mvmc_clips_create(ctypes.byref(cfg), ctypes.byref(self._h)), "mvmc_clips_create")
+        self._pinned = self.device.type == "cuda"
+        self._out_host = self._host_buffer(n_clips * STEP_OUT_DTYPE.itemsize, np.uint8)
+        self._kps_host = self._host_buffer(n_clips * n_views * max_poses * N_COCO * 3, np.float64)
+        self._np_host = self._host_buffer(n_clips * n_views, np.int32)
+
+    def _host_buffer(self, count, dtype):
+        tdt = {np.uint8: torch.uint8, np.float64: torch.float64, np.int32: torch.int32}[dtype]
+        t = torch.empty(count, dtype=tdt)
+        if self._pinned:
+            t = t.pin_memory()
+        return t
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
+
+    @property
+    def device_bytes(self):
+        return self.lib.mvmc_clips_device_bytes(self._h)
+
+    def close(self):
+        if self._h:
+            self.lib.mvmc_clips_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_calib(self, K, Rt, P=None):
+        """K [B,C,3,3], Rt [B,C,3,4] (numpy, float64); P defaults to K @ Rt computed with NumPy exactly as
+        load_calib does (src/motion_capture.py:250-272)."""
+        K = np.ascontiguousarray(K, dtype=np.float64).reshape(self.B, self.C, 3, 3)
+        Rt = np.ascontiguousarray(Rt, dtype=np.float64).reshape(self.B, self.C, 3, 4)
+        if P is None:
+            P = np.stack([np.stack([K[b, c] @ Rt[b, c] for c in range(self.C)]) for b in range(self.B)])
+        P = np.ascontiguousarray(P, dtype=np.float64).reshape(self.B, self.C, 3, 4)
+        check(self.lib.mvmc_clips_set_calib(self._h, ptr(K), ptr(Rt), ptr(P), self._stream()), "mvmc_clips_set_calib")
+        self.sync()
+
+    def reset(self):
+        check(self.lib.mvmc_clips_reset(self._h, self._stream()), "mvmc_clips_reset")
+
+    def sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def step_device(self, kps, n_pose, frame_idx):
+        """Device-resident step: kps [B,C,Pmax,17,3] f64, n_pose [B,C] i32 torch tensors on self.device. Async."""
+        assert kps.dtype == torch.float64 and n_pose.dtype == torch.int32 and kps.is_contiguous() and n_pose.is_contiguous()
+        check(self.lib.mvmc_clips_step(self._h, ptr(kps), ptr(n_pose), int(frame_idx), self._stream()), "mvmc_clips_step")
+
+    def last_out_device(self):
+        """uint8 view [B, sizeof(mvmc_step_out)] of the device records of the last step (no copy)."""
+        addr = self.lib.mvmc_clips_last_out(self._h)
+        return addr
+
+    def step(self, kps, n_pose, frame_idx, want_out=True):
+        """Host-buffer step (H2D copy, all kernels, D2H copy of the records, sync). Returns a NumPy structured
+        array [B] of STEP_OUT_DTYPE (a view on a reused pinned buffer; copy it to keep it)."""
+        kh = self._kps_host.numpy()
+        kh[:] = np.asarray(kps, dtype=np.float64).reshape(-1)
+        nh = self._np_host.numpy()
+        nh[:] = np.asarray(n_pose, dtype=np.int32).reshape(-1)
+        return self.step_pinned(frame_idx, want_out)
+
+    def step_pinned(self, frame_idx, want_out=True):
+        """Same, taking the inputs already written into self.kps_host / self.n_pose_host."""
+        outp = ptr(self._out_host) if want_out else None
+        check(self.lib.mvmc_clips_step_host(self._h, ptr(self._kps_host), ptr(self._np_host), int(frame_idx), outp,
+                                            self._stream()), "mvmc_clips_step_host")
+        if not want_out:
+            return None
+        rec = self._out_host.numpy().view(STEP_OUT_DTYPE)
+        if (rec["error"] != 0).any():
+            bad = np.nonzero(rec["error"])[0]
+            raise _lib.MvmcError(f"capacity exceeded in clips {bad[:8].tolist()} (raise max_tracks / max_new)")
+        return rec
+
+    @property
+    def kps_host(self):
+        return self._kps_host.numpy().reshape(self.B, self.C, self.Pmax, N_COCO, 3)
+
+    @property
+    def n_pose_host(self):
+        return self._np_host.numpy().reshape(self.B, self.C)
+
+    def set_tracks(self, n_trk, ids, state, hits, tsu, length, param, joints, next_id):
+        a = lambda x, dt, shape: np.ascontiguousarray(np.asarray(x, dtype=dt).reshape(shape))
+        B, T = self.B, self.Tmax
+        args = [a(n_trk, np.int32, (B,)), a(ids, np.int32, (B, T)), a(state, np.int32, (B, T)), a(hits, np.int32, (B, T)),
+                a(tsu, np.int32, (B, T)), a(length, np.int32, (B, T)), a(param, np.float64, (B, T, 68)),
+                a(joints, np.float64, (B, T, 54)), a(next_id, np.int32, (B,))]
+        check(self.lib.mvmc_clips_set_tracks_host(self._h, *[ptr(x) for x in args], self._stream()),
+              "mvmc_clips_set_tracks_host")
+
+    def read_matrices(self, b=0):
+        """(dst, sim, xbin, dim_groups) of clip b from the last step."""
+        N = self.Tmax + self.C * self.Pmax
+        dst = np.zeros((N, N))
+        sim = np.zeros((N, N))
+        xb = np.zeros((N, N), dtype=np.uint8)
+        n = ctypes.c_int(0)
+        dg = np.zeros(self.C + 2, dtype=np.int32)
+        check(self.lib.mvmc_clips_read_matrices_host(self._h, b, ptr(dst), ptr(sim), ptr(xb), ctypes.addressof(n), ptr(dg),
+                                                     self._stream()), "mvmc_clips_read_matrices_host")
+        k = n.value
+        return (dst.reshape(-1)[:k * k].reshape(k, k).copy(), sim.reshape(-1)[:k * k].reshape(k, k).copy(),
+                xb.reshape(-1)[:k * k].reshape(k, k).astype(bool), dg)

@@ -1,0 +1,169 @@
+"""Stage-level wrappers over the C-ABI (one per reference seam). Tensors are torch tensors
+on the CUDA device (or CPU tensors when the test tier has bound the kernel emulator)."""
+import torch
+
+from . import _lib
+from ._lib import MAX_SEL, N_B18, N_COCO, N_PARAM, check, ptr
+
+f64 = torch.float64
+i32 = torch.int32
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream if t.is_cuda else None
+
+
+def _c(t, dtype):
+    assert t.dtype == dtype, (t.dtype, dtype)
+    return t.contiguous()
+
+
+def rand_stream(n, device):
+    """First n doubles of numpy.random.RandomState(0).rand (mv_association.py:271)."""
+    import numpy as np
+    out = np.empty(n, dtype=np.float64)
+    check(_lib.get_lib().mvmc_rand_stream_host(out.ctypes.data, n), "mvmc_rand_stream_host")
+    return torch.from_numpy(out).to(device)
+
+
+def fundamental(P):
+    """mv_math_util.py:57-77 for all ordered camera pairs. P [B,C,3,4] -> F [B,C,C,3,3]."""
+    P = _c(P, f64)
+    B, C = P.shape[:2]
+    F = torch.empty((B, C, C, 3, 3), dtype=f64, device=P.device)
+    check(_lib.get_lib().mvmc_fundamental(ptr(P), ptr(F), B, C, _stream(P)), "mvmc_fundamental")
+    return F
+
+
+def fundamental_krt(K, Rt):
+    """mv_math_util.py:267-285. K [B,C,3,3], Rt [B,C,3,4] -> F32 [B,C,C,3,3] float32."""
+    K, Rt = _c(K, f64), _c(Rt, f64)
+    B, C = K.shape[:2]
+    F = torch.empty((B, C, C, 3, 3), dtype=torch.float32, device=K.device)
+    check(_lib.get_lib().mvmc_fundamental_krt(ptr(K), ptr(Rt), ptr(F), B, C, _stream(K)), "mvmc_fundamental_krt")
+    return F
+
+
+def prepare(kps, n_pose, n_trk, Tmax):
+    """filter_bad_pose + index layout. kps [B,C,Pmax,17,3]; returns dict(keep, dim_groups, idx_view, idx_pose)."""
+    kps, n_pose, n_trk = _c(kps, f64), _c(n_pose, i32), _c(n_trk, i32)
+    B, C, Pmax = kps.shape[:3]
+    N = Tmax + C * Pmax
+    dev = kps.device
+    keep = torch.zeros((B, C, Pmax), dtype=torch.uint8, device=dev)
+    dg = torch.zeros((B, C + 2), dtype=i32, device=dev)
+    iv = torch.zeros((B, N), dtype=i32, device=dev)
+    ip = torch.zeros((B, N), dtype=i32, device=dev)
+    check(_lib.get_lib().mvmc_prepare(ptr(kps), ptr(n_pose), ptr(n_trk), B, C, Pmax, Tmax, ptr(keep), ptr(dg), ptr(iv),
+                                      ptr(ip), _stream(kps)), "mvmc_prepare")
+    return dict(keep=keep, dim_groups=dg, idx_view=iv, idx_pose=ip, N=N, Tmax=Tmax)
+
+
+def affinity(kps, P, F, F32, trk_joints, n_trk, prep):
+    """dst / sim matrices [B,N,N] (leading n x n block valid)."""
+    kps, P, F, trk_joints, n_trk = _c(kps, f64), _c(P, f64), _c(F, f64), _c(trk_joints, f64), _c(n_trk, i32)
+    F32 = _c(F32, torch.float32)
+    B, C, Pmax = kps.shape[:3]
+    Tmax, N = prep["Tmax"], prep["N"]
+    assert trk_joints.shape == (B, Tmax, N_B18, 3)
+    dst = torch.zeros((B, N, N), dtype=f64, device=kps.device)
+    sim = torch.zeros((B, N, N), dtype=f64, device=kps.device)
+    check(_lib.get_lib().mvmc_affinity(ptr(kps), ptr(P), ptr(F), ptr(F32), ptr(trk_joints), ptr(n_trk),
+                                       ptr(prep["dim_groups"]), ptr(prep["idx_view"]), ptr(prep["idx_pose"]), B, C, Pmax,
+                                       Tmax, ptr(dst), ptr(sim), _stream(kps)), "mvmc_affinity")
+    return dst, sim
+
+
+def match_als(sim, dim_groups, rmax, f32_first_iter=None, rand=None):
+    """mv_association.py:222-318. sim [B,N,N], dim_groups [B,G+1] -> xbin [B,N,NW] uint32 (as int32 bits), n_iter [B]."""
+    sim, dim_groups = _c(sim, f64), _c(dim_groups, i32)
+    B, N, _ = sim.shape
+    G = dim_groups.shape[1] - 1
+    dev = sim.device
+    lib = _lib.get_lib()
+    if rand is None:
+        rand = rand_stream(N * rmax, dev)
+    ws = torch.empty(lib.mvmc_match_als_workspace_bytes(B, N, rmax) // 8, dtype=f64, device=dev)
+    NW = (N + 31) // 32
+    xbin = torch.zeros((B, N, NW), dtype=i32, device=dev)
+    n_iter = torch.zeros((B,), dtype=i32, device=dev)
+    f32p = ptr(_c(f32_first_iter, i32)) if f32_first_iter is not None else None
+    check(lib.mvmc_match_als(ptr(sim), ptr(dim_groups), G, f32p, ptr(rand), B, N, rmax, ptr(ws), ptr(xbin), ptr(n_iter),
+                             _stream(sim)), "mvmc_match_als")
+    return xbin, n_iter
+
+
+def unpack_xbin(xbin, n):
+    """[N,NW] int32 bit rows -> (n,n) bool numpy."""
+    import numpy as np
+    w = xbin.cpu().numpy().view(np.uint32)
+    bits = ((w[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(w.shape[0], -1)
+    return bits[:n, :n].astype(bool)
+
+
+def assign(xbin, prep, n_trk, C, max_new):
+    """closure + parse + decode. Returns dict of int tensors (see include/mvmc.h mvmc_assign)."""
+    xbin, n_trk = _c(xbin, i32), _c(n_trk, i32)
+    B, N, _ = xbin.shape
+    Tmax = prep["Tmax"]
+    dev = xbin.device
+    z = lambda *s: torch.zeros(s, dtype=i32, device=dev)
+    out = dict(trk_nsel=z(B, max(Tmax, 1)), trk_sel=z(B, max(Tmax, 1), MAX_SEL, 2), new_n=z(B), new_nsel=z(B, max_new),
+               new_sel=z(B, max_new, MAX_SEL, 2), n_dup=z(B), err=z(B))
+    check(_lib.get_lib().mvmc_assign(ptr(xbin), ptr(prep["dim_groups"]), ptr(prep["idx_view"]), ptr(prep["idx_pose"]),
+                                     ptr(n_trk), B, C, N, Tmax, max_new, ptr(out["trk_nsel"]), ptr(out["trk_sel"]),
+                                     ptr(out["new_n"]), ptr(out["new_nsel"]), ptr(out["new_sel"]), ptr(out["n_dup"]),
+                                     ptr(out["err"]), _stream(xbin)), "mvmc_assign")
+    return out
+
+
+def triangulate(obs, Psel, n_views, min_score, refine_nfev=0):
+    """mv_math_util.py:152-240. obs [M,V,K,3], Psel [M,V,3,4], n_views [M] -> [M,K,4]."""
+    obs, Psel, n_views = _c(obs, f64), _c(Psel, f64), _c(n_views, i32)
+    M, V, K = obs.shape[:3]
+    out = torch.zeros((M, K, 4), dtype=f64, device=obs.device)
+    check(_lib.get_lib().mvmc_triangulate(ptr(obs), ptr(Psel), ptr(n_views), M, V, K, float(min_score), int(refine_nfev),
+                                          ptr(out), _stream(obs)), "mvmc_triangulate")
+    return out
+
+
+def fk(params):
+    """inverse_kinematics.py:176-199. params [M,68] -> joints [M,18,3]."""
+    params = _c(params, f64)
+    M = params.shape[0]
+    out = torch.empty((M, N_B18, 3), dtype=f64, device=params.device)
+    check(_lib.get_lib().mvmc_fk(ptr(params), M, ptr(out), _stream(params)), "mvmc_fk")
+    return out
+
+
+def fk_chain(rot, offsets, parents, root=None):
+    """Generic chain FK. rot [M,J,3,3], offsets [J,3], parents [J] int32, root [M,3] or None -> [M,J,3]."""
+    rot, offsets, parents = _c(rot, f64), _c(offsets, f64), _c(parents, i32)
+    M, J = rot.shape[:2]
+    out = torch.empty((M, J, 3), dtype=f64, device=rot.device)
+    rp = ptr(_c(root, f64)) if root is not None else None
+    check(_lib.get_lib().mvmc_fk_chain(ptr(rot), ptr(offsets), ptr(parents), rp, M, J, ptr(out), _stream(rot)),
+          "mvmc_fk_chain")
+    return out
+
+
+def ik_solve(kps2d, Psel, n_views, x0, birth=None, max_nfev=None, free_mask=None):
+    """PoseSolver.solve batched. kps2d [M,V,17,3] (V == 8), Psel [M,V,3,4], n_views [M], x0 [M,68].
+    Returns x_out [M,68], joints [M,18,3], info [M,2,4] (nfev, njev, status, n_free), cost [M,2]."""
+    kps2d, Psel, n_views, x0 = _c(kps2d, f64), _c(Psel, f64), _c(n_views, i32), _c(x0, f64)
+    M, V = kps2d.shape[:2]
+    dev = kps2d.device
+    lib = _lib.get_lib()
+    if max_nfev is None:
+        max_nfev = torch.full((M,), 5, dtype=i32, device=dev)
+    max_nfev = _c(max_nfev, i32)
+    bp = ptr(_c(birth, torch.uint8)) if birth is not None else None
+    fp = ptr(_c(free_mask, torch.uint8)) if free_mask is not None else None
+    ws = torch.empty(lib.mvmc_ik_workspace_bytes(M, V) // 8, dtype=f64, device=dev)
+    x_out = torch.zeros((M, N_PARAM), dtype=f64, device=dev)
+    joints = torch.zeros((M, N_B18, 3), dtype=f64, device=dev)
+    info = torch.zeros((M, 2, 4), dtype=i32, device=dev)
+    cost = torch.zeros((M, 2), dtype=f64, device=dev)
+    check(lib.mvmc_ik_solve(ptr(kps2d), ptr(Psel), ptr(n_views), ptr(x0), bp, ptr(max_nfev), fp, M, V, ptr(ws), ptr(x_out),
+                            ptr(joints), ptr(info), ptr(cost), _stream(kps2d)), "mvmc_ik_solve")
+    return x_out, joints, info, cost

@@ -1,0 +1,17 @@
+#!/bin/bash
+# TEST INFRASTRUCTURE — compile the real kernel sources against the CPU emulator (no GPU needed).
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+ROOT="$(cd "$HERE/../.." && pwd)"
+SRC="$ROOT/multiview_motion_capture_b200/csrc"
+OUT="$HERE/libmvmc_emu.so"
+FLAGS="-O1 -g -fPIC -std=c++17 -DMVMC_EMU -ffp-contract=off -I$ROOT/include -I$HERE -I$SRC -Wno-unused-variable"
+objs=""
+for f in affinity als ik pipeline; do
+  g++ $FLAGS -x c++ -c "$SRC/$f.cu" -o "$HERE/$f.emu.o" &
+  objs="$objs $HERE/$f.emu.o"
+done
+g++ $FLAGS -c "$HERE/emu_main.cpp" -o "$HERE/emu_main.emu.o" &
+wait
+g++ -shared -o "$OUT" $objs "$HERE/emu_main.emu.o"
+echo "built $OUT"
