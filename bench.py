@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Headline benchmark: frames/s of association + triangulation + IK on synthetic 8-camera x 32-person
+BODY_25 scenes (BASELINE.json metric), B independent clips per GPU advancing one frame per step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path (one JSON line on rank 0)
+    python bench.py --impl reference [...]                          # the CPU restatement of the reference
+
+A "step" = every clip of the batch advances by one multi-view frame (all 8 views, all people):
+association (affinity + ALS matcher + assignment), IK update of every matched track, triangulation + IK
+birth of new tracks, lifecycle. value = clips * steps / device time, inputs resident in HBM. e2e = the same
+through mvmc_clips_step_host (pinned host inputs copied H2D and result records copied D2H every step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/s assoc+triangulate+IK (8 cams x 32 people x BODY_25)"
+WORKLOAD = "synthetic 8 cams x 32 people BODY_25 clips, association + triangulation + IK, one frame per clip per step"
+N_VIEWS, N_PEOPLE = 8, 32
+
+
+def make_inputs(n_clips, n_frames, seed, distinct):
+    from multiview_motion_capture_b200 import synthetic as S
+    distinct = min(distinct, n_clips)
+    base = [S.make_clip(N_VIEWS, N_PEOPLE, n_frames, seed=seed, clip_idx=i) for i in range(distinct)]
+    idx = np.arange(n_clips) % distinct
+    kps = np.stack([S.body25_to_coco(c["kps25"]) for c in base], 1)[:, idx]      # [F,B,C,P,17,3]
+    n_pose = np.stack([c["n_pose"] for c in base], 1)[:, idx]
+    K = np.stack([c["K"] for c in base])[idx]
+    RT = np.stack([c["RT"] for c in base])[idx]
+    return np.ascontiguousarray(kps), np.ascontiguousarray(n_pose.astype(np.int32)), K, RT, base
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        try:
+            self.p.terminate()
+            self.p.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            self.f.flush()
+            self.f.seek(0)
+            sm, mx, reasons = [], [], set()
+            for line in self.f.read().splitlines():
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(mx)), reasons=sorted(reasons), samples=len(sm))
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.f.name)
+            except Exception:
+                pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port), one clip per process, steady-state tracking frames
+# ------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, clip_idx, first_frame, n_steps, n_warm = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mvmc_oracle as o
+    from multiview_motion_capture_b200 import synthetic as S
+    n_frames = first_frame + n_steps + n_warm + 1
+    c = S.make_clip(N_VIEWS, N_PEOPLE, n_frames, seed=seed, clip_idx=clip_idx)
+    kps = S.body25_to_coco(c["kps25"])
+    trk = o.Tracker(o.projections(c["K"], c["RT"]), c["K"], c["RT"])
+    # steady state: tracks warm-started from the generator's ground truth of the previous frame (births are
+    # 10x more expensive and belong to the first frames of a clip, not to the steady state being measured)
+    f0 = first_frame - 1
+    for pi in range(N_PEOPLE):
+        prm = o.PoseParam(c["gt_root"][f0, pi].copy(), c["gt_euler"][f0, pi].copy(), trk.skel.side_bone_lens * c["gt_scale"][pi])
+        joints, _ = o.forward_kinematics(trk.skel, prm.root, prm.euler, prm.bone_lens)
+        t = o.Track(pi, [f0], [prm], [joints], [[]], state=o.CONFIRMED, hits=3)
+        trk.tracks.append(t)
+    trk.next_id = N_PEOPLE
+    times = []
+    for s in range(n_warm + n_steps):
+        f = first_frame + s
+        t0 = time.perf_counter()
+        trk.step(f, kps[f], c["n_pose"][f])
+        times.append(time.perf_counter() - t0)
+    return times[n_warm:], len(trk.tracks)
+
+
+def cpu_arm(n_steps, n_warm, cores, seed=1000):
+    """Returns (frames_per_s, wall_s_per_step list, cores). Each step: `cores` clips advance one frame in parallel."""
+    import multiprocessing as mp
+    env_keys = ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")
+    old = {k: os.environ.get(k) for k in env_keys}
+    for k in env_keys:
+        os.environ[k] = "1"
+    try:
+        ctx = mp.get_context("spawn")
+        with ctx.Pool(cores) as pool:
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, [(seed, 100000 + i, 3, n_steps, n_warm) for i in range(cores)])
+            wall = time.perf_counter() - t0
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    per_clip = np.array([r[0] for r in res])          # [cores, n_steps] seconds per frame
+    step_wall = per_clip.max(axis=0)                  # a step ends when the slowest clip has finished its frame
+    fps = cores * n_steps / float(step_wall.sum())
+    return fps, step_wall.tolist(), float(per_clip.mean()), wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = args.cpu_cores or os.cpu_count() or 1
+    fps, step_wall, mean_frame_s, wall = cpu_arm(args.steps, min(args.warmup, 1), cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(step_wall)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "clips_per_step": cores, "n_views": N_VIEWS, "n_people": N_PEOPLE,
+                   "state": "steady-state tracking frames, tracks warm-started from ground truth"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{cores} clips x {args.steps} frames, one process per core, OMP_NUM_THREADS=1, "
+                                   f"mean {mean_frame_s:.2f} s per clip-frame (oracle/mvmc_oracle.py, bit-identical to the "
+                                   f"reference on its Shelf fixture)"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from multiview_motion_capture_b200 import _lib
+    from multiview_motion_capture_b200.clips import ClipBatch
+    from multiview_motion_capture_b200._lib import STEP_OUT_DTYPE, check, ptr
+    lib = _lib.get_lib()
+
+    B, K, W = args.clips, args.steps, args.warmup
+    n_frames = W + K + 1
+    t_gen = time.time()
+    kps, n_pose, Kc, RT, _ = make_inputs(B, n_frames, seed=1000 + 7919 * rank, distinct=args.distinct)
+    t_gen = time.time() - t_gen
+    cb = ClipBatch(B, N_VIEWS, N_PEOPLE, max_tracks=args.max_tracks, max_new=N_PEOPLE, device=dev)
+    cb.set_calib(Kc, RT)
+    kps_pin = torch.from_numpy(kps).pin_memory()
+    np_pin = torch.from_numpy(n_pose).pin_memory()
+    kps_dev = kps_pin.to(dev, non_blocking=True)
+    np_dev = np_pin.to(dev, non_blocking=True)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident timing ----------------
+    for s in range(W):
+        cb.step_device(kps_dev[1 + s], np_dev[1 + s], 1 + s)
+    cb.stats(reset=True)
+    cb.profile(1)
+    launches0 = lib.mvmc_launch_count()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for s in range(K):
+        cb.step_device(kps_dev[1 + W + s], np_dev[1 + W + s], 1 + W + s)
+    summary = None
+    if world > 1:
+        # the only collective of the path: gather per-rank result summaries (north_star: NCCL only to gather)
+        rec = torch.frombuffer(bytearray(8), dtype=torch.float64).to(dev)
+        rec[0] = float(B * K)
+        gathered = [torch.zeros_like(rec) for _ in range(world)]
+        dist.all_gather(gathered, rec)
+        summary = gathered
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = lib.mvmc_launch_count() - launches0
+    stage_ms, n_prof = cb.profile(0)
+    st = cb.stats(reset=True)
+    value = world * B * K / (ms * 1e-3)
+
+    # ---------------- FP64 DFMA peak probe ----------------
+    sink = torch.zeros(8, dtype=torch.float64, device=dev)
+    blocks, iters = 148 * 8, 200000
+    check(lib.mvmc_fp64_probe(blocks, 1000, ptr(sink), stream.cuda_stream), "probe")
+    torch.cuda.synchronize(dev)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    check(lib.mvmc_fp64_probe(blocks, iters, ptr(sink), stream.cuda_stream), "probe")
+    p1.record(stream)
+    torch.cuda.synchronize(dev)
+    fp64_peak_tflops = blocks * 256 * iters * 16.0 / (p0.elapsed_time(p1) * 1e-3) / 1e12
+
+    # ---------------- end-to-end through the host-buffer C-ABI call ----------------
+    e2e = None
+    if not args.no_e2e:
+        cb.reset()
+        out_pin = torch.empty(B * STEP_OUT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+
+        def host_step(fi):
+            check(lib.mvmc_clips_step_host(cb._h, ptr(kps_pin[fi]), ptr(np_pin[fi]), fi, ptr(out_pin), stream.cuda_stream),
+                  "mvmc_clips_step_host")
+        for s in range(W):
+            host_step(1 + s)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(K):
+            host_step(1 + W + s)
+        torch.cuda.synchronize(dev)
+        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        rec = out_pin.numpy().view(STEP_OUT_DTYPE)
+        e2e = {"value": world * B * K / float(t_e2e.item()), "unit": "frames/s",
+               "h2d_bytes_per_step": int(kps_pin[0].numel() * 8 + np_pin[0].numel() * 4),
+               "d2h_bytes_per_step": int(out_pin.numel()),
+               "alive_tracks_per_clip": float(rec["n_alive"].mean()), "capacity_errors": int((rec["error"] != 0).sum())}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    n_prof = max(n_prof, 1)
+    als_ms = stage_ms["als"] / n_prof
+    ik_ms = stage_ms["ik"] / n_prof
+    dom = "k_als" if als_ms >= ik_ms else "k_ik_solve"
+    dom_ms = max(als_ms, ik_ms)
+    dom_flops = (st["als_flops"] if dom == "k_als" else st["ik_flops"]) / K
+    # algorithmic bytes per launch: inputs (BODY_25 detections as float64 COCO) + outputs (params + joints + assignments)
+    bytes_per_clip_frame = N_VIEWS * N_PEOPLE * 17 * 3 * 8 + N_PEOPLE * (68 + 54) * 8 + 288 * 4
+    alg_bytes = B * bytes_per_clip_frame
+    achieved_tf = dom_flops / (dom_ms * 1e-3) / 1e12
+    roofline = {
+        "kernel": dom, "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
+        "frac": achieved_tf / fp64_peak_tflops if fp64_peak_tflops > 0 else None, "traffic": None,
+        "peak_source": "FP64 DFMA probe kernel timed in this run (not in MEASURED_PEAKS.json; SURVEY.md 8d)",
+        "kernel_ms_per_launch": dom_ms, "algorithmic_flops_per_launch": dom_flops,
+        "hbm": {"achieved": alg_bytes / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes / (dom_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                "algorithmic_bytes_per_launch": alg_bytes},
+        "stage_ms_per_step": {k: v / n_prof for k, v in stage_ms.items()},
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = args.cpu_cores or os.cpu_count() or 1
+        try:
+            fps, step_wall, mean_frame_s, wall = cpu_arm(1, 0, cores)
+            cpu_baseline = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                            "sample": f"{cores} clips x 1 steady-state frame of the same 8x32 workload, one process per core, "
+                                      f"OMP_NUM_THREADS=1, mean {mean_frame_s:.2f} s per clip-frame, wall {wall:.0f} s"}
+        except Exception as e:  # pragma: no cover
+            cpu_baseline = {"value": None, "unit": "frames/s", "cores": cores, "kind": "port", "sample": f"failed: {e}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "clips_per_gpu": B, "distinct_clips": min(args.distinct, B), "n_views": N_VIEWS,
+                   "n_people": N_PEOPLE, "max_tracks": args.max_tracks,
+                   "l2": "each step reads a new frame for every clip and sweeps the per-clip ALS workspaces "
+                         f"({cb.device_bytes / 2**20:.0f} MiB on device, far larger than the 126 MB L2)",
+                   "als_iters_per_clip_frame": st["als_iters"] / max(st["clip_frames"], 1),
+                   "ik_solves_per_clip_frame": st["ik_solves"] / max(st["clip_frames"], 1) / 2,
+                   "input_gen_s": t_gen},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=296, help="clips per GPU (2 per SM)")
+    ap.add_argument("--distinct", type=int, default=37, help="distinct synthetic clips generated per rank (tiled to --clips)")
+    ap.add_argument("--max-tracks", type=int, default=40)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-cores", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -215,6 +215,19 @@ int mvmc_clips_set_tracks_host(mvmc_clips* h, const int* n_trk, const int* ids, 
 int mvmc_clips_read_matrices_host(mvmc_clips* h, int b, double* dst, double* sim, uint8_t* xbin, int* n,
                                   int* dim_groups, void* stream);
 
+/* Device-side work counters accumulated by every step (HOST out[8]): [0] ALS algorithmic flops
+ * sum I(6rn^2+8r^2n+4r^3), [1] ALS iterations, [2] clip-frames, [3] IK solves, [4] nfev, [5] njev,
+ * [6] IK algorithmic flops (SURVEY.md §8d formula), [7] sum n^2. Synchronises the stream. */
+int mvmc_clips_stats_host(mvmc_clips* h, double* out, int reset, void* stream);
+
+/* Per-stage device time via CUDA events on the step's stream. enable: 1 = start (resets), 0 = stop and read,
+ * -1 = read. out_ms[5] = {prepare+affinity, ALS, assign+gather, IK, commit} summed over *n_steps steps. */
+int mvmc_clips_profile(mvmc_clips* h, int enable, double* out_ms, int* n_steps, void* stream);
+
+/* FP64 DFMA peak probe (roofline denominator for the FP64-issue-bound kernels): blocks x 256 threads x
+ * iters x 8 FMAs. Time it with events on `stream`; flops = blocks*256*iters*16. */
+int mvmc_fp64_probe(int blocks, int iters, double* sink, void* stream);
+
 /* number of kernel launches enqueued by this library since load (for bench.py's gpu_launches) */
 unsigned long long mvmc_launch_count(void);
 

@@ -61,6 +61,9 @@ _SIGNATURES = {
     "mvmc_clips_step_host": (c_int, [c_void_p, _P, _P, c_int, _P, _P]),
     "mvmc_clips_set_tracks_host": (c_int, [c_void_p] + [_P] * 9 + [_P]),
     "mvmc_clips_read_matrices_host": (c_int, [c_void_p, c_int, _P, _P, _P, _P, _P, _P]),
+    "mvmc_clips_stats_host": (c_int, [c_void_p, _P, c_int, _P]),
+    "mvmc_clips_profile": (c_int, [c_void_p, c_int, _P, _P, _P]),
+    "mvmc_fp64_probe": (c_int, [c_int, c_int, _P, _P]),
     "mvmc_launch_count": (c_ulonglong, []),
 }
 

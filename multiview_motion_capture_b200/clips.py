@@ -18,6 +18,8 @@ class ClipBatch:
             device = "cpu" if _lib.is_emulator() else "cuda"
         self.device = torch.device(device)
         if self.device.type == "cuda":
+            if self.device.index is None:
+                self.device = torch.device("cuda", torch.cuda.current_device())
             torch.cuda.set_device(self.device)
         cfg = Config()
         lib.mvmc_default_config(ctypes.byref(cfg))
@@ -125,6 +127,22 @@ class ClipBatch:
                 a(joints, np.float64, (B, T, 54)), a(next_id, np.int32, (B,))]
         check(self.lib.mvmc_clips_set_tracks_host(self._h, *[ptr(x) for x in args], self._stream()),
               "mvmc_clips_set_tracks_host")
+
+    STAT_NAMES = ("als_flops", "als_iters", "clip_frames", "ik_solves", "nfev", "njev", "ik_flops", "sum_n2")
+    STAGE_NAMES = ("affinity", "als", "assign", "ik", "commit")
+
+    def stats(self, reset=False):
+        out = np.zeros(8)
+        check(self.lib.mvmc_clips_stats_host(self._h, ptr(out), int(reset), self._stream()), "mvmc_clips_stats_host")
+        return dict(zip(self.STAT_NAMES, out.tolist()))
+
+    def profile(self, enable):
+        """enable=1 start recording stage events; 0 stop + read; -1 read. Returns (dict stage->ms, n_steps)."""
+        out = np.zeros(5)
+        n = ctypes.c_int(0)
+        check(self.lib.mvmc_clips_profile(self._h, int(enable), ptr(out), ctypes.addressof(n), self._stream()),
+              "mvmc_clips_profile")
+        return dict(zip(self.STAGE_NAMES, out.tolist())), n.value
 
     def read_matrices(self, b=0):
         """(dst, sim, xbin, dim_groups) of clip b from the last step."""

@@ -14,6 +14,10 @@
 
 int mvmc_ensure_skeleton();
 
+#define MVMC_N_STATS 8
+#define MVMC_N_STAGES 5
+#define MVMC_PROF_STEPS 512
+
 // ------------------------------------------------------------------------------------------------
 // library-level state
 // ------------------------------------------------------------------------------------------------
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(128)
              const int* __restrict__ assign_err, const int* __restrict__ dim_groups, const int* __restrict__ als_iter,
              const double* __restrict__ x_out, const double* __restrict__ j_out, const int* __restrict__ info,
              const double* __restrict__ cost, int C, int Tmax, int max_new, int n_inits, int max_age, int frame_idx,
-             mvmc_step_out* __restrict__ out) {
+             mvmc_step_out* __restrict__ out, double* __restrict__ stats) {
     __shared__ int s_src[MVMC_MAX_TRACKS];   // for output slot o: source (old slot t, or Tmax+k for a birth)
     __shared__ int s_upd[MVMC_MAX_TRACKS];
     __shared__ int s_n;
@@ -216,6 +220,36 @@ __global__ void __launch_bounds__(128)
         rec.als_iters = als_iter[b];
         rec.n_dup_view = n_dup[b];
         rec.error = error;
+        // algorithmic work counters: ALS flops = I (6 r n^2 + 8 r^2 n + 4 r^3)
+        const int* dg = dim_groups + b * (C + 2);
+        const double n = dg[C + 1];
+        int maxsz = 0;
+        for (int q = 0; q < C + 1; q++) maxsz = max(maxsz, dg[q + 1] - dg[q]);
+        const double r = min((double)n, 2.0 * maxsz);
+        const double it = als_iter[b];
+        atomicAdd(&stats[0], it * (6.0 * r * n * n + 8.0 * r * r * n + 4.0 * r * r * r));
+        atomicAdd(&stats[1], it);
+        atomicAdd(&stats[2], 1.0);
+        double solves = 0, nfev = 0, njev = 0, ikflops = 0;
+        for (int o = 0; o < n_out; o++) {
+            if (!s_upd[o]) continue;
+            const size_t slot = (size_t)b * S + s_src[o];
+            const int* sel_n = (s_upd[o] == 1) ? trk_nsel + b * Tmax + s_src[o] : new_nsel + b * max_new + (s_src[o] - Tmax);
+            const double V = *sel_n, m = 32.0 * V;
+            for (int q = 0; q < 2; q++) {
+                const double np_ = info[slot * 8 + q * 4 + 3], fe = info[slot * 8 + q * 4], je = info[slot * 8 + q * 4 + 1];
+                const double fres = 18 * (3 * 40 + 2 * 16 + 30) + 17 * 45 + V * 16 * 30;
+                solves += 1;
+                nfev += fe;
+                njev += je;
+                ikflops += (fe + je * np_) * fres + je * (2.0 * m * np_ * np_ + 10.0 * np_ * np_ * np_);
+            }
+        }
+        atomicAdd(&stats[3], solves);
+        atomicAdd(&stats[4], nfev);
+        atomicAdd(&stats[5], njev);
+        atomicAdd(&stats[6], ikflops);
+        atomicAdd(&stats[7], n * n);
     }
     __syncthreads();
     const int n_out = s_n;
@@ -289,9 +323,34 @@ __global__ void __launch_bounds__(128)
     if (threadIdx.x == 0) st.n_trk[b] = n_out;
 }
 
+// FP64 DFMA peak probe: 8 independent FMA chains per thread, `iters` x 8 x 2 flops per thread.
+__global__ void __launch_bounds__(256) k_fp64_probe(int iters, double* __restrict__ sink) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c);
+        a1 = fma(a1, m, c);
+        a2 = fma(a2, m, c);
+        a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c);
+        a5 = fma(a5, m, c);
+        a6 = fma(a6, m, c);
+        a7 = fma(a7, m, c);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 1.2345) sink[0] = r;  // never true; keeps the chains alive
+}
+
 }  // namespace mvmc
 
 using namespace mvmc;
+
+extern "C" int mvmc_fp64_probe(int blocks, int iters, double* sink, void* stream) {
+    if (blocks <= 0 || iters <= 0 || !sink) return MVMC_ERR_INVALID;
+    MVMC_LAUNCH(k_fp64_probe, dim3(blocks), dim3(256), 0, stream, iters, sink);
+    MVMC_CHECK_LAUNCH("k_fp64_probe");
+    return MVMC_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // handle
@@ -322,6 +381,12 @@ struct mvmc_clips {
     uint8_t* w_birth = nullptr;
     void* ik_ws = nullptr;
     mvmc_step_out* out = nullptr;
+    double* stats = nullptr;  // [MVMC_N_STATS] device counters
+    // optional per-stage event timing
+    int profiling = 0;
+    int ev_step = 0;
+    std::vector<cudaEvent_t> events;  // [MVMC_PROF_STEPS][MVMC_N_STAGES+1]
+    double stage_ms[MVMC_N_STAGES] = {0, 0, 0, 0, 0};
 
     template <class T>
     int alloc(T** p, size_t count) {
@@ -354,6 +419,9 @@ extern "C" void mvmc_default_config(mvmc_config* cfg) {
 
 extern "C" void mvmc_clips_destroy(mvmc_clips* h) {
     if (!h) return;
+#ifndef MVMC_EMU
+    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+#endif
     for (void* p : h->allocs) cudaFree(p);
     delete h;
 }
@@ -461,6 +529,7 @@ extern "C" int mvmc_clips_create(const mvmc_config* cfg, mvmc_clips** out) {
         h->ik_ws = p;
     }
     TRY(h->alloc(&h->out, (size_t)B));
+    TRY(h->alloc(&h->stats, (size_t)MVMC_N_STATS));
     {
         std::vector<double> rs((size_t)N * rmax);
         mvmc_rand_stream_host(rs.data(), (int)rs.size());
@@ -498,6 +567,14 @@ extern "C" int mvmc_clips_reset(mvmc_clips* h, void* stream) {
 extern "C" int mvmc_clips_step(mvmc_clips* h, const double* kps, const int* n_pose, int frame_idx, void* stream) {
     if (!h || !kps || !n_pose) return MVMC_ERR_INVALID;
     const int B = h->B, C = h->C, Pmax = h->Pmax, Tmax = h->Tmax, N = h->N;
+    int ev = -1;
+#ifndef MVMC_EMU
+    if (h->profiling && h->ev_step < MVMC_PROF_STEPS) ev = (h->ev_step++) * (MVMC_N_STAGES + 1);
+#define MVMC_EV(i) do { if (ev >= 0) cudaEventRecord(h->events[ev + (i)], (cudaStream_t)stream); } while (0)
+#else
+#define MVMC_EV(i) do { (void)ev; } while (0)
+#endif
+    MVMC_EV(0);
     MVMC_LAUNCH(k_predict, dim3((B + 127) / 128), dim3(128), 0, stream, h->st, B, Tmax, h->f32_flag);
     MVMC_CHECK_LAUNCH("k_predict");
     int rc = mvmc_prepare(kps, n_pose, h->st.n_trk, B, C, Pmax, Tmax, h->keep, h->dim_groups, h->idx_view, h->idx_pose,
@@ -506,9 +583,11 @@ extern "C" int mvmc_clips_step(mvmc_clips* h, const double* kps, const int* n_po
     rc = mvmc_affinity(kps, h->P, h->F, h->F32, h->st.joints, h->st.n_trk, h->dim_groups, h->idx_view, h->idx_pose, B, C,
                        Pmax, Tmax, h->dst, h->sim, stream);
     if (rc) return rc;
+    MVMC_EV(1);
     rc = mvmc_match_als(h->sim, h->dim_groups, C + 1, h->f32_flag, h->rand_stream, B, N, h->rmax, h->als_ws, h->xbin,
                         h->als_iter, stream);
     if (rc) return rc;
+    MVMC_EV(2);
     rc = mvmc_assign(h->xbin, h->dim_groups, h->idx_view, h->idx_pose, h->st.n_trk, B, C, N, Tmax, h->cfg.max_new,
                      h->trk_nsel, h->trk_sel, h->new_n, h->new_nsel, h->new_sel, h->n_dup, h->assign_err, stream);
     if (rc) return rc;
@@ -516,13 +595,65 @@ extern "C" int mvmc_clips_step(mvmc_clips* h, const double* kps, const int* n_po
                 h->new_sel, C, Pmax, Tmax, h->cfg.max_new, h->cfg.nfev_update, h->cfg.nfev_birth, h->w_kps, h->w_P, h->w_nv,
                 h->w_x0, h->w_birth, h->w_nfev);
     MVMC_CHECK_LAUNCH("k_gather");
+    MVMC_EV(3);
     rc = mvmc_ik_solve(h->w_kps, h->w_P, h->w_nv, h->w_x0, h->w_birth, h->w_nfev, nullptr, B * h->S, MVMC_MAX_SEL, h->ik_ws,
                        h->w_xout, h->w_joints, h->w_info, h->w_cost, stream);
     if (rc) return rc;
+    MVMC_EV(4);
     MVMC_LAUNCH(k_commit, dim3(B), dim3(128), 0, stream, h->st, h->trk_nsel, h->trk_sel, h->new_n, h->new_nsel, h->new_sel,
                 h->n_dup, h->assign_err, h->dim_groups, h->als_iter, h->w_xout, h->w_joints, h->w_info, h->w_cost, C, Tmax,
-                h->cfg.max_new, h->cfg.n_inits, h->cfg.max_age, frame_idx, h->out);
+                h->cfg.max_new, h->cfg.n_inits, h->cfg.max_age, frame_idx, h->out, h->stats);
     MVMC_CHECK_LAUNCH("k_commit");
+    MVMC_EV(5);
+    return MVMC_OK;
+}
+
+// stats: [0] ALS flops, [1] ALS iterations, [2] clip-frames, [3] IK solves, [4] nfev, [5] njev, [6] IK flops (est.),
+// [7] sum n^2 (affinity entries)
+extern "C" int mvmc_clips_stats_host(mvmc_clips* h, double* out, int reset, void* stream) {
+    if (!h || !out) return MVMC_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    MVMC_CUDA_OK(cudaStreamSynchronize(s));
+    MVMC_CUDA_OK(cudaMemcpy(out, h->stats, MVMC_N_STATS * sizeof(double), cudaMemcpyDeviceToHost));
+    if (reset) MVMC_CUDA_OK(cudaMemset(h->stats, 0, MVMC_N_STATS * sizeof(double)));
+    return MVMC_OK;
+}
+
+// Per-stage device time from CUDA events recorded on the step's stream:
+// out[0] prepare+affinity, [1] ALS matcher, [2] assign+gather, [3] IK (updates + births), [4] commit  (ms, summed
+// over the steps since the last reset). enable: 1 start recording (resets), 0 stop, -1 just read.
+extern "C" int mvmc_clips_profile(mvmc_clips* h, int enable, double* out_ms, int* n_steps, void* stream) {
+    if (!h) return MVMC_ERR_INVALID;
+#ifndef MVMC_EMU
+    cudaStream_t s = (cudaStream_t)stream;
+    if (enable == 1) {
+        if (h->events.empty()) {
+            h->events.resize((size_t)MVMC_PROF_STEPS * (MVMC_N_STAGES + 1));
+            for (auto& e : h->events) MVMC_CUDA_OK(cudaEventCreate(&e));
+        }
+        h->profiling = 1;
+        h->ev_step = 0;
+        return MVMC_OK;
+    }
+    MVMC_CUDA_OK(cudaStreamSynchronize(s));
+    if (out_ms) {
+        for (int q = 0; q < MVMC_N_STAGES; q++) out_ms[q] = 0.0;
+        for (int st = 0; st < h->ev_step; st++)
+            for (int q = 0; q < MVMC_N_STAGES; q++) {
+                float ms = 0.f;
+                MVMC_CUDA_OK(cudaEventElapsedTime(&ms, h->events[(size_t)st * (MVMC_N_STAGES + 1) + q],
+                                                  h->events[(size_t)st * (MVMC_N_STAGES + 1) + q + 1]));
+                out_ms[q] += ms;
+            }
+    }
+    if (n_steps) *n_steps = h->ev_step;
+    if (enable == 0) h->profiling = 0;
+#else
+    (void)stream;
+    if (out_ms) for (int q = 0; q < MVMC_N_STAGES; q++) out_ms[q] = 0.0;
+    if (n_steps) *n_steps = 0;
+    (void)enable;
+#endif
     return MVMC_OK;
 }
 

@@ -1,0 +1,168 @@
+"""Synthetic multi-camera scenes of the shape BASELINE.json names.
+
+Cameras on a ring looking at the origin, people on a jittered floor grid animated by a smooth random
+walk of the BASIC_18 Euler angles, projected to OpenPose BODY_25 detections with pixel noise, joint
+dropout, per-view person misses and per-view shuffled person order. The same packed arrays feed the CUDA
+path, the oracle and (through oracle/make_golden.py) the real reference.
+
+Packed clip (dict of NumPy arrays):
+    kps25  [F, C, Pmax, 25, 3]  float64  BODY_25 (x, y, score), zero padded
+    n_pose [F, C]               int32
+    K [C,3,3], RT [C,3,4], img_wh [C,2]
+    gt_person [F, C, Pmax] int32 (person index behind each detection, -1 = padding)
+"""
+import numpy as np
+
+B18_PARENTS = np.array([-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 9, 10, 8, 12, 13, 8, 15, 15])
+B18_OFFSETS = np.array([
+    [0, 0, 0], [0.15, 0, 0], [0, 0, -0.5], [0, 0, -0.5], [-0.15, 0, 0], [0, 0, -0.5], [0, 0, -0.5],
+    [0, 0, 0.3], [0, 0, 0.3], [0.2, 0, 0], [0.3, 0, 0], [0.3, 0, 0], [-0.2, 0, 0], [-0.3, 0, 0],
+    [-0.3, 0, 0], [0, -0.02, 0.15], [0.07, 0.02, 0.1], [-0.07, 0.02, 0.1]], dtype=np.float64)
+LEAF_JOINTS = np.array([3, 6, 11, 14, 16, 17])
+# BODY_25 slot <- BASIC_18 joint (others are synthesised or left at score 0)
+_B25_FROM_B18 = {0: 15, 1: 8, 2: 12, 3: 13, 4: 14, 5: 9, 6: 10, 7: 11, 8: 0, 9: 4, 10: 5, 11: 6, 12: 1, 13: 2, 14: 3,
+                 17: 17, 18: 16}
+BODY25_TO_COCO = np.array([0, 16, 15, 18, 17, 5, 2, 6, 3, 7, 4, 12, 9, 13, 10, 14, 11])
+
+GOLDEN_SCENES = {
+    # name -> make_clip kwargs (kept tiny: the real reference needs ~0.3 s per track-frame)
+    "c4p3": dict(n_views=4, n_people=3, n_frames=9, seed=11, max_poses=4),
+    "c8p6": dict(n_views=8, n_people=6, n_frames=5, seed=12, max_poses=8),
+    "c8p12": dict(n_views=8, n_people=12, n_frames=3, seed=13, max_poses=12),
+}
+
+
+def body25_to_coco(kps25):
+    """OpenPose BODY_25 -> COCO-17 joint gather (reference: src/pose_def.py:262-270)."""
+    return kps25[..., BODY25_TO_COCO, :]
+
+
+def _rot_xyz(e):
+    """(...,3) Euler angles -> (...,3,3) with R = Rx(a) Ry(b) Rz(c)."""
+    a, b, c = e[..., 0], e[..., 1], e[..., 2]
+    ca, sa, cb, sb, cc, sc = np.cos(a), np.sin(a), np.cos(b), np.sin(b), np.cos(c), np.sin(c)
+    z, o = np.zeros_like(a), np.ones_like(a)
+    rx = np.stack([o, z, z, z, ca, -sa, z, sa, ca], -1).reshape(a.shape + (3, 3))
+    ry = np.stack([cb, z, sb, z, o, z, -sb, z, cb], -1).reshape(a.shape + (3, 3))
+    rz = np.stack([cc, -sc, z, sc, cc, z, z, z, o], -1).reshape(a.shape + (3, 3))
+    return rx @ ry @ rz
+
+
+def fk_batch(root, euler, scale):
+    """root (...,3), euler (...,18,3), scale (...) -> joints (...,18,3) on the reference skeleton."""
+    R = _rot_xyz(euler)
+    shp = root.shape[:-1]
+    pos = np.zeros(shp + (18, 3))
+    G = np.zeros(shp + (18, 3, 3))
+    G[..., 0, :, :] = R[..., 0, :, :]
+    pos[..., 0, :] = root
+    for j in range(1, 18):
+        p = B18_PARENTS[j]
+        G[..., j, :, :] = G[..., p, :, :] @ R[..., j, :, :]
+        pos[..., j, :] = pos[..., p, :] + (G[..., p, :, :] @ (B18_OFFSETS[j] * scale[..., None])[..., None])[..., 0]
+    return pos
+
+
+def make_cameras(rng, n_views, img_wh=(1920, 1080), focal=1000.0):
+    W, H = img_wh
+    K = np.array([[focal, 0, W / 2], [0, focal, H / 2], [0, 0, 1.0]])
+    Ks, RTs = [], []
+    base = rng.uniform(0, 2 * np.pi)
+    for v in range(n_views):
+        th = base + 2 * np.pi * v / n_views + rng.uniform(-0.1, 0.1)
+        r, h = rng.uniform(5.0, 6.0), rng.uniform(2.4, 3.0)
+        c = np.array([r * np.cos(th), r * np.sin(th), h])
+        fwd = -c / np.linalg.norm(c)
+        right = np.cross(fwd, np.array([0, 0, 1.0]))
+        right /= np.linalg.norm(right)
+        down = np.cross(fwd, right)
+        R = np.stack([right, down, fwd])
+        RTs.append(np.concatenate([R, (-R @ c)[:, None]], axis=1))
+        Ks.append(K.copy())
+    return np.array(Ks), np.array(RTs)
+
+
+def make_clip(n_views=8, n_people=32, n_frames=10, seed=1000, clip_idx=0, max_poses=None, img_wh=(1920, 1080),
+              noise_px=2.0, p_joint_drop=0.05, p_person_miss=0.10, fps=30.0, floor=10.0, shelf_calib=None):
+    """One packed clip. `shelf_calib=(K, RT, img_wh)` re-uses given cameras (config 2 uses the Shelf ones)."""
+    rng = np.random.default_rng(seed + clip_idx)
+    if shelf_calib is not None:
+        Ks, RTs, img_wh = np.asarray(shelf_calib[0]), np.asarray(shelf_calib[1]), tuple(shelf_calib[2])
+        n_views = len(Ks)
+        floor = 4.0
+    else:
+        Ks, RTs = make_cameras(rng, n_views, img_wh)
+    W, H = img_wh
+    Pm = max_poses or n_people
+    P = np.einsum("vij,vjk->vik", Ks, RTs)
+    # people on a jittered grid
+    g = int(np.ceil(np.sqrt(n_people)))
+    cell = floor / g
+    cells = rng.permutation(g * g)[:n_people]
+    jit = max(0.0, (cell - 0.8) / 2)
+    xy = np.stack([(cells % g + 0.5) * cell - floor / 2, (cells // g + 0.5) * cell - floor / 2], 1)
+    xy += rng.uniform(-jit, jit, size=xy.shape) if jit > 0 else 0.0
+    root = np.concatenate([xy, np.full((n_people, 1), 0.95)], 1)
+    scale = rng.uniform(0.9, 1.1, size=n_people)
+    root[:, 2] *= scale
+    euler = rng.normal(0, 0.15, size=(n_people, 18, 3)).clip(-0.8, 0.8)
+    euler[:, 0, 2] = rng.uniform(-0.8, 0.8, size=n_people)
+    euler[:, LEAF_JOINTS] = 0.0
+    vel = rng.normal(0, 0.5, size=(n_people, 2))
+    kps25 = np.zeros((n_frames, n_views, Pm, 25, 3))
+    n_pose = np.zeros((n_frames, n_views), dtype=np.int32)
+    gt_person = np.full((n_frames, n_views, Pm), -1, dtype=np.int32)
+    gt_joints = np.zeros((n_frames, n_people, 18, 3))
+    gt_root = np.zeros((n_frames, n_people, 3))
+    gt_euler = np.zeros((n_frames, n_people, 18, 3))
+    for f in range(n_frames):
+        if f > 0:
+            euler = (euler + rng.normal(0, 0.02, size=euler.shape)).clip(-0.8, 0.8)
+            euler[:, LEAF_JOINTS] = 0.0
+            vel = (vel + rng.normal(0, 0.05, size=vel.shape))
+            sp = np.linalg.norm(vel, axis=1, keepdims=True)
+            vel = np.where(sp > 1.5, vel * 1.5 / np.maximum(sp, 1e-9), vel)
+            root[:, :2] = (root[:, :2] + vel / fps).clip(-floor / 2, floor / 2)
+        J = fk_batch(root, euler, scale)  # (N,18,3)
+        gt_joints[f] = J
+        gt_root[f] = root
+        gt_euler[f] = euler
+        # 3D points behind the 25 BODY_25 slots
+        X = np.zeros((n_people, 25, 3))
+        has = np.zeros(25, dtype=bool)
+        for b25, b18 in _B25_FROM_B18.items():
+            X[:, b25] = J[:, b18]
+            has[b25] = True
+        ear_axis = J[:, 16] - J[:, 17]
+        ear_axis /= np.maximum(np.linalg.norm(ear_axis, axis=1, keepdims=True), 1e-9)
+        X[:, 16] = J[:, 15] + 0.03 * ear_axis  # L eye
+        X[:, 15] = J[:, 15] - 0.03 * ear_axis  # R eye
+        has[[15, 16]] = True
+        Xh = np.concatenate([X, np.ones((n_people, 25, 1))], -1)
+        for v in range(n_views):
+            uvw = Xh @ P[v].T
+            z = uvw[..., 2]
+            uv = uvw[..., :2] / np.where(np.abs(z) < 1e-9, 1e-9, z)[..., None]
+            uv = uv + rng.normal(0, noise_px, size=uv.shape)
+            score = rng.uniform(0.6, 0.95, size=(n_people, 25))
+            ok = has[None, :] & (z > 0.3) & (uv[..., 0] >= 0) & (uv[..., 0] < W) & (uv[..., 1] >= 0) & (uv[..., 1] < H)
+            ok &= rng.uniform(size=ok.shape) >= p_joint_drop
+            det = np.concatenate([uv, score[..., None]], -1) * ok[..., None]
+            seen = (ok[:, BODY25_TO_COCO].sum(1) >= 6) & (rng.uniform(size=n_people) >= p_person_miss)
+            ids = np.nonzero(seen)[0]
+            ids = rng.permutation(ids)[:Pm]
+            n_pose[f, v] = len(ids)
+            kps25[f, v, :len(ids)] = det[ids]
+            gt_person[f, v, :len(ids)] = ids
+    return dict(kps25=kps25, n_pose=n_pose, K=Ks, RT=RTs, img_wh=np.array([img_wh] * n_views, dtype=np.int32),
+                gt_person=gt_person, gt_joints=gt_joints, gt_root=gt_root, gt_euler=gt_euler, gt_scale=scale)
+
+
+def make_batch(n_clips, n_views, n_people, n_frames, seed=1000, max_poses=None, **kw):
+    """B clips stacked for the clip-batch pipeline: kps [F,B,C,Pmax,17,3] COCO, n_pose [F,B,C], K [B,C,3,3],
+    RT [B,C,3,4]."""
+    clips = [make_clip(n_views, n_people, n_frames, seed, clip_idx=i, max_poses=max_poses, **kw) for i in range(n_clips)]
+    kps = np.stack([body25_to_coco(c["kps25"]) for c in clips], 1)
+    n_pose = np.stack([c["n_pose"] for c in clips], 1)
+    return dict(kps=np.ascontiguousarray(kps), n_pose=np.ascontiguousarray(n_pose), K=np.stack([c["K"] for c in clips]),
+                RT=np.stack([c["RT"] for c in clips]), clips=clips)
