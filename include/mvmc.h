@@ -39,7 +39,7 @@ extern "C" {
 #define MVMC_N_COCO 17
 #define MVMC_N_B18 18
 #define MVMC_N_PARAM 68
-#define MVMC_MAX_SEL 8          /* 2D poses that can feed one IK solve */
+#define MVMC_MAX_SEL 16         /* 2D poses that can feed one IK solve (no-track frames may group >1 pose per view) */
 
 int mvmc_version(void);
 const char* mvmc_error_string(int code);

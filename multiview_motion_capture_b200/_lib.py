@@ -8,7 +8,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmvmc.so")
 
-MAX_VIEWS, MAX_POSES, MAX_TRACKS, N_COCO, N_B18, N_PARAM, MAX_SEL = 8, 32, 64, 17, 18, 68, 8
+MAX_VIEWS, MAX_POSES, MAX_TRACKS, N_COCO, N_B18, N_PARAM, MAX_SEL = 8, 32, 64, 17, 18, 68, 16
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 
 

@@ -1,4 +1,4 @@
-"""Builds libmvmc.so (the sm_100a CUDA kernels + C-ABI) in-tree with nvcc, and the oracle's C pieces.
+"""Builds libmvmc.so (the sm_100a CUDA kernels + C-ABI) in-tree with nvcc.
 
     python -m multiview_motion_capture_b200.build          # build if stale
 """
@@ -54,18 +54,6 @@ def build_cuda(force=False, verbose=True):
     if force or jobs or _stale(LIB, objs):
         run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
     return LIB
-
-
-def build_emulator(verbose=False):
-    """TEST INFRASTRUCTURE: the CPU kernel-emulator build used by the `-m "not gpu"` tier."""
-    script = os.path.join(ROOT, "tests", "emu", "build_emu.sh")
-    out = os.path.join(ROOT, "tests", "emu", "libmvmc_emu.so")
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "mvmc_common.cuh"),
-                                                        os.path.join(ROOT, "include", "mvmc.h"),
-                                                        os.path.join(ROOT, "tests", "emu", "cuda_emu.h")]
-    if _stale(out, deps):
-        subprocess.run(["bash", script], check=True, stdout=None if verbose else subprocess.DEVNULL)
-    return out
 
 
 if __name__ == "__main__":

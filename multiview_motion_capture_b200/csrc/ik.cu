@@ -148,7 +148,7 @@ struct TriResidual {  // mv_math_util.py:190-202
 // ---- shared-memory plan of one solver CTA ----
 constexpr int TRF_NMAX = 68;
 constexpr int TRF_LD = 69;
-constexpr int TRF_MMAX = 256;
+constexpr int TRF_MMAX = 512;  // 32 residuals per 2D pose x MVMC_MAX_SEL
 constexpr int TRF_CH = 32;  // rows of J per chunk when forming J J^T
 
 struct TrfShared {

@@ -1,0 +1,54 @@
+"""Device-agnostic replay of a golden scene through the clip-batch pipeline (mvmc_clips_*), teacher-forced (track
+table taken from the reference before every frame) or free-running. Used by the GPU tier on full scenes and by the
+CPU tier (kernel emulator) on a couple of frames."""
+import numpy as np
+
+import mvmc_oracle as o
+from helpers import GoldenTable, fkey, golden, pad_poses
+
+
+def run_golden_clip(dev, name, Pmax, Tmax, forced, B=1, max_new=8, frames=None):
+    from multiview_motion_capture_b200.clips import ClipBatch
+    inp, g = golden(name)
+    kps = o.body25_to_coco(inp["kps25"])
+    C = kps.shape[1]
+    cb = ClipBatch(B, C, Pmax, max_tracks=Tmax, max_new=max_new, device=dev)
+    cb.set_calib(np.repeat(inp["K"][None], B, 0), np.repeat(inp["RT"][None], B, 0))
+    tab = GoldenTable(g)
+    st = dict(frames=0, xbin=0, iters=0, alive=0, upd=0, matches=0, dj=[], replicas=0)
+    for f in (frames or range(int(g["first_frame"]), int(g["last_frame"]) + 1)):
+        k = fkey(f)
+        if forced:
+            cb.set_tracks(**tab.packed(f, B, Tmax))
+        recs = cb.step(np.repeat(pad_poses(kps[f], Pmax)[None], B, 0), np.repeat(inp["n_pose"][f][None], B, 0), f)
+        rec = recs[0].copy()
+        dst, sim, xb, dg = cb.read_matrices(0)
+        n_alive = int(rec["n_alive"])
+        tr = rec["tracks"][:n_alive]
+        upd = tr[tr["updated"] > 0]
+        st["frames"] += 1
+        same_x = xb.shape == g[k + "xbin"].shape and np.array_equal(xb, g[k + "xbin"].astype(bool))
+        st["xbin"] += int(same_x)
+        st["iters"] += int(rec["als_iters"] == int(g[k + "als_iters"]))
+        st["alive"] += int(tr["track_id"].tolist() == g[k + "alive_after"].tolist())
+        same_upd = upd["track_id"].tolist() == g[k + "upd_ids"].tolist()
+        st["upd"] += int(same_upd)
+        if forced:
+            assert same_x, (name, f, "X_bin")
+            assert rec["n_dup_view"] == int(g[k + "printed"])
+            assert tr["track_id"].tolist() == g[k + "alive_after"].tolist(), (name, f, "track ids")
+            state = np.stack([tr["state"], tr["hits"], tr["time_since_update"], tr["length"]], 1).reshape(-1, 4)
+            assert np.array_equal(state, g[k + "alive_state"]), (name, f, "lifecycle counters")
+            assert same_upd, (name, f)
+            # the (view, pose) pairs each updated track was solved from
+            for u, t in enumerate(upd):
+                views = sorted(int(v) for v in t["sel"][:t["n_sel"], 0])
+                assert views == np.nonzero(g[k + "upd_views"][u])[0].tolist(), (name, f, u)
+        if same_upd and len(upd):
+            st["dj"].extend(np.abs(upd["joints"].reshape(-1, 18, 3) - g[k + "upd_joints"]).max(axis=(1, 2)).tolist())
+        if B > 1:
+            st["replicas"] += int(all(recs[b].tobytes() == recs[0].tobytes() for b in range(1, B)))
+    cb.close()
+    return st
+
+

@@ -1,0 +1,340 @@
+"""Device-agnostic parity checks of every C-ABI stage against the oracle / the reference goldens.
+
+The same functions run in two tiers:
+  * `-m "not gpu"`: through tests/emu (the real kernel sources compiled for the CPU emulator), tiny subsets;
+  * `-m gpu`: through libmvmc.so on the B200, full sets.
+Tolerances (BASELINE.json north_star): association bit-exact, triangulation <= 1 mm, IK see test_*_ik."""
+import numpy as np
+import torch
+
+import mvmc_oracle as o
+from helpers import GoldenTable, fkey, golden, golden_matches, pad_poses, view_lists
+
+from multiview_motion_capture_b200 import stages as S
+from multiview_motion_capture_b200._lib import MAX_SEL
+
+f64, i32 = torch.float64, torch.int32
+
+
+def T(x, dev, dt=f64):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dt).to(dev).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------
+def check_fundamental(dev):
+    for name in ("shelf", "synth_c8p6"):
+        inp, _ = golden(name)
+        K, RT = inp["K"], inp["RT"]
+        Ps = np.array(o.projections(K, RT))
+        C = len(Ps)
+        F = S.fundamental(T(Ps[None], dev)).cpu().numpy()[0]
+        F32 = S.fundamental_krt(T(K[None], dev), T(RT[None], dev)).cpu().numpy()[0]
+        ref32 = o.pairwise_f_mats_krt(K, RT)
+        scale = np.abs(F).max()  # F[i,i] is pure rounding noise of LAPACK's det in the reference
+        for i in range(C):
+            for j in range(C):
+                ref = o.fundamental_from_projections(Ps[i], Ps[j])
+                assert np.abs(F[i, j] - ref).max() <= 1e-11 * scale, (name, i, j)
+                if i != j:
+                    assert np.abs(F32[i, j] - ref32[i, j]).max() <= 2e-6 * np.abs(ref32[i, j]).max(), (name, i, j)
+
+
+# ---------------------------------------------------------------------------------------------------
+def _forced_inputs(name, f, Pmax, Tmax, tab):
+    inp, g = golden(name)
+    kps = o.body25_to_coco(inp["kps25"])
+    tj = tab.joints(f)
+    n = len(tj)
+    assert n <= Tmax
+    trk = np.zeros((1, Tmax, 18, 3))
+    for i, j in enumerate(tj):
+        trk[0, i] = j.reshape(18, 3)
+    return pad_poses(kps[f], Pmax)[None], inp["n_pose"][f][None].astype(np.int32), np.array([n], np.int32), trk
+
+
+def check_affinity(dev, name, frames, Pmax=8, Tmax=24):
+    """prepare + affinity with the reference's own track poses: kept poses and index layout identical,
+    dst <= 1e-7 px, sim <= 1e-6 (1.2e-7 is the float32 rounding of the no-track path)."""
+    inp, g = golden(name)
+    Ps = np.array(o.projections(inp["K"], inp["RT"]))
+    C = len(Ps)
+    P = T(Ps[None], dev)
+    F = S.fundamental(P)
+    F32 = S.fundamental_krt(T(inp["K"][None], dev), T(inp["RT"][None], dev))
+    tab = GoldenTable(g)
+    worst = 0.0
+    for f in frames:
+        k = fkey(f)
+        kps, n_pose, n_trk, trk = _forced_inputs(name, f, Pmax, Tmax, tab)
+        prep = S.prepare(T(kps, dev), T(n_pose, dev, i32), T(n_trk, dev, i32), Tmax)
+        keep = prep["keep"].cpu().numpy()[0][:, :g[k + "kept"].shape[1]]
+        assert np.array_equal(keep, g[k + "kept"]), (name, f)
+        dg = prep["dim_groups"].cpu().numpy()[0]
+        gd = g[k + "dim_groups"]
+        if n_trk[0] > 0:
+            assert np.array_equal(dg, gd), (name, f, dg, gd)
+        else:  # the no-track path has no (empty) track group in the reference's dim_groups
+            assert np.array_equal(dg[1:], gd), (name, f, dg, gd)
+        dst, sim = S.affinity(T(kps, dev), P, F, F32, T(trk, dev), T(n_trk, dev, i32), prep)
+        n = int(dg[-1])
+        dst = dst.cpu().numpy()[0][:n, :n]
+        sim = sim.cpu().numpy()[0][:n, :n]
+        assert dst.shape == g[k + "dst"].shape
+        dd = np.abs(dst - g[k + "dst"]).max()
+        ds = np.abs(sim - g[k + "sim"].astype(np.float64)).max()
+        worst = max(worst, dd)
+        assert dd <= 1e-7 and ds <= 1e-6, (name, f, dd, ds)
+    return worst
+
+
+# ---------------------------------------------------------------------------------------------------
+def _als_problem(g, f, N, Gp1):
+    k = fkey(f)
+    sim = np.asarray(g[k + "sim"])
+    n = sim.shape[0]
+    W = np.zeros((N, N))
+    W[:n, :n] = sim.astype(np.float64)
+    dg = np.asarray(g[k + "dim_groups"], dtype=np.int32)
+    is32 = sim.dtype == np.float32
+    if len(dg) < Gp1:  # no-track frame: prepend the empty track group
+        dg = np.concatenate([[0], dg]).astype(np.int32)
+    assert len(dg) == Gp1
+    return W, dg, n, is32
+
+
+def check_als(dev, name, frames, N=64, rmax=48, exact_iters=True):
+    """match_als on the reference's own similarity matrices: X_bin bit-identical (and the stopping iteration)."""
+    inp, g = golden(name)
+    C = len(inp["K"])
+    probs = [_als_problem(g, f, N, C + 2) for f in frames]
+    sim = T(np.stack([p[0] for p in probs]), dev)
+    dg = T(np.stack([p[1] for p in probs]), dev, i32)
+    f32 = T(np.array([int(p[3]) for p in probs]), dev, i32)
+    xbin, n_iter = S.match_als(sim, dg, rmax, f32_first_iter=f32)
+    n_iter = n_iter.cpu().numpy()
+    same_it = 0
+    for b, f in enumerate(frames):
+        n = probs[b][2]
+        xb = S.unpack_xbin(xbin[b], n)
+        assert np.array_equal(xb, g[fkey(f) + "xbin"].astype(bool)), (name, f, "X_bin")
+        same_it += int(n_iter[b] == int(g[fkey(f) + "als_iters"]))
+        if exact_iters:
+            assert n_iter[b] == int(g[fkey(f) + "als_iters"]), (name, f, n_iter[b], int(g[fkey(f) + "als_iters"]))
+    return same_it
+
+
+# ---------------------------------------------------------------------------------------------------
+def _decode_assign(out, b, T_):
+    nsel = out["trk_nsel"][b]
+    trk = {}
+    for t in range(T_):
+        if nsel[t] >= 0:
+            trk[t] = [tuple(x) for x in out["trk_sel"][b, t, :nsel[t]].tolist()]
+    new = [[tuple(x) for x in out["new_sel"][b, k, :out["new_nsel"][b, k]].tolist()] for k in range(out["new_n"][b])]
+    return trk, new
+
+
+def check_assign(dev, name, frames, Pmax=8, Tmax=24, max_new=16):
+    """closure quirk + parse + decode from the reference's own X_bin: matches identical to the reference."""
+    inp, g = golden(name)
+    kpsall = o.body25_to_coco(inp["kps25"])
+    C = len(inp["K"])
+    N = Tmax + C * Pmax
+    NW = (N + 31) // 32
+    B = len(frames)
+    xb = np.zeros((B, N, NW * 32), dtype=np.uint8)
+    kps = np.zeros((B, C, Pmax, 17, 3))
+    n_pose = np.zeros((B, C), np.int32)
+    n_trk = np.zeros(B, np.int32)
+    for b, f in enumerate(frames):
+        k = fkey(f)
+        x = g[k + "xbin"]
+        xb[b, :x.shape[0], :x.shape[0]] = x
+        kps[b] = pad_poses(kpsall[f], Pmax)
+        n_pose[b] = inp["n_pose"][f]
+        n_trk[b] = len(g[k + "alive_before"])
+    words = (xb.reshape(B, N, NW, 32).astype(np.uint32) << np.arange(32, dtype=np.uint32)).sum(-1).astype(np.uint32)
+    prep = S.prepare(T(kps, dev), T(n_pose, dev, i32), T(n_trk, dev, i32), Tmax)
+    out = S.assign(T(words.view(np.int32), dev, i32), prep, T(n_trk, dev, i32), C, max_new)
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    assert (out["err"] == 0).all()
+    for b, f in enumerate(frames):
+        trk, new = _decode_assign(out, b, int(n_trk[b]))
+        tm, ng = golden_matches(g, f)
+        assert trk == tm, (name, f, trk, tm)
+        assert new == ng, (name, f, new, ng)
+        assert out["n_dup"][b] == int(g[fkey(f) + "printed"]), (name, f)
+
+
+# ---------------------------------------------------------------------------------------------------
+def check_triangulate(dev, name, limit=None):
+    """DLT (+ the 2-nfev refine) on every triangulation call the reference made: <= 1e-6 m (spec: 1 mm)."""
+    _, g = golden(name)
+    n = int(g["tri_count"])
+    idx = list(range(n))[:limit]
+    V = MAX_SEL
+    obs = np.zeros((len(idx), V, 18, 3))
+    Ps = np.zeros((len(idx), V, 3, 4))
+    nv = np.zeros(len(idx), np.int32)
+    for q, i in enumerate(idx):
+        P, pts = g[f"tri{i}_P"], g[f"tri{i}_pts"]
+        nv[q] = len(P)
+        obs[q, :len(P)] = pts
+        Ps[q, :len(P)] = P
+    lin = S.triangulate(T(obs, dev), T(Ps, dev), T(nv, dev, i32), 0.01, 0).cpu().numpy()
+    out = S.triangulate(T(obs, dev), T(Ps, dev), T(nv, dev, i32), 0.01, 2).cpu().numpy()
+    worst = 0.0
+    for q, i in enumerate(idx):
+        d0 = np.abs(lin[q] - g[f"tri{i}_linear"]).max()
+        d1 = np.abs(out[q] - g[f"tri{i}_out"]).max()
+        worst = max(worst, d0, d1)
+        assert d0 <= 1e-6 and d1 <= 1e-6, (name, i, d0, d1)
+    return worst
+
+
+# ---------------------------------------------------------------------------------------------------
+def check_fk(dev, M=64, seed=0):
+    """FK kernel vs the oracle: <= 1e-12 m; generic chain kernel vs chain_fk on the CMU-31 topology."""
+    rng = np.random.default_rng(seed)
+    skel = o.load_skeleton()
+    x = np.zeros((M, 68))
+    x[:, :3] = rng.normal(0, 2, (M, 3))
+    x[:, 3:57] = rng.uniform(-1.5, 1.5, (M, 54))
+    x[:, 57:] = skel.side_bone_lens * rng.uniform(0.8, 1.2, (M, 11))
+    J = S.fk(T(x, dev)).cpu().numpy()
+    for m in range(M):
+        ref, _ = o.forward_kinematics(skel, x[m, :3], x[m, 3:57].reshape(18, 3), x[m, 57:])
+        assert np.abs(J[m] - ref).max() <= 1e-12, m
+    # CMU skeleton (skeleton_CMU.yml topology: 31 joints)
+    parents = np.array([-1, 0, 1, 2, 3, 4, 0, 6, 7, 8, 9, 0, 11, 12, 13, 14, 15, 13, 17, 18, 19, 20, 21, 20, 13, 24, 25, 26,
+                        27, 28, 27], np.int32)
+    Jn = len(parents)
+    offs = rng.normal(0, 0.2, (Jn, 3))
+    from scipy.spatial.transform import Rotation
+    rot = Rotation.random(M * Jn, random_state=1).as_matrix().reshape(M, Jn, 3, 3)
+    root = rng.normal(0, 1, (M, 3))
+    got = S.fk_chain(T(rot, dev), T(offs, dev), T(parents, dev, i32), T(root, dev)).cpu().numpy()
+    for m in range(0, M, 7):
+        ref = o.chain_fk(offs, parents, rot[m], root[m])
+        assert np.abs(got[m] - ref).max() <= 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------
+def ik_problems(name, frames):
+    """Teacher-forced IK updates: for every track the reference updated at frame f, its previous parameters (warm start),
+    the 2D poses / projections the reference used, and the reference's answer."""
+    inp, g = golden(name)
+    kps = o.body25_to_coco(inp["kps25"])
+    Ps = np.array(o.projections(inp["K"], inp["RT"]))
+    tab = GoldenTable(g)
+    out = []
+    for f in frames:
+        k = fkey(f)
+        ids_before = tab.seek(f)
+        tm, ng = golden_matches(g, f)
+        upd = g[k + "upd_ids"].tolist()
+        for t_idx, sel in tm.items():
+            if len(sel) < 2:
+                continue
+            tid = ids_before[t_idx]
+            u = upd.index(tid)
+            out.append(dict(frame=f, birth=False, x0=tab.table[tid]["param"].copy(), sel=sel,
+                            kps=np.array([kps[f, v, p] for v, p in sel]), P=np.array([Ps[v] for v, _ in sel]),
+                            x_ref=np.concatenate([g[k + "upd_root"][u], g[k + "upd_euler"][u].reshape(-1), g[k + "upd_blens"][u]]),
+                            j_ref=g[k + "upd_joints"][u]))
+        n_new = 0
+        born = [t for t in upd if t not in ids_before]
+        for sel in ng:
+            if len(sel) < 2:
+                continue
+            tid = born[n_new]
+            n_new += 1
+            u = upd.index(tid)
+            out.append(dict(frame=f, birth=True, x0=np.zeros(68), sel=sel,
+                            kps=np.array([kps[f, v, p] for v, p in sel]), P=np.array([Ps[v] for v, _ in sel]),
+                            x_ref=np.concatenate([g[k + "upd_root"][u], g[k + "upd_euler"][u].reshape(-1), g[k + "upd_blens"][u]]),
+                            j_ref=g[k + "upd_joints"][u]))
+    return out
+
+
+def run_ik(dev, probs, free_mask=None, max_nfev=None):
+    M, V = len(probs), MAX_SEL
+    kps = np.zeros((M, V, 17, 3))
+    Ps = np.zeros((M, V, 3, 4))
+    nv = np.zeros(M, np.int32)
+    x0 = np.zeros((M, 68))
+    birth = np.zeros(M, np.uint8)
+    nfev = np.zeros(M, np.int32)
+    for m, p in enumerate(probs):
+        v = len(p["sel"])
+        kps[m, :v], Ps[m, :v], nv[m], x0[m], birth[m] = p["kps"], p["P"], v, p["x0"], int(p["birth"])
+        nfev[m] = (50 if p["birth"] else 5) if max_nfev is None else max_nfev
+    fm = T(free_mask, dev, torch.uint8) if free_mask is not None else None
+    x, joints, info, cost = S.ik_solve(T(kps, dev), T(Ps, dev), T(nv, dev, i32), T(x0, dev), T(birth, dev, torch.uint8),
+                                       T(nfev, dev, i32), fm)
+    return x.cpu().numpy(), joints.cpu().numpy(), info.cpu().numpy(), cost.cpu().numpy()
+
+
+LEAF_PARAM_MASK = np.ones(68, np.uint8)
+for _j in (3, 6, 11, 14, 16, 17):  # leaf joints' Euler angles are structurally unobservable
+    LEAF_PARAM_MASK[3 + 3 * _j: 6 + 3 * _j] = 0
+
+
+def oracle_ik(p, max_nfev, free=None):
+    """The oracle's solve for problem p with an optional free-parameter subset (same two-stage structure)."""
+    skel = o.load_skeleton()
+    obs = np.array([o.add_mid_spine(k) for k in p["kps"]])[:, o.IK_OBS_IDX, :]
+    Ps = list(p["P"])
+    x = p["x0"].copy()
+    res = []
+    for stage, npar in ((0, 57), (1, 68)):
+        act = np.array([i for i in range(npar) if free is None or free[i]])
+        lens_fixed = x[57:].copy()
+
+        def fun(z, act=act, npar=npar, lens_fixed=lens_fixed, base=x.copy()):
+            y = base.copy()
+            y[act] = z
+            return o._reproj_residual(skel, obs, Ps, y[:3], y[3:57].reshape(18, 3), y[57:] if npar == 68 else lens_fixed)
+
+        r = o.trf_least_squares(fun, x[act].copy(), max_nfev)
+        x[act] = r.x
+        res.append(r)
+    joints, _ = o.forward_kinematics(skel, x[:3], x[3:57].reshape(18, 3), x[57:])
+    return x, joints, res
+
+
+def well_posed_mask(p, rel=2e-3):
+    """Free-parameter mask [68] keeping only parameters the observations of problem p determine well: QR with column
+    pivoting on the oracle's forward-difference Jacobian at x0, columns with |R_ii| > rel |R_00|. On this subset the
+    trust-region trajectory is stable (no bifurcation, SURVEY.md §8c'), so the kernel can be held to the literal
+    north_star tolerance (1e-3 rad, 1 mm) against the oracle's restated SciPy TRF."""
+    import scipy.linalg as sl
+    skel = o.load_skeleton()
+    obs = np.array([o.add_mid_spine(k) for k in p["kps"]])[:, o.IK_OBS_IDX, :]
+    fun = lambda x: o._reproj_residual(skel, obs, list(p["P"]), x[:3], x[3:57].reshape(18, 3), x[57:])
+    x0 = p["x0"]
+    J = o.fd_jacobian(fun, x0, fun(x0))
+    _, R, piv = sl.qr(J, pivoting=True, mode="economic")
+    d = np.abs(np.diag(R))
+    mask = np.zeros(68, np.uint8)
+    mask[piv[d > rel * d[0]]] = 1
+    return mask
+
+
+def check_ik_well_posed(dev, probs, nfevs=(5, 30)):
+    """Kernel TRF == oracle TRF (== SciPy, test_oracle_golden) on well-posed subsets: identical (nfev, njev, status),
+    angles <= 1e-3 rad (measured ~1e-6), joints <= 1e-5 m."""
+    worst = (0.0, 0.0)
+    for p in probs:
+        mask = well_posed_mask(p)
+        for nf in nfevs:
+            x, joints, info, cost = run_ik(dev, [p], free_mask=mask, max_nfev=nf)
+            xr, jr, res = oracle_ik(p, nf, free=mask)
+            got = [tuple(info[0, s, :3].tolist()) for s in range(2)]
+            ref = [(r.nfev, r.njev, r.status) for r in res]
+            assert got == ref, (p["frame"], nf, got, ref)
+            da, dj = np.abs(x[0] - xr).max(), np.abs(joints[0] - jr).max()
+            assert da <= 1e-3 and dj <= 1e-5, (p["frame"], nf, da, dj)
+            assert abs(cost[0, 1] - res[1].cost) <= 1e-6 * max(1.0, res[1].cost)
+            worst = (max(worst[0], da), max(worst[1], dj))
+    return worst

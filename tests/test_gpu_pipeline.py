@@ -1,0 +1,117 @@
+"""GPU tier: the clip-batch pipeline (mvmc_clips_*) — association + IK + track lifecycle on the device — against
+the reference goldens, teacher-forced and free-running, plus size-independent properties at BASELINE sizes."""
+import numpy as np
+import pytest
+
+import mvmc_oracle as o
+from helpers import GoldenTable, fkey, golden, golden_matches, pad_poses
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+from pipeline_checks import run_golden_clip as _run_dev
+
+
+def _run(name, Pmax, Tmax, forced, B=1, max_new=8):
+    return _run_dev(DEV, name, Pmax, Tmax, forced, B=B, max_new=max_new)
+
+
+def test_shelf_teacher_forced_300_frames_identical_tracking(cuda):
+    """All 300 Shelf frames, track table taken from the reference before every frame: X_bin, ALS iteration
+    count, matches, births/deaths, track ids and lifecycle counters all identical to the reference."""
+    st = _run("shelf", 8, 24, forced=True)
+    dj = np.array(st["dj"])
+    print(f"shelf forced: {st}"[:200], f"joints vs reference: median {np.median(dj)*1e3:.2f} mm p90 {np.percentile(dj,90)*1e3:.2f} mm")
+    assert st["xbin"] == st["alive"] == st["upd"] == st["frames"] == 300
+    assert st["iters"] == 300
+    assert np.median(dj) <= 3e-3
+
+
+@pytest.mark.parametrize("name,Pmax,Tmax", [("synth_c4p3", 4, 8), ("synth_c8p6", 8, 12), ("synth_c8p12", 12, 16)])
+def test_synthetic_teacher_forced(cuda, name, Pmax, Tmax):
+    st = _run(name, Pmax, Tmax, forced=True, max_new=Pmax)
+    assert st["xbin"] == st["alive"] == st["upd"] == st["frames"]
+
+
+def test_shelf_free_running(cuda):
+    """Free-running (our own IK output feeds the next association). The reference's IK is chaotic at the 1-ulp level
+    (SURVEY.md 8c'), so identical tracking is not guaranteed; report the identical-frame rate, require the first
+    frames (before the chaos can leak into a discrete decision) and a majority overall."""
+    st = _run("shelf", 8, 24, forced=False, B=3)
+    print("shelf free-running identical-frame rates:", {k: v for k, v in st.items() if k != "dj"})
+    assert st["replicas"] == st["frames"]          # bit-deterministic across CTAs / replicas
+    assert st["xbin"] >= 0.7 * st["frames"]
+    assert st["alive"] >= 0.5 * st["frames"]
+
+
+def test_birth_joints_match_reference(cuda):
+    """Frame 1 of every golden scene: tracks are born from triangulation + 50-nfev IK; well inside 1 cm of the reference
+    (birth solves converge: status 2), ids in creation order."""
+    from multiview_motion_capture_b200.clips import ClipBatch
+    for name, Pmax, Tmax in [("shelf", 8, 24), ("synth_c4p3", 4, 8), ("synth_c8p6", 8, 12)]:
+        inp, g = golden(name)
+        kps = o.body25_to_coco(inp["kps25"])
+        C = kps.shape[1]
+        cb = ClipBatch(1, C, Pmax, max_tracks=Tmax, max_new=Pmax, device=DEV)
+        cb.set_calib(inp["K"][None], inp["RT"][None])
+        rec = cb.step(pad_poses(kps[1], Pmax)[None], inp["n_pose"][1][None], 1)[0].copy()
+        k = fkey(1)
+        n = int(rec["n_alive"])
+        assert rec["tracks"]["track_id"][:n].tolist() == g[k + "alive_after"].tolist()
+        dj = np.abs(rec["tracks"]["joints"][:n].reshape(-1, 18, 3) - g[k + "upd_joints"]).max(axis=(1, 2))
+        print(name, "birth joints vs reference (m):", dj)
+        assert np.median(dj) <= 1e-2
+        cb.close()
+
+
+def test_full_size_properties_8x32(cuda):
+    """BASELINE shape (8 cameras x 32 people), 6 clips x 6 frames, no oracle (it needs ~1 min/frame there):
+    replicated clips give bit-identical records; the assignment groups are pure w.r.t. the generator's ground-truth
+    person ids; track ids are handed out in creation order; FK(params) == joints; every IK solve lowers its cost."""
+    import torch
+    from multiview_motion_capture_b200 import stages as S, synthetic as syn
+    from multiview_motion_capture_b200.clips import ClipBatch
+    nF = 6
+    clips = [syn.make_clip(8, 32, nF + 1, seed=77, clip_idx=i) for i in range(3)]
+    B = 6
+    idx = [0, 1, 2, 0, 1, 2]
+    kps = np.stack([syn.body25_to_coco(clips[i]["kps25"]) for i in idx], 1)
+    n_pose = np.stack([clips[i]["n_pose"] for i in idx], 1)
+    cb = ClipBatch(B, 8, 32, max_tracks=48, max_new=32, device=DEV)
+    cb.set_calib(np.stack([clips[i]["K"] for i in idx]), np.stack([clips[i]["RT"] for i in idx]))
+    seen_ids = [set() for _ in range(B)]
+    for f in range(1, nF + 1):
+        recs = cb.step(kps[f], n_pose[f], f).copy()
+        assert (recs["error"] == 0).all()
+        for b in range(3):
+            assert recs[b].tobytes() == recs[b + 3].tobytes(), (f, b, "replica differs")
+        for b in range(3):
+            rec = recs[b]
+            n = int(rec["n_alive"])
+            tr = rec["tracks"][:n]
+            assert 24 <= n <= 40, (f, b, n)
+            ids = tr["track_id"].tolist()
+            assert ids == sorted(ids) and len(set(ids)) == n
+            new = [i for i, u in zip(ids, tr["updated"]) if u == 2]
+            assert all(i > max(seen_ids[b], default=-1) for i in new)
+            seen_ids[b].update(ids)
+            gt = clips[b]["gt_person"][f]
+            pure = 0
+            for t in tr[tr["updated"] > 0]:
+                who = {int(gt[v, p]) for v, p in t["sel"][:t["n_sel"]]}
+                pure += int(len(who) == 1)
+                assert t["n_sel"] >= 2
+            assert pure >= 0.9 * (tr["updated"] > 0).sum(), (f, b, pure)
+            upd = tr[tr["updated"] > 0]
+            j = S.fk(torch.as_tensor(upd["param"].copy(), device=DEV)).cpu().numpy()
+            assert np.abs(j.reshape(len(upd), 54) - upd["joints"]).max() <= 1e-12
+            assert (upd["cost"][:, 1] <= upd["cost"][:, 0] * (1 + 1e-12)).all()
+            assert np.isfinite(upd["param"]).all()
+            # joints close to the generator's ground truth (noise 2 px at ~6 m => a few cm)
+            if f >= 3:
+                gtj = clips[b]["gt_joints"][f]
+                err = [np.abs(t["joints"].reshape(18, 3)[1:15] - gtj[int(gt[t["sel"][0, 0], t["sel"][0, 1]])][1:15]).max()
+                       for t in upd]
+                assert np.median(err) < 0.15, (f, b, np.median(err))
+    cb.close()

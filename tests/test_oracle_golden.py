@@ -1,0 +1,166 @@
+"""Pins the oracle (oracle/mvmc_oracle.py) against outputs of the REAL reference recorded in
+tests/golden/*_ref.npz by oracle/make_golden.py (the reference ships no test vectors).
+Everything here is bit-exact: the oracle restates the reference's operation order."""
+import numpy as np
+import pytest
+
+import mvmc_oracle as o
+from helpers import GoldenTable, fkey, golden, golden_matches, view_lists
+
+SYNTH = ["synth_c4p3", "synth_c8p6", "synth_c8p12"]
+
+
+def _free_run(name, last):
+    inp, g = golden(name)
+    kps = o.body25_to_coco(inp["kps25"])
+    trk = o.Tracker(o.projections(inp["K"], inp["RT"]), inp["K"], inp["RT"])
+    for f in range(int(g["first_frame"]), last + 1):
+        k = fkey(f)
+        a = trk.step(f, kps[f], inp["n_pose"][f])
+        assert a.dst.shape == g[k + "dst"].shape
+        assert np.array_equal(a.dst, g[k + "dst"]), f"{name} frame {f}: dst"
+        assert np.array_equal(a.sim, g[k + "sim"].astype(np.float64)), f"{name} frame {f}: sim"
+        assert a.n_iter == int(g[k + "als_iters"]), f"{name} frame {f}: ALS iterations"
+        assert np.array_equal(a.x_bin, g[k + "xbin"].astype(bool)), f"{name} frame {f}: X_bin"
+        tm, ng = golden_matches(g, f)
+        assert a.track_matches == tm, f"{name} frame {f}: spatial_time_matches"
+        assert a.new_groups == ng, f"{name} frame {f}: spatial_matches"
+        assert a.n_dup_view == int(g[k + "printed"])
+        assert [t.track_id for t in trk.tracks] == g[k + "alive_after"].tolist(), f"{name} frame {f}: track ids"
+        st = np.array([[t.state, t.hits, t.time_since_update, len(t)] for t in trk.tracks]).reshape(-1, 4)
+        assert np.array_equal(st, g[k + "alive_state"])
+        upd = [t for t in trk.tracks if t.frame_idxs[-1] == f]
+        assert [t.track_id for t in upd] == g[k + "upd_ids"].tolist()
+        for i, t in enumerate(upd):
+            assert np.array_equal(t.params[-1].root, g[k + "upd_root"][i])
+            assert np.array_equal(t.params[-1].euler, g[k + "upd_euler"][i])
+            assert np.array_equal(t.params[-1].bone_lens, g[k + "upd_blens"][i])
+            assert np.array_equal(t.joints[-1], g[k + "upd_joints"][i])
+        # every least_squares call of the frame: same trajectory length and status
+        meta = g[k + "solve_meta"]
+        log = [e for e in trk.solve_log if e[0] in ("ik1", "ik2")]
+        ik_meta = meta[meta[:, 0] == 0]
+        assert len(log) == len(ik_meta)
+        for e, m in zip(log, ik_meta):
+            assert (e[2].nfev, e[2].njev, e[2].status) == (int(m[3]), int(m[4]), int(m[5]))
+    return trk, g
+
+
+def test_shelf_free_running_bit_exact():
+    """Frames 1..40 of the Shelf fixture, free-running (the oracle's own tracks feed the next frame)."""
+    _free_run("shelf", 40)
+
+
+@pytest.mark.parametrize("name", SYNTH)
+def test_synthetic_free_running_bit_exact(name):
+    _, g = golden(name)
+    trk, g = _free_run(name, int(g["last_frame"]))
+    final = trk.finish()
+    assert [t.track_id for t in final] == g["final_ids"].tolist()
+    assert [len(t) for t in final] == g["final_len"].tolist()
+    assert [t.frame_idxs[0] for t in final] == g["final_first_frame"].tolist()
+
+
+def test_shelf_association_teacher_forced_all_frames():
+    """Association only (no IK) on all 300 Shelf frames with the reference's own track poses."""
+    inp, g = golden("shelf")
+    kps = o.body25_to_coco(inp["kps25"])
+    Ps = o.projections(inp["K"], inp["RT"])
+    tab = GoldenTable(g)
+    for f in range(1, int(g["last_frame"]) + 1):
+        k = fkey(f)
+        ids, arr = view_lists(kps[f], inp["n_pose"][f], g[k + "kept"])
+        a = o.associate(tab.joints(f), arr, ids, Ps, inp["K"], inp["RT"])
+        assert np.array_equal(a.dst, g[k + "dst"]), f
+        assert a.n_iter == int(g[k + "als_iters"]), f
+        assert np.array_equal(a.x_bin, g[k + "xbin"].astype(bool)), f
+        tm, ng = golden_matches(g, f)
+        assert a.track_matches == tm and a.new_groups == ng, f
+        mm = o.transform_closure(a.x_bin)
+        assert np.array_equal(mm, g[k + "match_mat"].astype(bool)), f
+
+
+@pytest.mark.parametrize("name", ["shelf"] + SYNTH)
+def test_triangulation_records(name):
+    """Every triangulate_point_groups_from_multiple_views_linear call the reference made (track births)."""
+    _, g = golden(name)
+    n = int(g["tri_count"])
+    assert n > 0
+    for i in range(min(n, 12)):
+        P, pts = g[f"tri{i}_P"], g[f"tri{i}_pts"]
+        lin = o.triangulate_groups(list(P), list(pts), 0.01, False)
+        assert np.array_equal(lin, g[f"tri{i}_linear"]), i
+        out = o.triangulate_groups(list(P), list(pts), 0.01, True)
+        assert np.array_equal(out, g[f"tri{i}_out"]), i
+
+
+def test_trf_matches_scipy_on_well_posed_problem():
+    """The restated TRF against scipy.optimize.least_squares itself where SciPy is stable (SURVEY §8c' item 3):
+    leaf/unobserved DOFs removed, noise-free observations, run to convergence."""
+    from scipy.optimize import least_squares
+    skel = o.load_skeleton()
+    rng = np.random.default_rng(5)
+    inp, _ = golden("synth_c8p6")
+    Ps = o.projections(inp["K"], inp["RT"])
+    euler = rng.normal(0, 0.2, size=(18, 3))
+    leaves = [3, 6, 11, 14, 16, 17]
+    euler[leaves] = 0
+    root = np.array([0.3, -0.2, 0.95])
+    pos, _ = o.forward_kinematics(skel, root, euler, skel.side_bone_lens)
+    obs = []
+    for P in Ps:
+        pr = P @ np.concatenate([pos[o.IK_SKEL_IDX], np.ones((16, 1))], 1).T
+        obs.append(np.concatenate([(pr[:2] / (1e-5 + pr[2])).T, np.ones((16, 1))], 1))
+    obs = np.array(obs)
+    free = np.array([i for i in range(57) if i < 3 or ((i - 3) // 3) not in leaves])
+
+    def fun(z):
+        x = np.zeros(57)
+        x[free] = z
+        return o._reproj_residual(skel, obs, Ps, x[:3], x[3:].reshape(-1, 3), skel.side_bone_lens)
+
+    z0 = np.zeros(len(free))
+    z0[:3] = root + 0.05
+    for nfev in (3, 8, 200):
+        ref = least_squares(fun, z0, max_nfev=nfev)
+        got = o.trf_least_squares(fun, z0, nfev)
+        assert (got.nfev, got.njev, got.status) == (ref.nfev, ref.njev, ref.status)
+        assert np.allclose(got.x, ref.x, rtol=0, atol=1e-9)
+        assert abs(got.cost - ref.cost) <= 1e-9 * max(1.0, ref.cost)
+
+
+def test_fk_against_scipy_rotation():
+    from scipy.spatial.transform import Rotation
+    skel = o.load_skeleton()
+    rng = np.random.default_rng(0)
+    e = rng.uniform(-1, 1, size=(18, 3))
+    R = o.euler_to_rotmats(e)
+    assert np.abs(R - Rotation.from_euler("XYZ", e).as_matrix()).max() < 1e-9  # 1e-10 axis guard, Quaternions.py:444
+    pos, glob = o.forward_kinematics(skel, np.array([1.0, 2.0, 3.0]), e, skel.side_bone_lens)
+    assert np.allclose(pos[0], [1, 2, 3])
+    for j in range(1, 18):
+        p = skel.parents[j]
+        assert abs(np.linalg.norm(pos[j] - pos[p]) - skel.side_bone_lens[skel.side_to_full[j]]) < 1e-8
+
+
+def test_closure_quirk_matches_reference_loop():
+    """transform_closure only closes through the LAST index (mv_association.py:105-110)."""
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 5, 13):
+        x = rng.uniform(size=(n, n)) > 0.6
+        x = x | x.T | np.eye(n, dtype=bool)
+        temp = np.zeros_like(x)
+        for k in range(n):          # the reference's triple loop, verbatim semantics
+            for i in range(n):
+                for j in range(n):
+                    temp[i][j] = x[i, j] or (x[i, k] and x[k, j])
+        vis = np.zeros(n)
+        mm = np.zeros_like(x)
+        for i in range(n):
+            if vis[i]:
+                continue
+            for j in range(n):
+                if temp[i][j]:
+                    vis[j] = 1
+                    mm[j, i] = 1
+        assert np.array_equal(o.transform_closure(x), mm)
