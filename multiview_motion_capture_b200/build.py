@@ -33,7 +33,7 @@ def _stale(target, deps):
 
 def build_cuda(force=False, verbose=True):
     os.makedirs(LIBDIR, exist_ok=True)
-    headers = [os.path.join(ROOT, "include", "mvmc.h"), os.path.join(CSRC, "mvmc_common.cuh")]
+    headers = [os.path.join(ROOT, "include", "mvmc.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     nvcc = _nvcc()
     objs = []
     jobs = []

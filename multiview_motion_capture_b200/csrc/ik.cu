@@ -1,17 +1,17 @@
-// Forward kinematics, DLT triangulation and the reprojection IK (trust-region-reflective least squares
-// with a forward-difference Jacobian) as sm_100a CUDA kernels.
+// Forward kinematics, DLT triangulation and the reprojection IK (trust-region-reflective least squares with a
+// forward-difference Jacobian) as sm_100a CUDA kernels.
 //
 // Reference rows: B1/B2 mv_math_util.py:152-240; I0 inverse_kinematics.py:339-348;
 // I1 inverse_kinematics.py:176-199 + Quaternions.py:97-115,335-366,442-462; I2/I3 :202-277;
 // I4 scipy.optimize.least_squares(method='trf', jac='2-point', tr_solver='exact') restated on device
-// (SURVEY.md §3.3); I5 :380-433; I6 kinematics.py:18-31.
+// (trf_warp.cuh); I5 :380-433; I6 kinematics.py:18-31.
 //
-// k_ik_solve: ONE CTA PER SOLVE. Lanes own Jacobian columns (one perturbed FK + reprojection each);
-// J (n x m) lives in an L2-resident global scratch row per parameter; J J^T (n x n, n <= 68) and its
-// eigenvectors live in shared memory and are diagonalised by a parallel cyclic Jacobi method
-// (round-robin ordering, one 2x2 block per thread). The trust-region sub-problem is solved from the
-// eigen-decomposition exactly as SciPy does from the SVD (s^2 = lambda, s*uf = V^T g).
-#include "mvmc_common.cuh"
+// k_ik_solve: ONE WARP (one 32-thread CTA) PER SOLVE, persistent CTAs pulling work slots from an atomic counter.
+// Lanes own Jacobian columns: each runs the fully unrolled BASIC_18 chain in registers on its own perturbed
+// parameter vector and parks the 16 observed joint positions in shared memory; the Jacobian is then produced
+// half a camera view at a time and folded into J^T J by 8x8 register tiles. 4 resident CTAs per SM (53 KB of
+// shared memory each); FP64 CUDA-core work throughout (no dense contraction large enough for tensor cores).
+#include "trf_warp.cuh"
 
 namespace mvmc {
 
@@ -21,23 +21,25 @@ struct SkelConst {
     int side_to_full[MVMC_N_B18];
     double dirs[MVMC_N_B18][3];
     double ref_side_lens[11];
+    unsigned char param_dead[MVMC_N_PARAM];   // 1: the parameter cannot move any joint (leaf rotations, root bone length)
 };
 __constant__ SkelConst c_skel;
-__constant__ int c_ik_skel_idx[MVMC_N_IKJ] = {1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17};
 __constant__ int c_ik_obs_idx[MVMC_N_IKJ] = {11, 13, 15, 12, 14, 16, 17, 5, 7, 9, 6, 8, 10, 0, 3, 4};
 
-#ifdef MVMC_EMU
-#define DMUL(a, b) ((a) * (b))
-#define DSUB(a, b) ((a) - (b))
-#define DDIV(a, b) ((a) / (b))
-#else
-#define DMUL(a, b) __dmul_rn((a), (b))
-#define DSUB(a, b) __dsub_rn((a), (b))
-#define DDIV(a, b) __ddiv_rn((a), (b))
-#endif
-
-constexpr double kSqrtEps = 1.4901161193847656e-08;   // sqrt(2^-52)
-constexpr double kEps = 2.220446049250313e-16;
+// compile-time copies of the topology for the unrolled chain (kept equal to ensure_skeleton()'s tables)
+struct Topo {
+    static __host__ __device__ constexpr int parent(int j) {
+        constexpr int p[MVMC_N_B18] = {-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 9, 10, 8, 12, 13, 8, 15, 15};
+        return p[j];
+    }
+    static __host__ __device__ constexpr int s2f(int j) {
+        constexpr int t[MVMC_N_B18] = {7, 0, 1, 2, 0, 1, 2, 8, 9, 3, 4, 5, 3, 4, 5, 10, 6, 6};
+        return t[j];
+    }
+    static __host__ __device__ constexpr bool leaf(int j) { return j == 3 || j == 6 || j == 11 || j == 14 || j == 16 || j == 17; }
+    // slot of skeleton joint j among the 16 joints the IK observes (skeleton idx 1..7, 9..17), -1 otherwise
+    static __host__ __device__ constexpr int ik_slot(int j) { return (j == 0 || j == 8) ? -1 : (j < 8 ? j - 1 : j - 2); }
+};
 
 // local rotation R = Rx(a) Ry(b) Rz(c) via half-angle quaternions, as Quaternions.from_euler + transforms
 __device__ __forceinline__ void euler_to_mat(double ea, double eb, double ec, double* m) {
@@ -69,7 +71,7 @@ __device__ __forceinline__ void euler_to_mat(double ea, double eb, double ec, do
     m[8] = 1.0 - (xx + yy);
 }
 
-// x = [root(3) | euler(54)], lens = 11 side lengths -> pos[18][3]
+// x = [root(3) | euler(54)], lens = 11 side lengths -> pos[18][3]   (generic, table driven; used by k_fk)
 __device__ void fk_b18(const double* x, const double* lens, double (*pos)[3]) {
     double R[MVMC_N_B18][9];
     for (int j = 0; j < MVMC_N_B18; j++) {
@@ -94,424 +96,180 @@ __device__ void fk_b18(const double* x, const double* lens, double (*pos)[3]) {
     }
 }
 
-// ---- residual functors. eval(x, emit) calls emit(row, value) for every residual row. ----
-struct IkResidual {
+// The same chain fully unrolled over the compile-time topology, everything in registers: getx(i) supplies parameter
+// i of [root | euler | side lengths] (68), emit(j, x, y, z) receives joint j. Leaf rotations are never formed
+// (no joint position depends on them).
+template <int J, class GetX, class Emit>
+struct FkStep {
+    static __device__ __forceinline__ void run(GetX& getx, Emit& emit, double (&G)[MVMC_N_B18][9], double (&pos)[MVMC_N_B18][3]) {
+        constexpr int p = Topo::parent(J);
+        double m[9];
+        if (!Topo::leaf(J)) euler_to_mat(getx(3 + 3 * J), getx(4 + 3 * J), getx(5 + 3 * J), m);
+        if (J == 0) {
+#pragma unroll
+            for (int q = 0; q < 9; q++) G[0][q] = m[q];
+            pos[0][0] = getx(0);
+            pos[0][1] = getx(1);
+            pos[0][2] = getx(2);
+        } else {
+            const double len = getx(57 + Topo::s2f(J));
+            const double o0 = c_skel.dirs[J][0] * len, o1 = c_skel.dirs[J][1] * len, o2 = c_skel.dirs[J][2] * len;
+            const double* Rp = G[p < 0 ? 0 : p];
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                if (!Topo::leaf(J)) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+                        G[J][r * 3 + c] = Rp[r * 3] * m[c] + Rp[r * 3 + 1] * m[3 + c] + Rp[r * 3 + 2] * m[6 + c];
+                }
+                pos[J][r] = Rp[r * 3] * o0 + Rp[r * 3 + 1] * o1 + Rp[r * 3 + 2] * o2 + pos[p < 0 ? 0 : p][r];
+            }
+        }
+        emit(J, pos[J][0], pos[J][1], pos[J][2]);
+        FkStep<J + 1, GetX, Emit>::run(getx, emit, G, pos);
+    }
+};
+template <class GetX, class Emit>
+struct FkStep<MVMC_N_B18, GetX, Emit> {
+    static __device__ __forceinline__ void run(GetX&, Emit&, double (&)[MVMC_N_B18][9], double (&)[MVMC_N_B18][3]) {}
+};
+template <class GetX, class Emit>
+__device__ __forceinline__ void fk_unrolled(GetX getx, Emit emit) {
+    double G[MVMC_N_B18][9];
+    double pos[MVMC_N_B18][3];
+    FkStep<0, GetX, Emit>::run(getx, emit, G, pos);
+}
+
+__device__ __forceinline__ void project3(const double* Pv, double X, double Y, double Z, double& pu, double& pv, double& pw) {
+    pu = Pv[0] * X + Pv[1] * Y + Pv[2] * Z + Pv[3];
+    pv = Pv[4] * X + Pv[5] * Y + Pv[6] * Z + Pv[7];
+    pw = Pv[8] * X + Pv[9] * Y + Pv[10] * Z + Pv[11];
+}
+
+// ---- reprojection residual of the BASIC_18 pose (inverse_kinematics.py:202-277) ----
+// rows: (view v, observed joint q, {u, v}) -> (v*16 + q)*2 + {0,1};  a chunk = 8 joints of one view (16 rows)
+struct IkRes {
     const double* obs;   // [V][16][3] gathered at c_ik_obs_idx (shared)
     const double* P;     // [V][12] (shared)
-    const double* lens;  // fixed side lengths when with_lens == 0 (shared)
+    double* posb;        // [16][3] scratch (shared)
     int V;
-    int with_lens;       // 1: x[57..67] are the lengths
     __device__ int m() const { return V * MVMC_N_IKJ * 2; }
-    template <class Emit>
-    __device__ void eval(const double* x, Emit emit) const {
-        double pos[MVMC_N_B18][3];
-        fk_b18(x, with_lens ? x + 57 : lens, pos);
-        for (int v = 0; v < V; v++) {
-            const double* Pv = P + v * 12;
-            for (int q = 0; q < MVMC_N_IKJ; q++) {
-                const double* X = pos[c_ik_skel_idx[q]];
+    __device__ int n_chunks() const { return 2 * V; }
+    __device__ int chunk_rows(int) const { return 16; }
+    __device__ int chunk_row0(int c) const { return 16 * c; }
+
+    __device__ void eval(const double* x, double* f) {
+        const int lane = threadIdx.x & 31;
+        double* pb = posb;
+        // the chain is evaluated redundantly by every lane (uniform control flow); lane 0 parks the positions
+        fk_unrolled([&](int i) { return x[i]; },
+                    [&](int j, double px, double py, double pz) {
+                        const int sl = Topo::ik_slot(j);
+                        if (sl >= 0 && lane == 0) {
+                            pb[sl * 3] = px;
+                            pb[sl * 3 + 1] = py;
+                            pb[sl * 3 + 2] = pz;
+                        }
+                    });
+        __syncwarp();
+        for (int it = lane; it < V * MVMC_N_IKJ; it += 32) {
+            const int v = it >> 4, q = it & 15;
+            const double* o = obs + it * 3;
+            double pu, pv, pw;
+            project3(P + v * 12, pb[q * 3], pb[q * 3 + 1], pb[q * 3 + 2], pu, pv, pw);
+            const double den = 1e-5 + pw;
+            f[2 * it] = DMUL(DSUB(DDIV(pu, den), o[0]), o[2]);
+            f[2 * it + 1] = DMUL(DSUB(DDIV(pv, den), o[1]), o[2]);
+        }
+        __syncwarp();
+    }
+    // per column: perturbed chain; the 16 observed joint positions go to the scratch S[(slot*3+c)*WS_NC + col] (aliases s.A)
+    __device__ void fd_prepare(TrfWarp& s, int ncol) {
+        const int lane = threadIdx.x & 31;
+        double* S = s.A;
+        for (int c0 = 0; c0 < ncol; c0 += 32) {
+            const int c = c0 + lane;
+            const bool on = c < ncol;
+            const int prm = on ? s.act[c] : -1;
+            const double xp = on ? s.w[c] : 0.0;
+            const double* x = s.x;
+            fk_unrolled([&](int i) { return i == prm ? xp : x[i]; },
+                        [&](int j, double px, double py, double pz) {
+                            const int sl = Topo::ik_slot(j);
+                            if (sl >= 0 && on) {
+                                S[(sl * 3) * WS_NC + c] = px;
+                                S[(sl * 3 + 1) * WS_NC + c] = py;
+                                S[(sl * 3 + 2) * WS_NC + c] = pz;
+                            }
+                        });
+        }
+    }
+    __device__ void fd_chunk(TrfWarp& s, int ncol, int ch, const double* f) {
+        const int lane = threadIdx.x & 31;
+        const int v = ch >> 1, q0 = (ch & 1) * 8;
+        const double* S = s.A;
+        double Pv[12];
+#pragma unroll
+        for (int e = 0; e < 12; e++) Pv[e] = P[v * 12 + e];
+        for (int c = lane; c < ncol; c += 32) {
+            const double dx = s.dx[c];
+#pragma unroll
+            for (int qq = 0; qq < 8; qq++) {
+                const int q = q0 + qq;
                 const double* o = obs + (v * MVMC_N_IKJ + q) * 3;
-                const double pu = Pv[0] * X[0] + Pv[1] * X[1] + Pv[2] * X[2] + Pv[3];
-                const double pv = Pv[4] * X[0] + Pv[5] * X[1] + Pv[6] * X[2] + Pv[7];
-                const double pw = Pv[8] * X[0] + Pv[9] * X[1] + Pv[10] * X[2] + Pv[11];
+                double pu, pv, pw;
+                project3(Pv, S[(q * 3) * WS_NC + c], S[(q * 3 + 1) * WS_NC + c], S[(q * 3 + 2) * WS_NC + c], pu, pv, pw);
                 const double den = 1e-5 + pw;
-                emit((v * MVMC_N_IKJ + q) * 2, DMUL(DSUB(DDIV(pu, den), o[0]), o[2]));
-                emit((v * MVMC_N_IKJ + q) * 2 + 1, DMUL(DSUB(DDIV(pv, den), o[1]), o[2]));
+                const double ru = DMUL(DSUB(DDIV(pu, den), o[0]), o[2]);
+                const double rv = DMUL(DSUB(DDIV(pv, den), o[1]), o[2]);
+                const int row = (v * MVMC_N_IKJ + q) * 2;
+                s.Jc[(2 * qq) * WS_LDJ + c] = DDIV(DSUB(ru, f[row]), dx);
+                s.Jc[(2 * qq + 1) * WS_LDJ + c] = DDIV(DSUB(rv, f[row + 1]), dx);
             }
         }
     }
 };
 
-struct TriResidual {  // mv_math_util.py:190-202
+// ---- triangulation refine residual (mv_math_util.py:190-202): rows (view v, point k) -> v*K + k ----
+// a chunk = half of the points of one view
+struct TriRes {
     const double* obs;  // [V][K][3] (shared)
     const double* P;    // [V][12]
     int V, K;
+    __device__ int half() const { return (K + 1) / 2; }
     __device__ int m() const { return V * K; }
-    template <class Emit>
-    __device__ void eval(const double* x, Emit emit) const {
-        for (int v = 0; v < V; v++) {
-            const double* Pv = P + v * 12;
-            for (int k = 0; k < K; k++) {
-                const double* X = x + 3 * k;
-                const double* o = obs + (v * K + k) * 3;
-                const double pu = Pv[0] * X[0] + Pv[1] * X[1] + Pv[2] * X[2] + Pv[3];
-                const double pv = Pv[4] * X[0] + Pv[5] * X[1] + Pv[6] * X[2] + Pv[7];
-                const double pw = Pv[8] * X[0] + Pv[9] * X[1] + Pv[10] * X[2] + Pv[11];
-                const double den = pw + 1e-6;
-                const double du = DSUB(DDIV(pu, den), o[0]), dv = DSUB(DDIV(pv, den), o[1]);
-                emit(v * K + k, DMUL(sqrt(DMUL(du, du) + DMUL(dv, dv)), o[2]));
-            }
+    __device__ int n_chunks() const { return 2 * V; }
+    __device__ int chunk_rows(int c) const { return (c & 1) ? K - half() : half(); }
+    __device__ int chunk_row0(int c) const { return (c >> 1) * K + (c & 1) * half(); }
+    __device__ double one(const double* Pv, const double* o, double X, double Y, double Z) const {
+        double pu, pv, pw;
+        project3(Pv, X, Y, Z, pu, pv, pw);
+        const double den = pw + 1e-6;
+        const double du = DSUB(DDIV(pu, den), o[0]), dv = DSUB(DDIV(pv, den), o[1]);
+        return DMUL(sqrt(DMUL(du, du) + DMUL(dv, dv)), o[2]);
+    }
+    __device__ void eval(const double* x, double* f) {
+        const int lane = threadIdx.x & 31;
+        for (int it = lane; it < V * K; it += 32) {
+            const int v = it / K, k = it % K;
+            f[it] = one(P + v * 12, obs + it * 3, x[3 * k], x[3 * k + 1], x[3 * k + 2]);
+        }
+        __syncwarp();
+    }
+    __device__ void fd_prepare(TrfWarp&, int) {}
+    __device__ void fd_chunk(TrfWarp& s, int ncol, int ch, const double* f) {
+        const int lane = threadIdx.x & 31;
+        const int v = ch >> 1, k0 = (ch & 1) * half(), k1 = k0 + chunk_rows(ch);
+        for (int c = lane; c < ncol; c += 32) {
+            const int prm = s.act[c], k = prm / 3, comp = prm % 3;
+            if (k < k0 || k >= k1) continue;   // a point only moves its own residual rows
+            double X[3] = {s.x[3 * k], s.x[3 * k + 1], s.x[3 * k + 2]};
+            X[comp] = s.w[c];
+            const double r = one(P + v * 12, obs + (v * K + k) * 3, X[0], X[1], X[2]);
+            s.Jc[(k - k0) * WS_LDJ + c] = DDIV(DSUB(r, f[v * K + k]), s.dx[c]);
         }
     }
 };
-
-// ---- shared-memory plan of one solver CTA ----
-constexpr int TRF_NMAX = 68;
-constexpr int TRF_LD = 69;
-constexpr int TRF_MMAX = 512;  // 32 residuals per 2D pose x MVMC_MAX_SEL
-constexpr int TRF_CH = 32;  // rows of J per chunk when forming J J^T
-
-struct TrfShared {
-    double A[TRF_NMAX * TRF_LD];
-    double Vm[TRF_NMAX * TRF_LD];   // first used as the J chunk buffer, then as eigenvectors
-    double x[TRF_NMAX], xn[TRF_NMAX], p[TRF_NMAX], g[TRF_NMAX], lam[TRF_NMAX], suf[TRF_NMAX];
-    double f[TRF_MMAX], fn[TRF_MMAX];
-    double cs[TRF_NMAX / 2 + 1], sn[TRF_NMAX / 2 + 1];
-    double scratch[32];
-    double sc[8];  // scalars broadcast from warp 0: alpha, delta, pnorm, ...
-    int pr[TRF_NMAX / 2 + 1], qr[TRF_NMAX / 2 + 1];
-    int pos[TRF_NMAX + 2], pos2[TRF_NMAX + 2];
-    int act[TRF_NMAX];
-    int flag;
-};
-
-// Eigen-decomposition of the symmetric n x n matrix s.A: on exit lam[k] = eigenvalue, column k of Vm
-// the eigenvector. Parallel cyclic Jacobi, round-robin pair ordering.
-__device__ void jacobi_eig(TrfShared& s, int n) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int np = n + (n & 1);
-    const int half = np / 2;
-    for (int e = tid; e < n * n; e += nt) s.Vm[(e / n) * TRF_LD + (e % n)] = ((e / n) == (e % n)) ? 1.0 : 0.0;
-    for (int k = tid; k < np; k += nt) s.pos[k] = k;
-    __syncthreads();
-    for (int sweep = 0; sweep < 16; sweep++) {
-        if (tid == 0) s.flag = 0;
-        __syncthreads();
-        for (int round = 0; round < np - 1; round++) {
-            for (int k = tid; k < half; k += nt) {
-                int p = s.pos[k], q = s.pos[np - 1 - k];
-                if (p > q) {
-                    const int t = p;
-                    p = q;
-                    q = t;
-                }
-                double c = 1.0, sn = 0.0;
-                if (q < n) {
-                    const double app = s.A[p * TRF_LD + p], aqq = s.A[q * TRF_LD + q], apq = s.A[p * TRF_LD + q];
-                    if (apq != 0.0 && fabs(apq) > kEps * sqrt(fabs(app) * fabs(aqq))) {
-                        const double tau = (aqq - app) / (2.0 * apq);
-                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                        c = 1.0 / sqrt(1.0 + t * t);
-                        sn = t * c;
-                        s.flag = 1;
-                    }
-                }
-                s.pr[k] = p;
-                s.qr[k] = q;
-                s.cs[k] = c;
-                s.sn[k] = sn;
-            }
-            __syncthreads();
-            // A <- J^T A J, one 2x2 block per work item
-            for (int e = tid; e < half * half; e += nt) {
-                const int kk = e / half, ll = e % half;
-                const int p1 = s.pr[kk], q1 = s.qr[kk], p2 = s.pr[ll], q2 = s.qr[ll];
-                const double c1 = s.cs[kk], s1 = s.sn[kk], c2 = s.cs[ll], s2 = s.sn[ll];
-                if (c1 == 1.0 && c2 == 1.0 && s1 == 0.0 && s2 == 0.0) continue;
-                const bool v1 = q1 < n, v2 = q2 < n;  // a pair with the dummy index only has its p member
-                const double m00 = s.A[p1 * TRF_LD + p2];
-                const double m01 = v2 ? s.A[p1 * TRF_LD + q2] : 0.0;
-                const double m10 = v1 ? s.A[q1 * TRF_LD + p2] : 0.0;
-                const double m11 = (v1 && v2) ? s.A[q1 * TRF_LD + q2] : 0.0;
-                const double t00 = c1 * m00 - s1 * m10, t01 = c1 * m01 - s1 * m11;
-                const double t10 = s1 * m00 + c1 * m10, t11 = s1 * m01 + c1 * m11;
-                double r00 = c2 * t00 - s2 * t01, r01 = s2 * t00 + c2 * t01;
-                double r10 = c2 * t10 - s2 * t11, r11 = s2 * t10 + c2 * t11;
-                if (kk == ll) {
-                    r01 = 0.0;
-                    r10 = 0.0;
-                }
-                s.A[p1 * TRF_LD + p2] = r00;
-                if (v2) s.A[p1 * TRF_LD + q2] = r01;
-                if (v1) s.A[q1 * TRF_LD + p2] = r10;
-                if (v1 && v2) s.A[q1 * TRF_LD + q2] = r11;
-            }
-            // V <- V J
-            for (int e = tid; e < n * half; e += nt) {
-                const int i = e / half, kk = e % half;
-                const int p = s.pr[kk], q = s.qr[kk];
-                const double c = s.cs[kk], sn = s.sn[kk];
-                if (q >= n || (c == 1.0 && sn == 0.0)) continue;
-                const double vp = s.Vm[i * TRF_LD + p], vq = s.Vm[i * TRF_LD + q];
-                s.Vm[i * TRF_LD + p] = c * vp - sn * vq;
-                s.Vm[i * TRF_LD + q] = sn * vp + c * vq;
-            }
-            // next round: position 0 stays, the others rotate by one
-            for (int k = tid; k < np; k += nt) s.pos2[k] = (k == 0) ? s.pos[0] : (k == 1 ? s.pos[np - 1] : s.pos[k - 1]);
-            __syncthreads();
-            for (int k = tid; k < np; k += nt) s.pos[k] = s.pos2[k];
-            __syncthreads();
-        }
-        if (s.flag == 0) break;
-        __syncthreads();
-    }
-    for (int k = tid; k < n; k += nt) s.lam[k] = s.A[k * TRF_LD + k];
-    __syncthreads();
-}
-
-struct TrfResult {
-    int nfev, njev, status;
-    double cost;
-};
-
-// Jacobian by forward differences (SciPy's default 2-point rule), then g = J^T f and A = J^T J.
-// Jg: global scratch, row k (parameter act[k]) holds the m residual derivatives.
-template <class Res>
-__device__ void trf_jacobian(TrfShared& s, const Res& res, int n, int m, int nfull, double* __restrict__ Jg) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    if (tid < n) {
-        double xl[TRF_NMAX];
-        for (int i = 0; i < nfull; i++) xl[i] = s.x[i];
-        const int i = s.act[tid];
-        const double xi = xl[i];
-        const double h = kSqrtEps * (xi >= 0.0 ? 1.0 : -1.0) * fmax(1.0, fabs(xi));
-        const double xp = xi + h;
-        const double dx = DSUB(xp, xi);
-        xl[i] = xp;
-        double* row = Jg + (size_t)tid * TRF_MMAX;
-        const double* f0 = s.f;
-        res.eval(xl, [&](int r, double v) { row[r] = DDIV(DSUB(v, f0[r]), dx); });
-    }
-    __syncthreads();
-    // g[k] = sum_r J[k][r] f[r]
-    for (int k = tid; k < n; k += nt) {
-        const double* row = Jg + (size_t)k * TRF_MMAX;
-        double acc = 0.0;
-        for (int r = 0; r < m; r++) acc += row[r] * s.f[r];
-        s.g[k] = acc;
-    }
-    // A = J J^T over chunks of residual rows staged in shared memory (buffer aliases Vm)
-    double* chunk = s.Vm;  // [n][TRF_CH+1]
-    const int nn = n * n;
-    double acc[(TRF_NMAX * TRF_NMAX + 127) / 128];  // outputs per thread for >= 128 threads
-    const int per = (nn + nt - 1) / nt;
-    for (int q = 0; q < per; q++) acc[q] = 0.0;
-    for (int r0 = 0; r0 < m; r0 += TRF_CH) {
-        __syncthreads();
-        for (int e = tid; e < n * TRF_CH; e += nt) {
-            const int k = e / TRF_CH, rr = e % TRF_CH;
-            chunk[k * (TRF_CH + 1) + rr] = (r0 + rr < m) ? Jg[(size_t)k * TRF_MMAX + r0 + rr] : 0.0;
-        }
-        __syncthreads();
-        for (int q = 0; q < per; q++) {
-            const int e = tid + q * nt;
-            if (e < nn) {
-                const int k = e / n, l = e % n;
-                double a = acc[q];
-                for (int rr = 0; rr < TRF_CH; rr++) a += chunk[k * (TRF_CH + 1) + rr] * chunk[l * (TRF_CH + 1) + rr];
-                acc[q] = a;
-            }
-        }
-    }
-    __syncthreads();
-    for (int q = 0; q < per; q++) {
-        const int e = tid + q * nt;
-        if (e < nn) s.A[(e / n) * TRF_LD + (e % n)] = acc[q];
-    }
-    __syncthreads();
-}
-
-// scipy.optimize.least_squares(fun, x0, max_nfev=...) with method='trf', jac='2-point', no bounds.
-// s.x holds the full parameter vector (nfull entries); s.act[0..n) the optimised entries.
-template <class Res>
-__device__ TrfResult trf_solve(TrfShared& s, const Res& res, int n, int nfull, int max_nfev, double* __restrict__ Jg) {
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-    const int m = res.m();
-    const double ftol = 1e-8, xtol = 1e-8, gtol = 1e-8;
-    TrfResult out;
-    if (tid == 0) res.eval(s.x, [&](int r, double v) { s.f[r] = v; });
-    __syncthreads();
-    double part = 0.0;
-    for (int r = tid; r < m; r += nt) part += s.f[r] * s.f[r];
-    double cost = 0.5 * block_sum(part, s.scratch);
-    int nfev = 1, njev = 1;
-    trf_jacobian(s, res, n, m, nfull, Jg);
-    // Delta = ||x0|| over the optimised entries (1.0 if zero)
-    part = 0.0;
-    for (int k = tid; k < n; k += nt) part += s.x[s.act[k]] * s.x[s.act[k]];
-    double delta = sqrt(block_sum(part, s.scratch));
-    if (delta == 0.0) delta = 1.0;
-    double alpha = 0.0;
-    int status = -1;
-    while (true) {
-        double gn = 0.0;
-        for (int k = 0; k < n; k++) gn = fmax(gn, fabs(s.g[k]));
-        if (gn < gtol) status = 1;
-        if (status != -1 || nfev == max_nfev) break;
-        jacobi_eig(s, n);
-        // suf = V^T g  (= s * U^T f)
-        for (int k = tid; k < n; k += nt) {
-            double acc = 0.0;
-            for (int i = 0; i < n; i++) acc += s.Vm[i * TRF_LD + k] * s.g[i];
-            s.suf[k] = acc;
-            if (s.lam[k] < 0.0) s.lam[k] = 0.0;
-        }
-        __syncthreads();
-        double lmax = 0.0, lmin = INFINITY;
-        for (int k = 0; k < n; k++) {
-            lmax = fmax(lmax, s.lam[k]);
-            lmin = fmin(lmin, s.lam[k]);
-        }
-        const bool full_rank = (m >= n) && (sqrt(lmin) > kEps * m * sqrt(lmax));
-        double actual = -1.0, cost_new = cost;
-        while (actual <= 0.0 && nfev < max_nfev) {
-            // ---- trust-region sub-problem (warp 0), result: s.p (free entries), alpha ----
-            if (tid < 32) {
-                double a_new = alpha;
-                bool gn_step = false;
-                double scale_to = 0.0;  // 0: no rescale
-                if (full_rank) {
-                    double pn2 = 0.0;
-                    for (int k = lane; k < n; k += 32) {
-                        const double w = s.suf[k] / s.lam[k];
-                        pn2 += w * w;
-                    }
-                    pn2 = warp_sum(pn2);
-                    if (sqrt(pn2) <= delta) {
-                        gn_step = true;
-                        a_new = 0.0;
-                    }
-                }
-                if (!gn_step) {
-                    double sn2 = 0.0;
-                    for (int k = lane; k < n; k += 32) sn2 += s.suf[k] * s.suf[k];
-                    sn2 = warp_sum(sn2);
-                    double a_hi = sqrt(sn2) / delta, a_lo = 0.0;
-                    if (full_rank) {
-                        double q1 = 0.0, q3 = 0.0;
-                        for (int k = lane; k < n; k += 32) {
-                            const double den = s.lam[k];
-                            const double w = s.suf[k] / den;
-                            q1 += w * w;
-                            q3 += s.suf[k] * s.suf[k] / (den * den * den);
-                        }
-                        q1 = warp_sum(q1);
-                        q3 = warp_sum(q3);
-                        const double pn = sqrt(q1);
-                        a_lo = -(pn - delta) / (-q3 / pn);
-                    }
-                    double al = alpha;
-                    if (!full_rank && al == 0.0) al = fmax(0.001 * a_hi, sqrt(a_lo * a_hi));
-                    for (int itn = 0; itn < 10; itn++) {
-                        if (al < a_lo || al > a_hi) al = fmax(0.001 * a_hi, sqrt(a_lo * a_hi));
-                        double q1 = 0.0, q3 = 0.0;
-                        for (int k = lane; k < n; k += 32) {
-                            const double den = s.lam[k] + al;
-                            const double w = s.suf[k] / den;
-                            q1 += w * w;
-                            q3 += s.suf[k] * s.suf[k] / (den * den * den);
-                        }
-                        q1 = warp_sum(q1);
-                        q3 = warp_sum(q3);
-                        const double pn = sqrt(q1);
-                        const double phi = pn - delta, dphi = -q3 / pn;
-                        if (phi < 0.0) a_hi = al;
-                        const double ratio = phi / dphi;
-                        a_lo = fmax(a_lo, al - ratio);
-                        al -= (phi + delta) * ratio / delta;
-                        if (fabs(phi) < 0.01 * delta) break;
-                    }
-                    a_new = al;
-                    scale_to = delta;
-                }
-                // p = -V w, w = suf / (lam + alpha)   (w parked in s.fn, which is rewritten by the next eval)
-                for (int k = lane; k < n; k += 32) s.fn[k] = s.suf[k] / (s.lam[k] + a_new);
-                __syncwarp();
-                double pn2 = 0.0;
-                for (int i = lane; i < n; i += 32) {
-                    double acc = 0.0;
-                    for (int k = 0; k < n; k++) acc += s.Vm[i * TRF_LD + k] * s.fn[k];
-                    s.p[i] = -acc;
-                    pn2 += acc * acc;
-                }
-                pn2 = warp_sum(pn2);
-                double sc = 1.0;
-                if (scale_to > 0.0) {
-                    sc = scale_to / sqrt(pn2);
-                    double pn2b = 0.0;
-                    for (int i = lane; i < n; i += 32) {
-                        s.p[i] *= sc;
-                        pn2b += s.p[i] * s.p[i];
-                    }
-                    pn2 = warp_sum(pn2b);
-                }
-                __syncwarp();
-                // predicted reduction: -(0.5 |J p|^2 + g.p), |J p|^2 = sum lam_k (V^T p)_k^2, V^T p = -sc w
-                double jp2 = 0.0, gp = 0.0;
-                for (int k = lane; k < n; k += 32) {
-                    const double w = s.fn[k] * sc;
-                    jp2 += s.lam[k] * w * w;
-                    gp += s.g[k] * s.p[k];
-                }
-                jp2 = warp_sum(jp2);
-                gp = warp_sum(gp);
-                if (lane == 0) {
-                    s.sc[0] = a_new;
-                    s.sc[1] = sqrt(pn2);
-                    s.sc[2] = -(0.5 * jp2 + gp);
-                }
-            }
-            __syncthreads();
-            alpha = s.sc[0];
-            const double p_norm = s.sc[1], predicted = s.sc[2];
-            for (int i = tid; i < nfull; i += nt) s.xn[i] = s.x[i];
-            __syncthreads();
-            for (int k = tid; k < n; k += nt) s.xn[s.act[k]] = s.x[s.act[k]] + s.p[k];
-            __syncthreads();
-            if (tid == 0) res.eval(s.xn, [&](int r, double v) { s.fn[r] = v; });
-            __syncthreads();
-            nfev++;
-            part = 0.0;
-            int bad = 0;
-            for (int r = tid; r < m; r += nt) {
-                const double v = s.fn[r];
-                part += v * v;
-                if (!(fabs(v) <= 1.79769313486231570e308)) bad = 1;
-            }
-            cost_new = 0.5 * block_sum(part, s.scratch);
-            if (!(cost_new <= 1.79769313486231570e308)) bad = 1;  // any non-finite residual poisons the sum
-            (void)bad;
-            if (!(cost_new == cost_new) || cost_new > 1.79769313486231570e308) {
-                delta = 0.25 * p_norm;
-                continue;
-            }
-            actual = cost - cost_new;
-            double ratio;
-            if (predicted > 0.0) ratio = actual / predicted;
-            else if (predicted == 0.0 && actual == 0.0) ratio = 1.0;
-            else ratio = 0.0;
-            double delta_new = delta;
-            if (ratio < 0.25) delta_new = 0.25 * p_norm;
-            else if (ratio > 0.75 && p_norm > 0.95 * delta) delta_new = delta * 2.0;
-            part = 0.0;
-            for (int k = tid; k < n; k += nt) part += s.x[s.act[k]] * s.x[s.act[k]];
-            const double x_norm = sqrt(block_sum(part, s.scratch));
-            const bool f_ok = actual < ftol * cost && ratio > 0.25;
-            const bool x_ok = p_norm < xtol * (xtol + x_norm);
-            if (f_ok && x_ok) status = 4;
-            else if (f_ok) status = 2;
-            else if (x_ok) status = 3;
-            if (status != -1) break;
-            alpha *= delta / delta_new;
-            delta = delta_new;
-        }
-        if (actual > 0.0) {
-            __syncthreads();
-            for (int i = tid; i < nfull; i += nt) s.x[i] = s.xn[i];
-            for (int r = tid; r < m; r += nt) s.f[r] = s.fn[r];
-            __syncthreads();
-            cost = cost_new;
-            trf_jacobian(s, res, n, m, nfull, Jg);
-            njev++;
-        }
-    }
-    if (status == -1) status = 0;
-    out.nfev = nfev;
-    out.njev = njev;
-    out.status = status;
-    out.cost = cost;
-    return out;
-}
 
 // ---- DLT: null vector of the (2V x 4) system by one-sided Jacobi (single thread, tiny) ----
 __device__ void dlt_point(const double* P /*[V][12]*/, const double* xy /*[V][2]*/, const int* sel, int nsel, double* out3) {
@@ -601,155 +359,186 @@ __device__ __forceinline__ void mid_spine(const double* k, double* o) {
     o[2] = sc;
 }
 
-constexpr int IK_THREADS = 256;
-
-struct IkShared {
-    TrfShared t;
-    double obs18[MVMC_MAX_SEL * 18 * 3];
-    double obs16[MVMC_MAX_SEL * MVMC_N_IKJ * 3];
-    double P[MVMC_MAX_SEL * 12];
-    double lens[11];
+// ---- per-warp shared memory of the solver kernels ----
+template <int VMAX>
+struct alignas(16) IkWarpSh {
+    TrfWarp t;
+    double f[32 * VMAX], fn[32 * VMAX];
+    double obs16[VMAX * MVMC_N_IKJ * 3];
+    double obs18[VMAX * 18 * 3];
+    double P[VMAX * 12];
+    double posb[MVMC_N_IKJ * 3];
     double p3[18 * 4];
 };
 
-__global__ void __launch_bounds__(IK_THREADS)
-    k_ik_solve(const double* __restrict__ kps2d, const double* __restrict__ Psel, const int* __restrict__ n_views,
-               const double* __restrict__ x0, const uint8_t* __restrict__ birth, const int* __restrict__ max_nfev,
-               const uint8_t* __restrict__ free_mask, int M, int V, double* __restrict__ ws, double* __restrict__ x_out,
-               double* __restrict__ joints, int* __restrict__ info, double* __restrict__ cost_out) {
-    MVMC_DYN_SMEM(IkShared, shp);
-    IkShared& sh = *shp;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    double* Jg = ws + (size_t)blockIdx.x * TRF_NMAX * TRF_MMAX;  // one Jacobian scratch per resident CTA
-  for (int mI = blockIdx.x; mI < M; mI += gridDim.x) {  // persistent CTAs stride over the work slots
-    const int nv = n_views[mI];
-    if (nv < 2) continue;  // the reference never solves from fewer than two views (motion_capture.py:926,942)
-    __syncthreads();
-    const bool is_birth = birth != nullptr && birth[mI] != 0;
-    const int nfev_cap = max_nfev[mI];
-    // stage observations (+ mid spine) and projection matrices
-    for (int e = tid; e < nv * MVMC_N_COCO * 3; e += nt) {
-        const int v = e / (MVMC_N_COCO * 3), q = e % (MVMC_N_COCO * 3);
-        sh.obs18[v * 54 + q] = kps2d[((size_t)mI * V + v) * (MVMC_N_COCO * 3) + q];
+// Triangulate K (<= 18) joints from nv views (+ optional refine_nfev-evaluation TRF refine); result in sh.p3 [K][4].
+template <int VMAX>
+__device__ void warp_triangulate(IkWarpSh<VMAX>& sh, const double* obs /*[nv][K][3] shared*/, int nv, int K, double min_score,
+                                 int refine_nfev) {
+    const int lane = threadIdx.x & 31;
+    if (lane < K) triangulate_joint(obs, sh.P, nv, K, lane, min_score, sh.p3 + lane * 4);
+    __syncwarp();
+    if (refine_nfev <= 0) return;
+    for (int e = lane; e < MVMC_N_PARAM; e += 32) sh.t.x[e] = 0.0;
+    __syncwarp();
+    for (int e = lane; e < 3 * K; e += 32) {
+        sh.t.x[e] = sh.p3[(e / 3) * 4 + (e % 3)];
+        sh.t.act[e] = e;
     }
-    for (int e = tid; e < nv * 12; e += nt) sh.P[e] = Psel[(size_t)mI * V * 12 + e];
-    __syncthreads();
-    if (tid < nv) mid_spine(sh.obs18 + tid * 54, sh.obs18 + tid * 54 + 51);
-    __syncthreads();
-    for (int e = tid; e < nv * MVMC_N_IKJ * 3; e += nt) {
-        const int v = e / (MVMC_N_IKJ * 3), q = (e / 3) % MVMC_N_IKJ, c = e % 3;
-        sh.obs16[e] = sh.obs18[v * 54 + c_ik_obs_idx[q] * 3 + c];
-    }
-    __syncthreads();
-    if (is_birth) {
-        // triangulate 18 joints (min score 0.01), refine with a 2-nfev TRF, inverse_kinematics.py:389-396
-        if (tid < 18) triangulate_joint(sh.obs18, sh.P, nv, 18, tid, 0.01, sh.p3 + tid * 4);
-        __syncthreads();
-        for (int e = tid; e < 54; e += nt) {
-            sh.t.x[e] = sh.p3[(e / 3) * 4 + (e % 3)];
-            sh.t.act[e] = e;
-        }
-        __syncthreads();
-        TriResidual tr{sh.obs18, sh.P, nv, 18};
-        trf_solve(sh.t, tr, 54, 54, 2, Jg);
-        __syncthreads();
-        if (tid == 0) {
-            double root[3];
-            for (int c = 0; c < 3; c++) root[c] = 0.5 * (sh.t.x[kCocoLHip * 3 + c] + sh.t.x[kCocoRHip * 3 + c]);
-            for (int c = 0; c < 3; c++) sh.t.x[c] = root[c];
-            for (int e = 3; e < 57; e++) sh.t.x[e] = 0.0;
-            for (int e = 0; e < 11; e++) sh.t.x[57 + e] = c_skel.ref_side_lens[e];
-        }
-    } else {
-        for (int e = tid; e < MVMC_N_PARAM; e += nt) sh.t.x[e] = x0[(size_t)mI * MVMC_N_PARAM + e];
-    }
-    __syncthreads();
-    // ---- solve 1: root + angles, lengths fixed (solve_pose_reproj) ----
-    if (tid < 11) sh.lens[tid] = sh.t.x[57 + tid];
-    if (tid == 0) {
-        int n = 0;
-        for (int e = 0; e < 57; e++)
-            if (!free_mask || free_mask[e]) sh.t.act[n++] = e;
-        sh.t.flag = n;
-    }
-    __syncthreads();
-    int n1 = sh.t.flag;
-    __syncthreads();
-    IkResidual r1{sh.obs16, sh.P, sh.lens, nv, 0};
-    TrfResult a = {1, 1, 0, 0.0};
-    if (n1 > 0) a = trf_solve(sh.t, r1, n1, 57, nfev_cap, Jg);
-    __syncthreads();
-    // ---- solve 2: root + angles + lengths (solve_pose_bone_lens_reproj) ----
-    if (tid == 0) {
-        int n = 0;
-        for (int e = 0; e < MVMC_N_PARAM; e++)
-            if (!free_mask || free_mask[e]) sh.t.act[n++] = e;
-        sh.t.flag = n;
-    }
-    __syncthreads();
-    int n2 = sh.t.flag;
-    __syncthreads();
-    IkResidual r2{sh.obs16, sh.P, sh.lens, nv, 1};
-    TrfResult bres = {1, 1, 0, 0.0};
-    if (n2 > 0) bres = trf_solve(sh.t, r2, n2, MVMC_N_PARAM, nfev_cap, Jg);
-    __syncthreads();
-    for (int e = tid; e < MVMC_N_PARAM; e += nt) x_out[(size_t)mI * MVMC_N_PARAM + e] = sh.t.x[e];
-    if (tid == 0) {
-        double pos[MVMC_N_B18][3];
-        fk_b18(sh.t.x, sh.t.x + 57, pos);
-        for (int j = 0; j < MVMC_N_B18; j++)
-            for (int c = 0; c < 3; c++) joints[((size_t)mI * MVMC_N_B18 + j) * 3 + c] = pos[j][c];
-        int* inf = info + (size_t)mI * 8;
-        inf[0] = a.nfev;
-        inf[1] = a.njev;
-        inf[2] = a.status;
-        inf[3] = n1;
-        inf[4] = bres.nfev;
-        inf[5] = bres.njev;
-        inf[6] = bres.status;
-        inf[7] = n2;
-        cost_out[(size_t)mI * 2] = a.cost;
-        cost_out[(size_t)mI * 2 + 1] = bres.cost;
-    }
-  }
+    __syncwarp();
+    TriRes tr{obs, sh.P, nv, K};
+    trf_solve_warp(sh.t, tr, 3 * K, 3 * K, 0.0, false, refine_nfev, sh.f, sh.fn);
+    __syncwarp();
+    for (int e = lane; e < 3 * K; e += 32) sh.p3[(e / 3) * 4 + (e % 3)] = sh.t.x[e];
+    __syncwarp();
 }
 
-struct TriShared {
-    TrfShared t;
-    double obs[MVMC_MAX_SEL * 18 * 3];
-    double P[MVMC_MAX_SEL * 12];
-    double p3[18 * 4];
-};
-
-__global__ void __launch_bounds__(IK_THREADS)
-    k_triangulate(const double* __restrict__ obs, const double* __restrict__ Psel, const int* __restrict__ n_views, int M,
-                  int V, int K, double min_score, int refine_nfev, double* __restrict__ ws, double* __restrict__ out) {
-    MVMC_DYN_SMEM(TriShared, shp);
-    TriShared& sh = *shp;
-    const int tid = threadIdx.x, nt = blockDim.x;
-  for (int mI = blockIdx.x; mI < M; mI += gridDim.x) {
-    const int nv = n_views[mI];
-    if (nv < 1) continue;
-    __syncthreads();
-    for (int e = tid; e < nv * K * 3; e += nt) sh.obs[e] = obs[(size_t)mI * V * K * 3 + e];
-    for (int e = tid; e < nv * 12; e += nt) sh.P[e] = Psel[(size_t)mI * V * 12 + e];
-    __syncthreads();
-    if (tid < K) triangulate_joint(sh.obs, sh.P, nv, K, tid, min_score, sh.p3 + tid * 4);
-    __syncthreads();
-    if (refine_nfev > 0) {
-        for (int e = tid; e < 3 * K; e += nt) {
-            sh.t.x[e] = sh.p3[(e / 3) * 4 + (e % 3)];
-            sh.t.act[e] = e;
+// active-column list of one IK stage: optimised (free_mask) parameters in [0, npar) that can move a joint.
+// returns ncol; n_opt / x2_dead / has_dead describe the optimised-but-dead parameters (they enter SciPy's norms).
+__device__ int ik_columns(TrfWarp& t, const uint8_t* free_mask, int npar, int& n_opt, double& x2_dead, bool& has_dead) {
+    const int lane = threadIdx.x & 31;
+    int ncol = 0;
+    n_opt = 0;
+    x2_dead = 0.0;
+    has_dead = false;
+    for (int e0 = 0; e0 < npar; e0 += 32) {
+        const int e = e0 + lane;
+        const bool opt = e < npar && (!free_mask || free_mask[e]);
+        const bool live = opt && !c_skel.param_dead[e];
+        const unsigned mo = __ballot_sync(MVMC_FULL, opt), ml = __ballot_sync(MVMC_FULL, live);
+        if (live) {
+            const int c = ncol + __popc(ml & ((1u << lane) - 1u));
+            if (c < WS_NC) t.act[c] = e;
         }
-        __syncthreads();
-        TriResidual tr{sh.obs, sh.P, nv, K};
-        trf_solve(sh.t, tr, 3 * K, 3 * K, refine_nfev, ws + (size_t)blockIdx.x * TRF_NMAX * TRF_MMAX);
-        __syncthreads();
-        for (int e = tid; e < 3 * K; e += nt) sh.p3[(e / 3) * 4 + (e % 3)] = sh.t.x[e];
-        __syncthreads();
+        const double xv = (opt && !live) ? t.x[e] : 0.0;
+        x2_dead += warp_sum(xv * xv);
+        n_opt += __popc(mo);
+        ncol += __popc(ml);
+        has_dead = has_dead || (mo != ml);
     }
-    for (int e = tid; e < K * 4; e += nt) out[(size_t)mI * K * 4 + e] = sh.p3[e];
-  }
+    __syncwarp();
+    return ncol;
+}
+
+template <int VMAX>
+__global__ void __launch_bounds__(32)
+    k_ik_solve(const double* __restrict__ kps2d, const double* __restrict__ Psel, const int* __restrict__ n_views,
+               const double* __restrict__ x0, const uint8_t* __restrict__ birth, const int* __restrict__ max_nfev,
+               const uint8_t* __restrict__ free_mask, int n_items, int cnt, int S, int s0, int V, int* __restrict__ counter,
+               double* __restrict__ x_out, double* __restrict__ joints, int* __restrict__ info, double* __restrict__ cost_out) {
+    MVMC_DYN_SMEM(IkWarpSh<VMAX>, shp);
+    IkWarpSh<VMAX>& sh = *shp;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(counter, 1);
+        item = __shfl_sync(MVMC_FULL, item, 0);
+        if (item >= n_items) break;
+        const int mI = (item / cnt) * S + s0 + item % cnt;
+        const int nv = n_views[mI];
+        if (nv < 2) continue;  // the reference never solves from fewer than two views (motion_capture.py:926,942)
+        int* inf = info + (size_t)mI * 8;
+        if (nv > VMAX) {       // cannot happen through the pipeline (it sizes VMAX from the slot kind)
+            if (lane < 8) inf[lane] = -1;
+            continue;
+        }
+        const bool is_birth = birth != nullptr && birth[mI] != 0;
+        const int nfev_cap = max_nfev[mI];
+        __syncwarp();
+        // stage observations (+ mid spine) and projection matrices
+        for (int e = lane; e < nv * MVMC_N_COCO * 3; e += 32) {
+            const int v = e / (MVMC_N_COCO * 3), q = e % (MVMC_N_COCO * 3);
+            sh.obs18[v * 54 + q] = kps2d[((size_t)mI * V + v) * (MVMC_N_COCO * 3) + q];
+        }
+        for (int e = lane; e < nv * 12; e += 32) sh.P[e] = Psel[(size_t)mI * V * 12 + e];
+        __syncwarp();
+        if (lane < nv) mid_spine(sh.obs18 + lane * 54, sh.obs18 + lane * 54 + 51);
+        __syncwarp();
+        for (int e = lane; e < nv * MVMC_N_IKJ * 3; e += 32) {
+            const int v = e / (MVMC_N_IKJ * 3), q = (e / 3) % MVMC_N_IKJ, c = e % 3;
+            sh.obs16[e] = sh.obs18[v * 54 + c_ik_obs_idx[q] * 3 + c];
+        }
+        __syncwarp();
+        if (is_birth) {
+            // triangulate 18 joints (min score 0.01), refine with a 2-nfev TRF, inverse_kinematics.py:389-396
+            warp_triangulate(sh, sh.obs18, nv, 18, 0.01, 2);
+            if (lane == 0) {
+                double root[3];
+                for (int c = 0; c < 3; c++) root[c] = 0.5 * (sh.p3[kCocoLHip * 4 + c] + sh.p3[kCocoRHip * 4 + c]);
+                for (int c = 0; c < 3; c++) sh.t.x[c] = root[c];
+                for (int e = 3; e < 57; e++) sh.t.x[e] = 0.0;
+                for (int e = 0; e < 11; e++) sh.t.x[57 + e] = c_skel.ref_side_lens[e];
+            }
+        } else {
+            for (int e = lane; e < MVMC_N_PARAM; e += 32) sh.t.x[e] = x0[(size_t)mI * MVMC_N_PARAM + e];
+        }
+        __syncwarp();
+        IkRes res{sh.obs16, sh.P, sh.posb, nv};
+        TrfResult r[2];
+        int ncols[2];
+#pragma unroll 1
+        for (int stage = 0; stage < 2; stage++) {
+            // stage 0: root + angles, lengths fixed (solve_pose_reproj); stage 1: + the 11 side lengths
+            int n_opt;
+            double x2_dead;
+            bool has_dead;
+            const int ncol = ik_columns(sh.t, free_mask, stage == 0 ? 57 : MVMC_N_PARAM, n_opt, x2_dead, has_dead);
+            ncols[stage] = n_opt;
+            r[stage].nfev = 1;
+            r[stage].njev = 1;
+            r[stage].status = 0;
+            r[stage].cost = 0.0;
+            if (ncol > WS_NC) {
+                r[stage].status = -2;
+            } else if (ncol > 0) {
+                r[stage] = trf_solve_warp(sh.t, res, ncol, n_opt, x2_dead, has_dead, nfev_cap, sh.f, sh.fn);
+            }
+            __syncwarp();
+        }
+        for (int e = lane; e < MVMC_N_PARAM; e += 32) x_out[(size_t)mI * MVMC_N_PARAM + e] = sh.t.x[e];
+        {
+            const double* x = sh.t.x;
+            double* jout = joints + (size_t)mI * MVMC_N_B18 * 3;
+            fk_unrolled([&](int i) { return x[i]; },
+                        [&](int j, double px, double py, double pz) {
+                            if (lane == 0) {
+                                jout[j * 3] = px;
+                                jout[j * 3 + 1] = py;
+                                jout[j * 3 + 2] = pz;
+                            }
+                        });
+        }
+        if (lane == 0) {
+            for (int q = 0; q < 2; q++) {
+                inf[4 * q] = r[q].nfev;
+                inf[4 * q + 1] = r[q].njev;
+                inf[4 * q + 2] = r[q].status;
+                inf[4 * q + 3] = ncols[q];
+                cost_out[(size_t)mI * 2 + q] = r[q].cost;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int VMAX>
+__global__ void __launch_bounds__(32)
+    k_triangulate(const double* __restrict__ obs, const double* __restrict__ Psel, const int* __restrict__ n_views, int M,
+                  int V, int K, double min_score, int refine_nfev, double* __restrict__ out) {
+    MVMC_DYN_SMEM(IkWarpSh<VMAX>, shp);
+    IkWarpSh<VMAX>& sh = *shp;
+    const int lane = threadIdx.x & 31;
+    for (int mI = blockIdx.x; mI < M; mI += gridDim.x) {
+        const int nv = n_views[mI];
+        if (nv < 1 || nv > VMAX) continue;
+        __syncwarp();
+        for (int e = lane; e < nv * K * 3; e += 32) sh.obs18[e] = obs[(size_t)mI * V * K * 3 + e];
+        for (int e = lane; e < nv * 12; e += 32) sh.P[e] = Psel[(size_t)mI * V * 12 + e];
+        __syncwarp();
+        warp_triangulate(sh, sh.obs18, nv, K, min_score, refine_nfev);
+        for (int e = lane; e < K * 4; e += 32) out[(size_t)mI * K * 4 + e] = sh.p3[e];
+        __syncwarp();
+    }
 }
 
 __global__ void k_fk(const double* __restrict__ params, int M, double* __restrict__ joints) {
@@ -819,14 +608,14 @@ static int ensure_skeleton() {
         {0, 0, 0},     {0.15, 0, 0}, {0, 0, -0.5}, {0, 0, -0.5},  {-0.15, 0, 0}, {0, 0, -0.5},
         {0, 0, -0.5},  {0, 0, 0.3},  {0, 0, 0.3},  {0.2, 0, 0},   {0.3, 0, 0},   {0.3, 0, 0},
         {-0.2, 0, 0},  {-0.3, 0, 0}, {-0.3, 0, 0}, {0, -0.02, 0.15}, {0.07, 0.02, 0.1}, {-0.07, 0.02, 0.1}};
-    static const int parents[MVMC_N_B18] = {-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 9, 10, 8, 12, 13, 8, 15, 15};
-    static const int s2f[MVMC_N_B18] = {7, 0, 1, 2, 0, 1, 2, 8, 9, 3, 4, 5, 3, 4, 5, 10, 6, 6};
     static const int side_src[11] = {1, 2, 3, 9, 10, 11, 16, 0, 7, 8, 15};
     SkelConst h;
     double lens[MVMC_N_B18];
+    bool has_child[MVMC_N_B18] = {};
     for (int j = 0; j < MVMC_N_B18; j++) {
-        h.parents[j] = parents[j];
-        h.side_to_full[j] = s2f[j];
+        h.parents[j] = Topo::parent(j);
+        h.side_to_full[j] = Topo::s2f(j);
+        if (h.parents[j] >= 0) has_child[h.parents[j]] = true;
         volatile double a = off[j][0] * off[j][0];
         volatile double b = off[j][1] * off[j][1];
         volatile double c = off[j][2] * off[j][2];
@@ -836,18 +625,53 @@ static int ensure_skeleton() {
         for (int q = 0; q < 3; q++) h.dirs[j][q] = (j == 0) ? off[j][q] : off[j][q] / lens[j];
     }
     for (int e = 0; e < 11; e++) h.ref_side_lens[e] = lens[side_src[e]];
+    // a parameter is dead when no joint position depends on it: rotations of childless joints, and a side length
+    // that only the root uses (the root's own offset is replaced by the root translation)
+    for (int e = 0; e < MVMC_N_PARAM; e++) h.param_dead[e] = 0;
+    for (int j = 0; j < MVMC_N_B18; j++) {
+        if (has_child[j] != !Topo::leaf(j)) return MVMC_ERR_INVALID;
+        if (!has_child[j])
+            for (int c = 0; c < 3; c++) h.param_dead[3 + 3 * j + c] = 1;
+    }
+    for (int e = 0; e < 11; e++) {
+        bool used = false;
+        for (int j = 1; j < MVMC_N_B18; j++) used = used || h.side_to_full[j] == e;
+        if (!used) h.param_dead[57 + e] = 1;
+    }
     MVMC_CUDA_OK(cudaMemcpyToSymbol(c_skel, &h, sizeof(h)));
     g_skel_ready = true;
     return MVMC_OK;
 }
 
-// persistent grid: at most this many CTAs stride over the work slots (148 SMs x 2 resident CTAs x 4)
-constexpr int IK_MAX_GRID = 1184;
+// persistent grid: 148 SMs x 4 resident one-warp CTAs
+constexpr int IK_MAX_GRID = 148 * 4;
 static int ik_grid(int M) { return M < IK_MAX_GRID ? M : IK_MAX_GRID; }
 
 extern "C" size_t mvmc_ik_workspace_bytes(int M, int V) {
+    (void)M;
     (void)V;
-    return (size_t)ik_grid(M) * TRF_NMAX * TRF_MMAX * sizeof(double);
+    return 256;  // work counters of the persistent CTAs
+}
+
+// Internal launcher shared with the clip pipeline: items i in [0, n_items) map to slot (i / cnt) * S + s0 + i % cnt.
+int mvmc_ik_launch(const double* kps2d, const double* Psel, const int* n_views, const double* x0, const uint8_t* birth,
+                   const int* max_nfev, const uint8_t* free_mask, int n_items, int cnt, int S, int s0, int V, int vmax,
+                   int* counter, double* x_out, double* joints, int* info, double* cost, void* stream) {
+    int rc = ensure_skeleton();
+    if (rc) return rc;
+    MVMC_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
+    if (vmax <= 8) {
+        MVMC_CUDA_OK(cudaFuncSetAttribute(k_ik_solve<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IkWarpSh<8>)));
+        MVMC_LAUNCH(k_ik_solve<8>, dim3(ik_grid(n_items)), dim3(32), sizeof(IkWarpSh<8>), stream, kps2d, Psel, n_views, x0, birth,
+                    max_nfev, free_mask, n_items, cnt, S, s0, V, counter, x_out, joints, info, cost);
+    } else {
+        MVMC_CUDA_OK(cudaFuncSetAttribute(k_ik_solve<MVMC_MAX_SEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(IkWarpSh<MVMC_MAX_SEL>)));
+        MVMC_LAUNCH(k_ik_solve<MVMC_MAX_SEL>, dim3(ik_grid(n_items)), dim3(32), sizeof(IkWarpSh<MVMC_MAX_SEL>), stream, kps2d,
+                    Psel, n_views, x0, birth, max_nfev, free_mask, n_items, cnt, S, s0, V, counter, x_out, joints, info, cost);
+    }
+    MVMC_CHECK_LAUNCH("k_ik_solve");
+    return MVMC_OK;
 }
 
 extern "C" int mvmc_ik_solve(const double* kps2d, const double* Psel, const int* n_views, const double* x0,
@@ -856,33 +680,19 @@ extern "C" int mvmc_ik_solve(const double* kps2d, const double* Psel, const int*
     if (!kps2d || !Psel || !n_views || !x0 || !max_nfev || !workspace || !x_out || !joints || !info || !cost)
         return MVMC_ERR_INVALID;
     if (M <= 0 || V < 2 || V > MVMC_MAX_SEL) return MVMC_ERR_INVALID;
-    int rc = ensure_skeleton();
-    if (rc) return rc;
-    MVMC_CUDA_OK(cudaFuncSetAttribute(k_ik_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IkShared)));
-    MVMC_LAUNCH(k_ik_solve, dim3(ik_grid(M)), dim3(IK_THREADS), sizeof(IkShared), stream, kps2d, Psel, n_views, x0, birth,
-                max_nfev, free_mask, M, V, (double*)workspace, x_out, joints, info, cost);
-    MVMC_CHECK_LAUNCH("k_ik_solve");
-    return MVMC_OK;
+    return mvmc_ik_launch(kps2d, Psel, n_views, x0, birth, max_nfev, free_mask, M, M, M, 0, V, V, (int*)workspace, x_out,
+                          joints, info, cost, stream);
 }
 
 extern "C" int mvmc_triangulate(const double* obs, const double* Psel, const int* n_views, int M, int V, int K,
                                 double min_score, int refine_nfev, double* out, void* stream) {
     if (!obs || !Psel || !n_views || !out) return MVMC_ERR_INVALID;
     if (M <= 0 || V < 1 || V > MVMC_MAX_SEL || K < 1 || K > 18 || refine_nfev < 0) return MVMC_ERR_INVALID;
-    double* ws = nullptr;
-    if (refine_nfev > 0) {
-        // the refine needs a Jacobian scratch; allocated per call (stage API only; the clip pipeline owns its own)
-        MVMC_CUDA_OK(cudaMalloc((void**)&ws, mvmc_ik_workspace_bytes(M, V)));
-    }
-    MVMC_CUDA_OK(cudaFuncSetAttribute(k_triangulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TriShared)));
-    MVMC_LAUNCH(k_triangulate, dim3(ik_grid(M)), dim3(IK_THREADS), sizeof(TriShared), stream, obs, Psel, n_views, M, V, K,
-                min_score, refine_nfev, ws, out);
-    cudaError_t e = cudaGetLastError();
-    if (ws) {
-        cudaStreamSynchronize((cudaStream_t)stream);
-        cudaFree(ws);
-    }
-    if (e != cudaSuccess) return mvmc_set_cuda_error(e, "k_triangulate");
+    MVMC_CUDA_OK(cudaFuncSetAttribute(k_triangulate<MVMC_MAX_SEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(IkWarpSh<MVMC_MAX_SEL>)));
+    MVMC_LAUNCH(k_triangulate<MVMC_MAX_SEL>, dim3(ik_grid(M)), dim3(32), sizeof(IkWarpSh<MVMC_MAX_SEL>), stream, obs, Psel,
+                n_views, M, V, K, min_score, refine_nfev, out);
+    MVMC_CHECK_LAUNCH("k_triangulate");
     return MVMC_OK;
 }
 

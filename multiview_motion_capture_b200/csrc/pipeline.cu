@@ -13,6 +13,9 @@
 #include <vector>
 
 int mvmc_ensure_skeleton();
+int mvmc_ik_launch(const double* kps2d, const double* Psel, const int* n_views, const double* x0, const uint8_t* birth,
+                   const int* max_nfev, const uint8_t* free_mask, int n_items, int cnt, int S, int s0, int V, int vmax,
+                   int* counter, double* x_out, double* joints, int* info, double* cost, void* stream);
 
 #define MVMC_N_STATS 8
 #define MVMC_N_STAGES 5
@@ -596,8 +599,13 @@ extern "C" int mvmc_clips_step(mvmc_clips* h, const double* kps, const int* n_po
                 h->w_x0, h->w_birth, h->w_nfev);
     MVMC_CHECK_LAUNCH("k_gather");
     MVMC_EV(3);
-    rc = mvmc_ik_solve(h->w_kps, h->w_P, h->w_nv, h->w_x0, h->w_birth, h->w_nfev, nullptr, B * h->S, MVMC_MAX_SEL, h->ik_ws,
-                       h->w_xout, h->w_joints, h->w_info, h->w_cost, stream);
+    // track updates use one pose per view (<= C observations); births of no-track frames may group more (<= MVMC_MAX_SEL)
+    rc = mvmc_ik_launch(h->w_kps, h->w_P, h->w_nv, h->w_x0, h->w_birth, h->w_nfev, nullptr, B * Tmax, Tmax, h->S, 0,
+                        MVMC_MAX_SEL, C, (int*)h->ik_ws, h->w_xout, h->w_joints, h->w_info, h->w_cost, stream);
+    if (rc) return rc;
+    rc = mvmc_ik_launch(h->w_kps, h->w_P, h->w_nv, h->w_x0, h->w_birth, h->w_nfev, nullptr, B * h->cfg.max_new, h->cfg.max_new,
+                        h->S, Tmax, MVMC_MAX_SEL, MVMC_MAX_SEL, (int*)h->ik_ws + 16, h->w_xout, h->w_joints, h->w_info,
+                        h->w_cost, stream);
     if (rc) return rc;
     MVMC_EV(4);
     MVMC_LAUNCH(k_commit, dim3(B), dim3(128), 0, stream, h->st, h->trk_nsel, h->trk_sel, h->new_n, h->new_nsel, h->new_sel,

@@ -1,0 +1,459 @@
+// Warp-synchronous trust-region-reflective least squares (unbounded), forward-difference Jacobian.
+//
+// Restates scipy.optimize.least_squares(method='trf', jac='2-point', tr_solver='exact', x_scale=1) as used by the
+// reference (inverse_kinematics.py:236,274; mv_math_util.py:207): same step-size rule for the finite
+// differences, same Moré iteration on the Levenberg-Marquardt parameter, same accept/reject/radius logic.
+//
+// ONE WARP PER SOLVE, no block barrier anywhere:
+//   * lanes own Jacobian columns (one perturbed model evaluation each),
+//   * J^T J is accumulated view by view from a 32-row chunk of J staged in shared memory, 8x8 register tiles
+//     (lane = tile of the lower triangle, 64 DFMA per 16 doubles loaded),
+//   * instead of SciPy's SVD of J, J^T J = Q T Q^T is reduced ONCE per Jacobian to tridiagonal form by Householder
+//     reflections; every evaluation of the secular function phi(alpha) = ||(J^T J + alpha I)^-1 g|| - Delta and of
+//     its derivative is then an O(n) tridiagonal LDL^T solve in the Q basis (mathematically the same phi, phi' SciPy
+//     evaluates from singular values), and the step is rotated back with the stored reflectors.
+// Every scalar the control flow depends on comes out of xor-butterfly reductions, which leave bitwise-identical
+// values on all lanes, so the warp never diverges on a decision.
+#pragma once
+#include "mvmc_common.cuh"
+
+namespace mvmc {
+
+constexpr int WS_NC = 56;    // live Jacobian columns per solve (multiple of 8; BASIC_18: 39 / 49, triangulation refine: 54)
+constexpr int WS_NT = WS_NC / 8;
+constexpr int WS_LDA = 57;   // row stride of A (odd: conflict-free column walks with 64-bit accesses)
+constexpr int WS_LDJ = 58;   // row stride of the J chunk (16-byte aligned rows, odd multiple of 16 B: conflict-free LDS.128)
+constexpr int WS_CH = 16;    // rows of J per chunk
+constexpr double kSqrtEps = 1.4901161193847656e-08;   // sqrt(2^-52)
+constexpr double kEps = 2.220446049250313e-16;
+constexpr double kDblMax = 1.79769313486231570e308;
+
+#ifdef MVMC_EMU
+#define DMUL(a, b) ((a) * (b))
+#define DSUB(a, b) ((a) - (b))
+#define DDIV(a, b) ((a) / (b))
+#else
+#define DMUL(a, b) __dmul_rn((a), (b))
+#define DSUB(a, b) __dsub_rn((a), (b))
+#define DDIV(a, b) __ddiv_rn((a), (b))
+#endif
+
+struct alignas(16) TrfWarp {
+    double A[WS_NC * WS_LDA];       // J^T J, then the Householder vectors; aliased by the FD scratch while J is formed
+    double Jc[WS_CH * WS_LDJ];      // current chunk of J, row major
+    double x[MVMC_N_PARAM], xn[MVMC_N_PARAM];
+    double g[WS_NC], gt[WS_NC], p[WS_NC], pt[WS_NC], d[WS_NC], e[WS_NC], tau[WS_NC], w[WS_NC], u[WS_NC], dx[WS_NC];
+    double dl[WS_NC], ll[WS_NC], yy[WS_NC], zz[WS_NC];
+    double sc[8];
+    int act[WS_NC];                 // parameter index behind each Jacobian column
+};
+
+struct TrfResult {
+    int nfev, njev, status;
+    double cost;
+};
+
+__device__ __forceinline__ double warp_max_abs(double v) { return warp_max(fabs(v)); }
+
+// lane -> tile (ti >= tj) of the lower triangle of a WS_NT x WS_NT tile grid
+__device__ __forceinline__ void lane_tile(int lane, int& ti, int& tj) {
+    int t = lane;
+    ti = 0;
+    while (t > ti) {
+        t -= ti + 1;
+        ti++;
+    }
+    tj = t;
+}
+
+// ---- Jacobian, g = J^T f, A = J^T J, then A = Q T Q^T ---------------------------------------------------------------
+// Res interface (all members are called by the whole warp):
+//   int  m() const;                      residual rows
+//   int  n_chunks() const;               J is produced chunk by chunk (a chunk = half a camera view, <= WS_CH rows)
+//   int  chunk_rows(int c) const;        rows of chunk c;  row index of its first row = chunk_row0(c)
+//   void eval(const double* x, double* f);                 all residuals at x (x, f in shared memory)
+//   void fd_prepare(TrfWarp& s, int ncol);                 per column: perturb, evaluate the model, park the state in s.A
+//   void fd_chunk(TrfWarp& s, int ncol, int c, const double* f);   fill s.Jc[r][col] = (r'(x + h e_col) - f) / dx for chunk c
+template <class Res>
+__device__ void trf_jacobian(TrfWarp& s, Res& res, int ncol, const double* f) {
+    const int lane = threadIdx.x & 31;
+    for (int e = lane; e < WS_CH * WS_LDJ; e += 32) s.Jc[e] = 0.0;
+    // SciPy's 2-point rule: h = sqrt(eps) * sign(x) * max(1, |x|) with sign(0) = +1, dx = (x + h) - x
+    for (int c = lane; c < ncol; c += 32) {
+        const double xi = s.x[s.act[c]];
+        const double h = kSqrtEps * (xi >= 0.0 ? 1.0 : -1.0) * fmax(1.0, fabs(xi));
+        s.dx[c] = DSUB(xi + h, xi);
+        s.w[c] = xi + h;    // perturbed value of the column's parameter
+    }
+    __syncwarp();
+    res.fd_prepare(s, ncol);
+    __syncwarp();
+    int ti, tj;
+    lane_tile(lane, ti, tj);
+    const bool tile_on = ti < WS_NT && 8 * tj < ncol && 8 * ti < ((ncol + 7) & ~7);
+    double acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) acc[a][b] = 0.0;
+    double g0 = 0.0, g1 = 0.0;
+    const int nch = res.n_chunks();
+    for (int c = 0; c < nch; c++) {
+        res.fd_chunk(s, ncol, c, f);
+        __syncwarp();
+        const int rows = res.chunk_rows(c);
+        const double* fr = f + res.chunk_row0(c);
+        if (tile_on) {
+            const double* pa = s.Jc + 8 * ti;
+            const double* pb = s.Jc + 8 * tj;
+            for (int r = 0; r < rows; r++) {
+                double a[8], b[8];
+#pragma unroll
+                for (int q = 0; q < 8; q += 2) {
+                    const double2 va = *reinterpret_cast<const double2*>(pa + r * WS_LDJ + q);
+                    const double2 vb = *reinterpret_cast<const double2*>(pb + r * WS_LDJ + q);
+                    a[q] = va.x;
+                    a[q + 1] = va.y;
+                    b[q] = vb.x;
+                    b[q + 1] = vb.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            }
+        }
+        for (int r = 0; r < rows; r++) {
+            const double fv = fr[r];
+            g0 = fma(s.Jc[r * WS_LDJ + lane], fv, g0);
+            if (lane + 32 < WS_NC) g1 = fma(s.Jc[r * WS_LDJ + lane + 32], fv, g1);
+        }
+        __syncwarp();
+    }
+    // the FD scratch (aliasing A) is dead from here on
+    for (int e = lane; e < WS_NC * WS_LDA; e += 32) s.A[e] = 0.0;
+    __syncwarp();
+    if (tile_on) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int r = 8 * ti + i, c = 8 * tj + j;
+                s.A[r * WS_LDA + c] = acc[i][j];
+                s.A[c * WS_LDA + r] = acc[i][j];   // (on diagonal tiles both orders are written with the same products)
+            }
+    }
+    if (lane < ncol) s.g[lane] = g0;
+    if (lane + 32 < ncol) s.g[lane + 32] = g1;
+    __syncwarp();
+    // diagonal tiles: acc[i][j] and acc[j][i] are the same sum in the same order, so A is exactly symmetric
+}
+
+// A (n x n, symmetric, full storage) -> tridiagonal T = Q^T A Q: d[0..n), e[0..n-1); reflector k is stored in
+// A[k+2.., k] (v[k+1] = 1 implicit) with s.tau[k]. LAPACK dsytd2 (lower) arithmetic, one warp.
+__device__ void warp_tridiagonalise(TrfWarp& s, int n) {
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k + 1 < n; k++) {
+        const int r0 = k + 1 + lane, r1 = r0 + 32;
+        const double a0 = r0 < n ? s.A[r0 * WS_LDA + k] : 0.0;
+        const double a1 = r1 < n ? s.A[r1 * WS_LDA + k] : 0.0;
+        const double alpha = __shfl_sync(MVMC_FULL, a0, 0);
+        const double xn2 = warp_sum((lane == 0 ? 0.0 : a0 * a0) + a1 * a1);
+        if (lane == 0) s.d[k] = s.A[k * WS_LDA + k];
+        if (xn2 == 0.0) {
+            if (lane == 0) {
+                s.tau[k] = 0.0;
+                s.e[k] = alpha;
+            }
+            __syncwarp();
+            continue;
+        }
+        const double beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+        const double tau = (beta - alpha) / beta;
+        const double scal = 1.0 / (alpha - beta);
+        const double v0 = lane == 0 ? 1.0 : a0 * scal;
+        const double v1 = a1 * scal;
+        if (r0 < n) {
+            s.u[r0] = v0;
+            if (lane != 0) s.A[r0 * WS_LDA + k] = v0;
+        }
+        if (r1 < n) {
+            s.u[r1] = v1;
+            s.A[r1 * WS_LDA + k] = v1;
+        }
+        if (lane == 0) {
+            s.tau[k] = tau;
+            s.e[k] = beta;
+        }
+        __syncwarp();
+        // w = tau * A22 v
+        double w0 = 0.0, w1 = 0.0;
+        if (r0 < n) {
+            const double* row = s.A + r0 * WS_LDA;
+            for (int c = k + 1; c < n; c++) w0 = fma(row[c], s.u[c], w0);
+        }
+        if (r1 < n) {
+            const double* row = s.A + r1 * WS_LDA;
+            for (int c = k + 1; c < n; c++) w1 = fma(row[c], s.u[c], w1);
+        }
+        w0 *= tau;
+        w1 *= tau;
+        const double wv = warp_sum((r0 < n ? w0 * v0 : 0.0) + (r1 < n ? w1 * v1 : 0.0));
+        const double kk = -0.5 * tau * wv;
+        w0 = fma(kk, v0, w0);
+        w1 = fma(kk, v1, w1);
+        if (r0 < n) s.w[r0] = w0;
+        if (r1 < n) s.w[r1] = w1;
+        __syncwarp();
+        // A22 -= v w^T + w v^T
+        if (r0 < n) {
+            double* row = s.A + r0 * WS_LDA;
+            for (int c = k + 1; c < n; c++) row[c] = row[c] - v0 * s.w[c] - w0 * s.u[c];
+        }
+        if (r1 < n) {
+            double* row = s.A + r1 * WS_LDA;
+            for (int c = k + 1; c < n; c++) row[c] = row[c] - v1 * s.w[c] - w1 * s.u[c];
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        s.d[n - 1] = s.A[(n - 1) * WS_LDA + (n - 1)];
+        if (n >= 1) s.e[n - 1] = 0.0;
+    }
+    __syncwarp();
+}
+
+// y <- H_k y for k = 0..n-3 (forward = true: y <- Q^T y) or k = n-3..0 (y <- Q y). y in shared memory.
+__device__ void warp_apply_q(const TrfWarp& s, int n, double* y, bool transpose) {
+    const int lane = threadIdx.x & 31;
+    for (int q = 0; q + 2 < n; q++) {
+        const int k = transpose ? q : n - 3 - q;
+        const double tau = s.tau[k];
+        if (tau == 0.0) continue;  // uniform
+        const int r0 = k + 1 + lane, r1 = r0 + 32;
+        const double v0 = r0 < n ? (lane == 0 ? 1.0 : s.A[r0 * WS_LDA + k]) : 0.0;
+        const double v1 = r1 < n ? s.A[r1 * WS_LDA + k] : 0.0;
+        const double y0 = r0 < n ? y[r0] : 0.0;
+        const double y1 = r1 < n ? y[r1] : 0.0;
+        const double dot = tau * warp_sum(v0 * y0 + v1 * y1);
+        if (r0 < n) y[r0] = y0 - dot * v0;
+        if (r1 < n) y[r1] = y1 - dot * v1;
+        __syncwarp();
+    }
+}
+
+// LDL^T of T + alpha I (lane 0); returns false when a pivot is not positive (clamped to keep going).
+__device__ __forceinline__ bool tri_factor(TrfWarp& s, int n, double alpha, double floor_) {
+    bool pd = true;
+    double piv = s.d[0] + alpha;
+    for (int i = 0; i < n; i++) {
+        if (!(piv > floor_)) {
+            pd = false;
+            piv = floor_;
+        }
+        s.dl[i] = piv;
+        if (i + 1 < n) {
+            const double l = s.e[i] / piv;
+            s.ll[i] = l;
+            piv = (s.d[i + 1] + alpha) - l * s.e[i];
+        }
+    }
+    return pd;
+}
+// y = (T + alpha I)^-1 b, returns ||y||^2; also w with L w = b left in `wout` when not null
+__device__ __forceinline__ double tri_solve(const TrfWarp& s, int n, const double* b, double* y) {
+    y[0] = b[0];
+    for (int i = 1; i < n; i++) y[i] = b[i] - s.ll[i - 1] * y[i - 1];
+    double nn = 0.0;
+    y[n - 1] = y[n - 1] / s.dl[n - 1];
+    nn = y[n - 1] * y[n - 1];
+    for (int i = n - 2; i >= 0; i--) {
+        y[i] = y[i] / s.dl[i] - s.ll[i] * y[i + 1];
+        nn = fma(y[i], y[i], nn);
+    }
+    return nn;
+}
+// b^T (T + alpha I)^-1 b through L w = b, sum w_i^2 / dl_i
+__device__ __forceinline__ double tri_quad(const TrfWarp& s, int n, const double* b, double* w) {
+    w[0] = b[0];
+    double q = w[0] * w[0] / s.dl[0];
+    for (int i = 1; i < n; i++) {
+        w[i] = b[i] - s.ll[i - 1] * w[i - 1];
+        q += w[i] * w[i] / s.dl[i];
+    }
+    return q;
+}
+
+// SciPy solve_lsq_trust_region in the Q basis. In: s.d, s.e, s.gt (= Q^T g), delta, alpha (warm start), full_rank.
+// Out: s.pt (step in the Q basis, already rescaled), returns alpha; sc[1] = ||p||, sc[2] = predicted reduction.
+__device__ double trf_subproblem(TrfWarp& s, int n, double delta, double alpha, bool full_rank) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        double gn2 = 0.0, dmax = 0.0;
+        for (int i = 0; i < n; i++) {
+            gn2 = fma(s.gt[i], s.gt[i], gn2);
+            dmax = fmax(dmax, fabs(s.d[i]));
+        }
+        const double floor_ = kEps * kEps * fmax(dmax, 1e-300);  // only guards against non-positive pivots
+        bool done = false;
+        double scale_to = 0.0;
+        double a_lo = 0.0, a_hi = sqrt(gn2) / delta;
+        if (full_rank) {
+            const bool pd = tri_factor(s, n, 0.0, floor_);
+            const double nn = tri_solve(s, n, s.gt, s.yy);
+            if (pd && sqrt(nn) <= delta) {
+                alpha = 0.0;
+                done = true;  // Gauss-Newton step
+            } else if (pd) {
+                const double pn = sqrt(nn);
+                const double q = tri_quad(s, n, s.yy, s.zz);
+                a_lo = -(pn - delta) / (-q / pn);
+            } else {
+                full_rank = false;
+            }
+        }
+        if (!done) {
+            if (!full_rank && alpha == 0.0) alpha = fmax(0.001 * a_hi, sqrt(a_lo * a_hi));
+            for (int it = 0; it < 10; it++) {
+                if (alpha < a_lo || alpha > a_hi) alpha = fmax(0.001 * a_hi, sqrt(a_lo * a_hi));
+                tri_factor(s, n, alpha, floor_);
+                const double pn = sqrt(tri_solve(s, n, s.gt, s.yy));
+                const double q = tri_quad(s, n, s.yy, s.zz);
+                const double phi = pn - delta, dphi = -q / pn;
+                if (phi < 0.0) a_hi = alpha;
+                const double ratio = phi / dphi;
+                a_lo = fmax(a_lo, alpha - ratio);
+                alpha -= (phi + delta) * ratio / delta;
+                if (fabs(phi) < 0.01 * delta) break;
+            }
+            tri_factor(s, n, alpha, floor_);
+            tri_solve(s, n, s.gt, s.yy);
+            scale_to = delta;
+        }
+        // p~ = -y (rescaled to the radius unless it is the Gauss-Newton step)
+        double nn = 0.0;
+        for (int i = 0; i < n; i++) nn = fma(s.yy[i], s.yy[i], nn);
+        double sc = -1.0;
+        if (scale_to > 0.0) sc = -scale_to / sqrt(nn);
+        nn = 0.0;
+        for (int i = 0; i < n; i++) {
+            const double v = s.yy[i] * sc;
+            s.pt[i] = v;
+            nn = fma(v, v, nn);
+        }
+        // predicted reduction -(0.5 p^T A p + g^T p) = -(0.5 p~^T T p~ + g~^T p~)
+        double tp = 0.0, gp = 0.0;
+        for (int i = 0; i < n; i++) {
+            double t = s.d[i] * s.pt[i];
+            if (i > 0) t = fma(s.e[i - 1], s.pt[i - 1], t);
+            if (i + 1 < n) t = fma(s.e[i], s.pt[i + 1], t);
+            tp = fma(s.pt[i], t, tp);
+            gp = fma(s.gt[i], s.pt[i], gp);
+        }
+        s.sc[0] = alpha;
+        s.sc[1] = sqrt(nn);
+        s.sc[2] = -(0.5 * tp + gp);
+    }
+    __syncwarp();
+    return s.sc[0];
+}
+
+// scipy.optimize.least_squares(fun, x0, max_nfev=...), method='trf', jac='2-point', unbounded.
+// s.x holds the full parameter vector; s.act[0..ncol) the optimised parameters that can move a residual
+// ("live" columns); n_opt = number of optimised parameters including structurally dead ones (they only enter
+// SciPy's norms of x and its m >= n rank test); x2_dead = sum of squares of the dead optimised parameters.
+template <class Res>
+__device__ TrfResult trf_solve_warp(TrfWarp& s, Res& res, int ncol, int n_opt, double x2_dead, bool has_dead, int max_nfev,
+                                    double* f, double* fn) {
+    const int lane = threadIdx.x & 31;
+    const int m = res.m();
+    const double ftol = 1e-8, xtol = 1e-8, gtol = 1e-8;
+    res.eval(s.x, f);
+    __syncwarp();
+    double part = 0.0;
+    for (int r = lane; r < m; r += 32) part = fma(f[r], f[r], part);
+    double cost = 0.5 * warp_sum(part);
+    int nfev = 1, njev = 1;
+    trf_jacobian(s, res, ncol, f);
+    part = 0.0;
+    for (int c = lane; c < ncol; c += 32) part = fma(s.x[s.act[c]], s.x[s.act[c]], part);
+    double delta = sqrt(warp_sum(part) + x2_dead);
+    if (delta == 0.0) delta = 1.0;
+    double alpha = 0.0;
+    int status = -1;
+    while (true) {
+        double gn = 0.0;
+        for (int c = lane; c < ncol; c += 32) gn = fmax(gn, fabs(s.g[c]));
+        gn = warp_max(gn);
+        if (gn < gtol) status = 1;
+        if (status != -1 || nfev == max_nfev) break;
+        // zero columns of J?  (exactly zero diagonal of J^T J)
+        int zc = 0;
+        for (int c = lane; c < ncol; c += 32) zc |= (s.A[c * WS_LDA + c] == 0.0) ? 1 : 0;
+        zc = warp_sum_i(zc);
+        const bool full_rank = (m >= n_opt) && !has_dead && zc == 0;
+        for (int c = lane; c < ncol; c += 32) s.gt[c] = s.g[c];
+        __syncwarp();
+        warp_tridiagonalise(s, ncol);
+        warp_apply_q(s, ncol, s.gt, true);
+        double actual = -1.0, cost_new = cost;
+        while (actual <= 0.0 && nfev < max_nfev) {
+            alpha = trf_subproblem(s, ncol, delta, alpha, full_rank);
+            const double p_norm = s.sc[1], predicted = s.sc[2];
+            for (int c = lane; c < ncol; c += 32) s.p[c] = s.pt[c];
+            __syncwarp();
+            warp_apply_q(s, ncol, s.p, false);
+            for (int i = lane; i < MVMC_N_PARAM; i += 32) s.xn[i] = s.x[i];
+            __syncwarp();
+            for (int c = lane; c < ncol; c += 32) s.xn[s.act[c]] = s.x[s.act[c]] + s.p[c];
+            __syncwarp();
+            res.eval(s.xn, fn);
+            __syncwarp();
+            nfev++;
+            part = 0.0;
+            for (int r = lane; r < m; r += 32) part = fma(fn[r], fn[r], part);
+            cost_new = 0.5 * warp_sum(part);
+            if (!(cost_new <= kDblMax)) {  // a non-finite residual poisons the sum (NaN or inf)
+                delta = 0.25 * p_norm;
+                continue;
+            }
+            actual = cost - cost_new;
+            double ratio;
+            if (predicted > 0.0) ratio = actual / predicted;
+            else if (predicted == 0.0 && actual == 0.0) ratio = 1.0;
+            else ratio = 0.0;
+            double delta_new = delta;
+            if (ratio < 0.25) delta_new = 0.25 * p_norm;
+            else if (ratio > 0.75 && p_norm > 0.95 * delta) delta_new = delta * 2.0;
+            part = 0.0;
+            for (int c = lane; c < ncol; c += 32) part = fma(s.x[s.act[c]], s.x[s.act[c]], part);
+            const double x_norm = sqrt(warp_sum(part) + x2_dead);
+            const bool f_ok = actual < ftol * cost && ratio > 0.25;
+            const bool x_ok = p_norm < xtol * (xtol + x_norm);
+            if (f_ok && x_ok) status = 4;
+            else if (f_ok) status = 2;
+            else if (x_ok) status = 3;
+            if (status != -1) break;
+            alpha *= delta / delta_new;
+            delta = delta_new;
+        }
+        if (actual > 0.0) {
+            for (int i = lane; i < MVMC_N_PARAM; i += 32) s.x[i] = s.xn[i];
+            for (int r = lane; r < m; r += 32) f[r] = fn[r];
+            __syncwarp();
+            cost = cost_new;
+            // SciPy re-evaluates J here even when the loop is about to stop; x, cost and the counters do not depend on it
+            if (status == -1 && nfev < max_nfev) trf_jacobian(s, res, ncol, f);
+            njev++;
+        }
+    }
+    if (status == -1) status = 0;
+    TrfResult out;
+    out.nfev = nfev;
+    out.njev = njev;
+    out.status = status;
+    out.cost = cost;
+    return out;
+}
+
+}  // namespace mvmc

@@ -23,6 +23,7 @@ struct dim3 {
     unsigned x, y, z;
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
+struct alignas(16) double2 { double x, y; };
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 typedef int cudaError_t;
