@@ -91,12 +91,16 @@ int mvmc_match_als(const double* sim, const int* dim_groups, int n_groups, const
  * :762-808 / :618-624 group decoding. Outputs, per instance:
  *   trk_nsel [B,Tmax]: -1 = track absent from spatial_time_matches, else number of (view,pose) pairs;
  *   trk_sel  [B,Tmax,MVMC_MAX_SEL,2]: (view, pose id);
- *   new_n [B]; new_nsel [B,Nb]; new_sel [B,Nb,MVMC_MAX_SEL,2] for 2D-only groups (ALL of them, in
- *   reference order, including single-view ones), Nb = max_new;
- *   n_dup [B]: how often the "more than one pose per view" hack fired; err [B]: 0 or MVMC_ERR_CAPACITY. */
+ *   new_n [B]; new_nsel [B,Nb]; new_sel [B,Nb,MVMC_MAX_SEL,2] for the 2D-only groups with >= 2 poses (the ones
+ *   the reference turns into new tracks, motion_capture.py:942), in reference order, Nb = max_new;
+ *   counts [B,4]: [0] how often the "more than one pose per view" rule fired (motion_capture.py:779,798), [1] 2D-only
+ *   groups that rule shrank to a single pose (listed by the reference, never born), [2] groups with more than
+ *   MVMC_MAX_SEL poses, of which only the first MVMC_MAX_SEL are kept (no-track frames of crowded scenes, where the
+ *   reference's float32 affinity merges dozens of poses of different people into one group), [3] reserved;
+ *   err [B]: 0 or MVMC_ERR_CAPACITY. */
 int mvmc_assign(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose,
                 const int* n_trk, int B, int C, int N, int Tmax, int max_new, int* trk_nsel, int* trk_sel,
-                int* new_n, int* new_nsel, int* new_sel, int* n_dup, int* err, void* stream);
+                int* new_n, int* new_nsel, int* new_sel, int* counts, int* err, void* stream);
 
 /* B1 + B2 — mv_math_util.py:152-240 (DLT per joint + optional 2-nfev TRF refine).
  * obs [M,V,K,3] (x,y,score), Psel [M,V,3,4], n_views [M] (<= V <= MVMC_MAX_SEL), K <= 18 joints.
@@ -138,7 +142,7 @@ typedef struct mvmc_config {
     int n_views;      /* C <= MVMC_MAX_VIEWS */
     int max_poses;    /* Pmax <= MVMC_MAX_POSES */
     int max_tracks;   /* Tmax <= MVMC_MAX_TRACKS */
-    int max_new;      /* births per clip per frame that can be solved (<= 32) */
+    int max_new;      /* births per clip per frame that can be solved (<= 64) */
     int n_inits;      /* hits to confirm a track (reference: 3) */
     int max_age;      /* misses tolerated by a confirmed track (reference: 0) */
     int nfev_update;  /* reference: 5 */
@@ -189,6 +193,7 @@ typedef struct mvmc_step_out {
     int32_t als_iters;
     int32_t n_dup_view;
     int32_t error;                    /* 0 or MVMC_ERR_CAPACITY */
+    int32_t n_truncated;              /* groups cut to their first MVMC_MAX_SEL poses (see mvmc_assign) */
     mvmc_track_out tracks[MVMC_MAX_TRACKS];
 } mvmc_step_out;
 

@@ -27,6 +27,7 @@ TRACK_OUT_DTYPE = np.dtype([
 STEP_OUT_DTYPE = np.dtype([
     ("frame_idx", np.int32), ("n_alive", np.int32), ("n_died", np.int32), ("died_ids", np.int32, (MAX_TRACKS,)),
     ("n_total", np.int32), ("als_iters", np.int32), ("n_dup_view", np.int32), ("error", np.int32),
+    ("n_truncated", np.int32),
     ("tracks", TRACK_OUT_DTYPE, (MAX_TRACKS,)),
 ], align=True)
 

@@ -25,7 +25,7 @@ class ClipBatch:
         lib.mvmc_default_config(ctypes.byref(cfg))
         cfg.n_clips, cfg.n_views, cfg.max_poses = n_clips, n_views, max_poses
         cfg.max_tracks = max_tracks if max_tracks is not None else min(64, 2 * max_poses)
-        cfg.max_new = max_new if max_new is not None else min(32, max(4, max_poses))
+        cfg.max_new = max_new if max_new is not None else min(64, max(4, 2 * max_poses))
         cfg.n_inits, cfg.max_age, cfg.nfev_update, cfg.nfev_birth = n_inits, max_age, nfev_update, nfev_birth
         self.cfg = cfg
         self.B, self.C, self.Pmax, self.Tmax = n_clips, n_views, max_poses, cfg.max_tracks

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(32)
     k_assign(const uint32_t* __restrict__ xbin, const int* __restrict__ dim_groups, const int* __restrict__ idx_view,
              const int* __restrict__ idx_pose, const int* __restrict__ n_trk, int C, int N, int Tmax, int max_new,
              int* __restrict__ trk_nsel, int* __restrict__ trk_sel, int* __restrict__ new_n, int* __restrict__ new_nsel,
-             int* __restrict__ new_sel, int* __restrict__ n_dup, int* __restrict__ err) {
+             int* __restrict__ new_sel, int* __restrict__ counts, int* __restrict__ err) {
     const int b = blockIdx.x, lane = threadIdx.x;
     const int NW = (N + 31) / 32;
     const int n = dim_groups[b * (C + 2) + C + 1];
@@ -289,21 +289,18 @@ __global__ void __launch_bounds__(32)
     int* ns = new_sel + (size_t)b * max_new * MVMC_MAX_SEL * 2;
     // members[c] (bit rows) of the kept leader columns are re-derived on the fly; we only need, per
     // leader c, temp[c] = X[c] | (X[c][n-1] ? X[n-1] : 0).
-    __shared__ uint32_t s_leader[32];   // leader flags as bitset (N <= 1024)
     __shared__ int s_members[MVMC_MAX_TRACKS + MVMC_MAX_VIEWS * MVMC_MAX_POSES];
     for (int t = lane; t < Tmax; t += 32) tn[t] = -1;
     if (lane == 0) {
         new_n[b] = 0;
-        n_dup[b] = 0;
+        for (int q = 0; q < 4; q++) counts[4 * b + q] = 0;
         err[b] = 0;
     }
-    s_leader[lane] = 0;
-    __syncwarp();
     if (n <= 0) return;
     const uint32_t last_row = (lane < NW) ? xb[(size_t)(n - 1) * NW + lane] : 0u;
     uint32_t vis = 0;       // this lane's word of `vis`
     uint32_t assigned = 0;  // this lane's word of "row already attached to a kept column"
-    int n_new = 0, dup = 0, error = 0;
+    int n_new = 0, dup = 0, error = 0, n_single = 0, n_trunc = 0;
     const bool has_trk = T > 0;
     for (int i = 0; i < n; i++) {
         const uint32_t vw = __shfl_sync(MVMC_FULL, vis, i >> 5);
@@ -344,6 +341,7 @@ __global__ void __launch_bounds__(32)
             int sel[MVMC_MAX_SEL][2];
             int nsel = 0;
             uint32_t seen_views = 0;
+            bool over = false;
             for (int q = 0; q < base; q++) {
                 const int g = s_members[q];
                 if (has_trk && g < T) continue;
@@ -360,9 +358,10 @@ __global__ void __launch_bounds__(32)
                     sel[nsel][1] = ip[g];
                     nsel++;
                 } else {
-                    error = MVMC_ERR_CAPACITY;
+                    over = true;  // keep the first MVMC_MAX_SEL poses (include/mvmc.h: n_truncated)
                 }
             }
+            if (over) n_trunc++;
             if (nsel > 0) {
                 if (t_idx >= 0) {
                     tn[t_idx] = nsel;
@@ -370,6 +369,8 @@ __global__ void __launch_bounds__(32)
                         ts[(t_idx * MVMC_MAX_SEL + q) * 2] = sel[q][0];
                         ts[(t_idx * MVMC_MAX_SEL + q) * 2 + 1] = sel[q][1];
                     }
+                } else if (nsel < 2) {
+                    n_single++;  // a 2D-only group the one-pose-per-view rule shrank to one pose: never born
                 } else if (n_new < max_new) {
                     nn_[n_new] = nsel;
                     for (int q = 0; q < nsel; q++) {
@@ -386,7 +387,9 @@ __global__ void __launch_bounds__(32)
     }
     if (lane == 0) {
         new_n[b] = n_new;
-        n_dup[b] = dup;
+        counts[4 * b] = dup;
+        counts[4 * b + 1] = n_single;
+        counts[4 * b + 2] = n_trunc;
         err[b] = error;
     }
 }
@@ -419,15 +422,15 @@ extern "C" int mvmc_match_als(const double* sim, const int* dim_groups, int n_gr
 
 extern "C" int mvmc_assign(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose,
                            const int* n_trk, int B, int C, int N, int Tmax, int max_new, int* trk_nsel, int* trk_sel,
-                           int* new_n, int* new_nsel, int* new_sel, int* n_dup, int* err, void* stream) {
+                           int* new_n, int* new_nsel, int* new_sel, int* counts, int* err, void* stream) {
     if (!xbin || !dim_groups || !idx_view || !idx_pose || !n_trk || !trk_nsel || !trk_sel || !new_n || !new_nsel ||
-        !new_sel || !n_dup || !err)
+        !new_sel || !counts || !err)
         return MVMC_ERR_INVALID;
     if (B <= 0 || N <= 0 || N > 1024 || C <= 0 || C > MVMC_MAX_VIEWS || Tmax < 0 || Tmax > MVMC_MAX_TRACKS ||
         max_new <= 0)
         return MVMC_ERR_INVALID;
     MVMC_LAUNCH(k_assign, dim3(B), dim3(32), 0, stream, xbin, dim_groups, idx_view, idx_pose, n_trk, C, N, Tmax, max_new,
-                trk_nsel, trk_sel, new_n, new_nsel, new_sel, n_dup, err);
+                trk_nsel, trk_sel, new_n, new_nsel, new_sel, counts, err);
     MVMC_CHECK_LAUNCH("k_assign");
     return MVMC_OK;
 }

@@ -262,6 +262,7 @@ struct TriRes {
         const int v = ch >> 1, k0 = (ch & 1) * half(), k1 = k0 + chunk_rows(ch);
         for (int c = lane; c < ncol; c += 32) {
             const int prm = s.act[c], k = prm / 3, comp = prm % 3;
+            for (int r = 0; r < k1 - k0; r++) s.Jc[r * WS_LDJ + c] = 0.0;   // (the other half-view's entry is stale)
             if (k < k0 || k >= k1) continue;   // a point only moves its own residual rows
             double X[3] = {s.x[3 * k], s.x[3 * k + 1], s.x[3 * k + 2]};
             X[comp] = s.w[c];

@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(128)
         rec.n_died = n_died;
         rec.n_total = dim_groups[b * (C + 2) + C + 1];
         rec.als_iters = als_iter[b];
-        rec.n_dup_view = n_dup[b];
+        rec.n_dup_view = n_dup[4 * b];
+        rec.n_truncated = n_dup[4 * b + 2];
         rec.error = error;
         // algorithmic work counters: ALS flops = I (6 r n^2 + 8 r^2 n + 4 r^3)
         const int* dg = dim_groups + b * (C + 2);
@@ -444,7 +445,7 @@ extern "C" int mvmc_clips_create(const mvmc_config* cfg, mvmc_clips** out) {
     if (!cfg || !out) return MVMC_ERR_INVALID;
     if (cfg->n_clips <= 0 || cfg->n_views <= 0 || cfg->n_views > MVMC_MAX_VIEWS || cfg->max_poses <= 0 ||
         cfg->max_poses > MVMC_MAX_POSES || cfg->max_tracks <= 0 || cfg->max_tracks > MVMC_MAX_TRACKS || cfg->max_new <= 0 ||
-        cfg->max_new > 32 || cfg->nfev_update < 1 || cfg->nfev_birth < 1)
+        cfg->max_new > 64 || cfg->nfev_update < 1 || cfg->nfev_birth < 1)
         return MVMC_ERR_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return MVMC_ERR_NO_DEVICE;
@@ -506,7 +507,7 @@ extern "C" int mvmc_clips_create(const mvmc_config* cfg, mvmc_clips** out) {
     TRY(h->alloc(&h->new_n, (size_t)B));
     TRY(h->alloc(&h->new_nsel, (size_t)B * cfg->max_new));
     TRY(h->alloc(&h->new_sel, (size_t)B * cfg->max_new * MVMC_MAX_SEL * 2));
-    TRY(h->alloc(&h->n_dup, (size_t)B));
+    TRY(h->alloc(&h->n_dup, (size_t)B * 4));
     TRY(h->alloc(&h->assign_err, (size_t)B));
     TRY(h->alloc(&h->w_kps, M * MVMC_MAX_SEL * MVMC_N_COCO * 3));
     TRY(h->alloc(&h->w_P, M * MVMC_MAX_SEL * 12));

@@ -6,7 +6,7 @@
 //
 // ONE WARP PER SOLVE, no block barrier anywhere:
 //   * lanes own Jacobian columns (one perturbed model evaluation each),
-//   * J^T J is accumulated view by view from a 32-row chunk of J staged in shared memory, 8x8 register tiles
+//   * J^T J is accumulated view by view from a 16-row chunk of J staged in shared memory, 8x8 register tiles
 //     (lane = tile of the lower triangle, 64 DFMA per 16 doubles loaded),
 //   * instead of SciPy's SVD of J, J^T J = Q T Q^T is reduced ONCE per Jacobian to tridiagonal form by Householder
 //     reflections; every evaluation of the secular function phi(alpha) = ||(J^T J + alpha I)^-1 g|| - Delta and of
@@ -295,11 +295,17 @@ __device__ double trf_subproblem(TrfWarp& s, int n, double delta, double alpha, 
             dmax = fmax(dmax, fabs(s.d[i]));
         }
         const double floor_ = kEps * kEps * fmax(dmax, 1e-300);  // only guards against non-positive pivots
+        // SciPy works from singular values, so exactly rank-deficient directions (s = 0, s*uf = 0) drop out even when the
+        // Moré iteration ends at alpha ~ 0 (e.g. the 2-view triangulation refine, where phi(alpha) < 0 for every alpha and
+        // the pseudo-inverse step gets stretched to the radius). J^T J + alpha I has no such luxury: keep the linear algebra
+        // numerically positive definite with a floor on alpha far below anything the data resolves (16 eps lambda_max),
+        // which turns the alpha -> 0 limit into the same pseudo-inverse step. The iteration on alpha itself is unchanged.
+        const double amin = 16.0 * kEps * dmax;
         bool done = false;
         double scale_to = 0.0;
         double a_lo = 0.0, a_hi = sqrt(gn2) / delta;
         if (full_rank) {
-            const bool pd = tri_factor(s, n, 0.0, floor_);
+            const bool pd = tri_factor(s, n, amin, floor_);
             const double nn = tri_solve(s, n, s.gt, s.yy);
             if (pd && sqrt(nn) <= delta) {
                 alpha = 0.0;
@@ -316,7 +322,7 @@ __device__ double trf_subproblem(TrfWarp& s, int n, double delta, double alpha, 
             if (!full_rank && alpha == 0.0) alpha = fmax(0.001 * a_hi, sqrt(a_lo * a_hi));
             for (int it = 0; it < 10; it++) {
                 if (alpha < a_lo || alpha > a_hi) alpha = fmax(0.001 * a_hi, sqrt(a_lo * a_hi));
-                tri_factor(s, n, alpha, floor_);
+                tri_factor(s, n, fmax(alpha, amin), floor_);
                 const double pn = sqrt(tri_solve(s, n, s.gt, s.yy));
                 const double q = tri_quad(s, n, s.yy, s.zz);
                 const double phi = pn - delta, dphi = -q / pn;
@@ -326,7 +332,7 @@ __device__ double trf_subproblem(TrfWarp& s, int n, double delta, double alpha, 
                 alpha -= (phi + delta) * ratio / delta;
                 if (fabs(phi) < 0.01 * delta) break;
             }
-            tri_factor(s, n, alpha, floor_);
+            tri_factor(s, n, fmax(alpha, amin), floor_);
             tri_solve(s, n, s.gt, s.yy);
             scale_to = delta;
         }

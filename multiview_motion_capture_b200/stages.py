@@ -109,10 +109,10 @@ def assign(xbin, prep, n_trk, C, max_new):
     dev = xbin.device
     z = lambda *s: torch.zeros(s, dtype=i32, device=dev)
     out = dict(trk_nsel=z(B, max(Tmax, 1)), trk_sel=z(B, max(Tmax, 1), MAX_SEL, 2), new_n=z(B), new_nsel=z(B, max_new),
-               new_sel=z(B, max_new, MAX_SEL, 2), n_dup=z(B), err=z(B))
+               new_sel=z(B, max_new, MAX_SEL, 2), counts=z(B, 4), err=z(B))
     check(_lib.get_lib().mvmc_assign(ptr(xbin), ptr(prep["dim_groups"]), ptr(prep["idx_view"]), ptr(prep["idx_pose"]),
                                      ptr(n_trk), B, C, N, Tmax, max_new, ptr(out["trk_nsel"]), ptr(out["trk_sel"]),
-                                     ptr(out["new_n"]), ptr(out["new_nsel"]), ptr(out["new_sel"]), ptr(out["n_dup"]),
+                                     ptr(out["new_n"]), ptr(out["new_nsel"]), ptr(out["new_sel"]), ptr(out["counts"]),
                                      ptr(out["err"]), _stream(xbin)), "mvmc_assign")
     return out
 

@@ -15,7 +15,7 @@ def run_golden_clip(dev, name, Pmax, Tmax, forced, B=1, max_new=8, frames=None):
     cb = ClipBatch(B, C, Pmax, max_tracks=Tmax, max_new=max_new, device=dev)
     cb.set_calib(np.repeat(inp["K"][None], B, 0), np.repeat(inp["RT"][None], B, 0))
     tab = GoldenTable(g)
-    st = dict(frames=0, xbin=0, iters=0, alive=0, upd=0, matches=0, dj=[], replicas=0)
+    st = dict(frames=0, xbin=0, iters=0, alive=0, n_alive=0, upd=0, dj=[], replicas=0, first_mismatch=10 ** 9)
     for f in (frames or range(int(g["first_frame"]), int(g["last_frame"]) + 1)):
         k = fkey(f)
         if forced:
@@ -31,6 +31,9 @@ def run_golden_clip(dev, name, Pmax, Tmax, forced, B=1, max_new=8, frames=None):
         st["xbin"] += int(same_x)
         st["iters"] += int(rec["als_iters"] == int(g[k + "als_iters"]))
         st["alive"] += int(tr["track_id"].tolist() == g[k + "alive_after"].tolist())
+        st["n_alive"] += int(n_alive == len(g[k + "alive_after"]))
+        if not (same_x and tr["track_id"].tolist() == g[k + "alive_after"].tolist()):
+            st["first_mismatch"] = min(st["first_mismatch"], f)
         same_upd = upd["track_id"].tolist() == g[k + "upd_ids"].tolist()
         st["upd"] += int(same_upd)
         if forced:
@@ -42,7 +45,7 @@ def run_golden_clip(dev, name, Pmax, Tmax, forced, B=1, max_new=8, frames=None):
             assert same_upd, (name, f)
             # the (view, pose) pairs each updated track was solved from
             for u, t in enumerate(upd):
-                views = sorted(int(v) for v in t["sel"][:t["n_sel"], 0])
+                views = sorted({int(v) for v in t["sel"][:t["n_sel"], 0]})   # no-track groups may hold >1 pose per view
                 assert views == np.nonzero(g[k + "upd_views"][u])[0].tolist(), (name, f, u)
         if same_upd and len(upd):
             st["dj"].extend(np.abs(upd["joints"].reshape(-1, 18, 3) - g[k + "upd_joints"]).max(axis=(1, 2)).tolist())

