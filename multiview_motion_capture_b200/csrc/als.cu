@@ -1,77 +1,178 @@
-// ALS/ADMM low-rank multi-way matcher + closure/parse/decode.
+// ALS/ADMM low-rank multi-way matcher (the reference's live association solver).
 //
-// Reference rows: A5 mv_association.py:222-318 (match_als),
-// A6 mv_association.py:99-121 (transform_closure) + motion_capture.py:417-446 (parse_match_result)
-// + motion_capture.py:762-808 / :618-624 (group decoding).
+// Reference row: A5 mv_association.py:222-318 (match_als). Per iteration
+//     Xt = Z - (Y - W + beta)/mu;  B = (inv(A^T A + a/mu I) A^T Xt)^T;  A = (inv(B^T B + a/mu I) B^T Xt^T)^T;
+//     X = A B^T;  Z = clip(X + Y/mu) with same-group blocks zeroed and unit diagonal;  Y += mu (X - Z)
+// until ||X - Z||_F / n < tol and mu ||X - X_prev||_F / n < tol, mu doubled / halved on a 10x imbalance.
 //
-// k_als: ONE CTA PER INSTANCE (clip-frame). All iterates (W,Z,Y,Xt,X: n x n; A,B: n x r) live in a
-// per-instance global workspace that stays L2-resident (<= 4.6 MB at n=320); the r x r normal matrix
-// is inverted in shared memory. The three n*n*r products per iteration are FP64 CUDA-core tiled GEMMs
-// (64x64 tile, 4x4 per thread) — this stage is DFMA-issue bound, not HBM bound.
+// k_als: ONE CTA (6 warps) PER CLIP-FRAME, 3 resident CTAs per SM. The n x n iterates (W, Z, Y, X, Xt) and the
+// n x r factors live in a per-clip global workspace; the seven products of an iteration (three of them 2 r n^2
+// flops: the dominant cost of the whole capture path) run as tiled FP64 tensor-core GEMMs:
+//   * CTA tile 64 x 96, k-chunks of 16 staged in shared memory by 16-byte cp.async (LDGSTS) with zero fill, double buffered;
+//   * each warp owns 16 output columns x up to 8 row tiles and issues mma.sync.m8n8k4.f64 (DMMA) from conflict-free
+//     fragment loads (row strides chosen so the 4 x 8 fragment footprint covers every bank once);
+//   * the Z / Y / X / next-Xt update and both residual norms are the epilogue of the X = A B^T product, so an
+//     iteration makes three passes over n x n data (Xt twice, the epilogue's X, Y, W once) instead of seven;
+//   * Xt for the next iteration is written by that epilogue assuming mu stays (it changes a handful of times per
+//     solve; then one element-wise pass rebuilds Xt from Z, Y, W with the new mu) - same arithmetic, same values.
+// FP64 DMMA and DFMA have the same peak on B200 (37 TFLOP/s measured, tools/micro/dmma_probe.cu); DMMA is used because it
+// needs 8x fewer issue slots and 4x less shared-memory bandwidth per flop, which is what bounds a small-tile GEMM.
 #include "mvmc_common.cuh"
 
 namespace mvmc {
 
-constexpr int ALS_TS = 64;
-constexpr int ALS_KC = 16;
-constexpr int ALS_LD = ALS_TS + 2;
-constexpr int ALS_THREADS = 256;
+constexpr int AL_THREADS = 192;
+constexpr int AL_WARPS = 6;
+constexpr int AL_KC = 16;                 // k-chunk
+constexpr int AL_TM = 64;                 // CTA tile rows
+constexpr int AL_TN = 96;                 // CTA tile columns (6 warps x 16)
+constexpr int AL_SKM = AL_TM + 8;         // k-major tile row stride, M operand  (= 64 B mod 128 B)
+constexpr int AL_SKN = AL_TN + 8;         // k-major tile row stride, N operand
+constexpr int AL_SI = AL_KC + 4;          // i-major tile row stride               (= 32 B mod 128 B)
+constexpr int AL_STAGE_M = (AL_KC * AL_SKM > AL_TM * AL_SI) ? AL_KC * AL_SKM : AL_TM * AL_SI;   // doubles
+constexpr int AL_STAGE_N = (AL_KC * AL_SKN > AL_TN * AL_SI) ? AL_KC * AL_SKN : AL_TN * AL_SI;
+constexpr int AL_STAGE = AL_STAGE_M + AL_STAGE_N;
+constexpr int AL_POOL = 8192;             // doubles of shared memory shared by the two stages and the r x r inverse
+constexpr int AL_RSMEM = 88;              // largest r whose normal matrix is inverted in shared memory
+static_assert(2 * AL_STAGE <= AL_POOL, "stages must fit the pool");
+static_assert(AL_RSMEM * (AL_RSMEM + 1) <= AL_POOL, "inverse must fit the pool");
 
-// S[kk][ii] = src[(k0+kk)*ld + (i0+ii)]  (ii contiguous in memory)
-__device__ __forceinline__ void load_kmajor(double* S, const double* __restrict__ src, int ld, int i0, int k0, int I,
-                                            int K) {
-    const int ii = threadIdx.x & 63;
-    for (int kk = threadIdx.x >> 6; kk < ALS_KC; kk += 4) {
-        const int k = k0 + kk, i = i0 + ii;
-        S[kk * ALS_LD + ii] = (k < K && i < I) ? src[(size_t)k * ld + i] : 0.0;
+// ---- asynchronous 16-byte global -> shared copies with zero fill ----
+__device__ __forceinline__ void cp16(double* dst, const double* src, int n_valid /*0,1,2 doubles*/) {
+#ifdef MVMC_EMU
+    dst[0] = n_valid > 0 ? src[0] : 0.0;
+    dst[1] = n_valid > 1 ? src[1] : 0.0;
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int bytes = n_valid * 8;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_commit() {
+#ifndef MVMC_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+#ifndef MVMC_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+// D(8x8) += A(8x4) * B(4x8): lane holds a = A[lane/4][lane%4], b = B[lane%4][lane/4], c0/c1 = C[lane/4][2*(lane%4) + {0,1}]
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+#ifdef MVMC_EMU
+    emu::dmma_884(c0, c1, a, b);
+#else
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+#endif
+}
+
+// An operand of a product, seen as element(k, i), 0 <= k < K (contraction index), 0 <= i < I.
+struct Operand {
+    const double* p;
+    int ld;
+    int I;
+    bool kmajor;   // true: element(k, i) = p[k*ld + i];  false: element(k, i) = p[i*ld + k]
+};
+
+// Stage the [k0, k0+KC) x [i0, i0+TI) block of `op` into shared memory (zero filled outside K x I).
+template <int TI>
+__device__ __forceinline__ void stage_operand(double* S, const Operand& op, int i0, int k0, int K) {
+    constexpr int SK = TI + 8;
+    if (op.kmajor) {
+        // S[kk*SK + ii], 16-byte pieces along i
+        for (int e = threadIdx.x; e < AL_KC * (TI / 2); e += AL_THREADS) {
+            const int kk = e / (TI / 2), ii = (e % (TI / 2)) * 2;
+            const int k = k0 + kk, i = i0 + ii;
+            int nv = (k < K) ? op.I - i : 0;
+            nv = nv < 0 ? 0 : (nv > 2 ? 2 : nv);
+            cp16(S + kk * SK + ii, nv > 0 ? op.p + (size_t)k * op.ld + i : op.p, nv);
+        }
+    } else {
+        // S[ii*SI + kk], 16-byte pieces along k
+        for (int e = threadIdx.x; e < TI * (AL_KC / 2); e += AL_THREADS) {
+            const int ii = e / (AL_KC / 2), kk = (e % (AL_KC / 2)) * 2;
+            const int k = k0 + kk, i = i0 + ii;
+            int nv = (i < op.I) ? K - k : 0;
+            nv = nv < 0 ? 0 : (nv > 2 ? 2 : nv);
+            cp16(S + ii * AL_SI + kk, nv > 0 ? op.p + (size_t)i * op.ld + k : op.p, nv);
+        }
     }
 }
-// S[kk][ii] = src[(i0+ii)*ld + (k0+kk)]  (kk contiguous in memory)
-__device__ __forceinline__ void load_imajor(double* S, const double* __restrict__ src, int ld, int i0, int k0, int I,
-                                            int K) {
-    const int kk = threadIdx.x & 15;
-    for (int ii = threadIdx.x >> 4; ii < ALS_TS; ii += 16) {
-        const int k = k0 + kk, i = i0 + ii;
-        S[kk * ALS_LD + ii] = (k < K && i < I) ? src[(size_t)i * ld + k] : 0.0;
-    }
+
+template <int TI>
+__device__ __forceinline__ double frag(const double* S, bool kmajor, int i8, int kk, int lane) {
+    // element(k = kk + lane%4, i = i8 + lane/4)
+    return kmajor ? S[(kk + (lane & 3)) * (TI + 8) + i8 + (lane >> 2)] : S[(i8 + (lane >> 2)) * AL_SI + kk + (lane & 3)];
 }
 
-template <class LA, class LB, class EP>
-__device__ __forceinline__ void gemm_tiles(int M, int N, int K, LA la, LB lb, EP ep, double* As, double* Bs) {
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    for (int m0 = 0; m0 < M; m0 += ALS_TS)
-        for (int n0 = 0; n0 < N; n0 += ALS_TS) {
-            double acc[4][4];
+// C[m][n] = sum_k Mop(k, m) * Nop(k, n) for m < Mop.I, n < Nop.I; ep(m, n, v0, v1) receives C[m][n], C[m][n+1]
+// (n even; the caller guards n+1 < N). All threads of the CTA must call it. `pool` holds the two stages.
+template <class EP>
+__device__ void cta_gemm(const Operand& Mop, const Operand& Nop, int K, double* pool, EP ep) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int M = Mop.I, N = Nop.I;
+    const int nk = (K + AL_KC - 1) / AL_KC;
+    for (int m0 = 0; m0 < M; m0 += AL_TM) {
+        const int mt = min(8, (M - m0 + 7) >> 3);           // live row tiles of this CTA tile
+        for (int n0 = 0; n0 < N; n0 += AL_TN) {
+            const int nw0 = n0 + warp * 16;                   // this warp's 16 columns
+            const int nt = nw0 >= N ? 0 : min(2, (N - nw0 + 7) >> 3);
+            double acc[8][2][2];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+            for (int a = 0; a < 8; a++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
-            for (int k0 = 0; k0 < K; k0 += ALS_KC) {
-                la(As, m0, k0);
-                lb(Bs, n0, k0, m0);
+                for (int b = 0; b < 2; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+            __syncthreads();   // the pool may still be read by the previous tile / another phase
+            stage_operand<AL_TM>(pool, Mop, m0, 0, K);
+            stage_operand<AL_TN>(pool + AL_STAGE_M, Nop, n0, 0, K);
+            cp_commit();
+            for (int kc = 0; kc < nk; kc++) {
+                double* cur = pool + (kc & 1) * AL_STAGE;
+                if (kc + 1 < nk) {
+                    double* nxt = pool + ((kc + 1) & 1) * AL_STAGE;
+                    stage_operand<AL_TM>(nxt, Mop, m0, (kc + 1) * AL_KC, K);
+                    stage_operand<AL_TN>(nxt + AL_STAGE_M, Nop, n0, (kc + 1) * AL_KC, K);
+                    cp_commit();
+                    cp_wait<1>();
+                } else {
+                    cp_wait<0>();
+                }
                 __syncthreads();
+                if (nt > 0) {
+                    const double* Sm = cur;
+                    const double* Sn = cur + AL_STAGE_M;
 #pragma unroll
-                for (int kk = 0; kk < ALS_KC; kk++) {
-                    double a[4], b[4];
+                    for (int kk = 0; kk < AL_KC; kk += 4) {
+                        const double b0 = frag<AL_TN>(Sn, Nop.kmajor, warp * 16, kk, lane);
+                        const double b1 = nt > 1 ? frag<AL_TN>(Sn, Nop.kmajor, warp * 16 + 8, kk, lane) : 0.0;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) a[i] = As[kk * ALS_LD + ty * 4 + i];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) b[j] = Bs[kk * ALS_LD + tx * 4 + j];
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-#pragma unroll
-                        for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                        for (int a = 0; a < 8; a++) {
+                            if (a < mt) {
+                                const double av = frag<AL_TM>(Sm, Mop.kmajor, a * 8, kk, lane);
+                                dmma(acc[a][0][0], acc[a][0][1], av, b0);
+                                if (nt > 1) dmma(acc[a][1][0], acc[a][1][1], av, b1);
+                            }
+                        }
+                    }
                 }
                 __syncthreads();
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+            for (int a = 0; a < 8; a++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int m = m0 + ty * 4 + i, nn = n0 + tx * 4 + j;
-                    if (m < M && nn < N) ep(m, nn, acc[i][j]);
+                for (int b = 0; b < 2; b++) {
+                    if (a < mt && b < nt) {
+                        const int m = m0 + a * 8 + (lane >> 2), n = nw0 + b * 8 + 2 * (lane & 3);
+                        if (m < M && n < N) ep(m, n, acc[a][b][0], acc[a][b][1]);
+                    }
                 }
         }
+    }
 }
 
 // In-place inverse of the SPD r x r matrix G (leading dimension ldg) by Gauss-Jordan without pivoting.
@@ -95,7 +196,33 @@ __device__ void invert_spd(double* G, int r, int ldg) {
     }
 }
 
-__global__ void __launch_bounds__(ALS_THREADS)
+// Gg (r x r, ld ldr, global) <- inverse of Gg; through shared memory when it fits
+__device__ void invert_normal_matrix(double* Gg, int r, int ldr, double* pool) {
+    __syncthreads();
+    if (r <= AL_RSMEM) {
+        const int ldg = r + 1;
+        for (int e = threadIdx.x; e < r * r; e += blockDim.x) pool[(e / r) * ldg + (e % r)] = Gg[(size_t)(e / r) * ldr + (e % r)];
+        __syncthreads();
+        invert_spd(pool, r, ldg);
+        for (int e = threadIdx.x; e < r * r; e += blockDim.x) Gg[(size_t)(e / r) * ldr + (e % r)] = pool[(e / r) * ldg + (e % r)];
+    } else {
+        invert_spd(Gg, r, ldr);
+    }
+    __syncthreads();
+}
+
+struct AlsLayout {
+    int N, ldn, ldr;
+    size_t per;
+    __host__ __device__ AlsLayout(int N_, int rmax) {
+        N = N_;
+        ldn = (N_ + 7) & ~7;
+        ldr = (rmax + 7) & ~7;
+        per = (size_t)5 * N * ldn + (size_t)2 * N * ldr + (size_t)ldr * ldn + (size_t)ldr * ldr;
+    }
+};
+
+__global__ void __launch_bounds__(AL_THREADS, 3)
     k_als(const double* __restrict__ sim, const int* __restrict__ dim_groups, int n_groups,
           const int* __restrict__ f32_first_iter, const double* __restrict__ rand_stream, int N, int rmax,
           double* __restrict__ ws, uint32_t* __restrict__ xbin, int* __restrict__ n_iter_out, double alpha, double beta,
@@ -114,23 +241,22 @@ __global__ void __launch_bounds__(ALS_THREADS)
     for (int g = 0; g < n_groups; g++) maxsz = max(maxsz, dg[g + 1] - dg[g]);
     int r = min(n, 2 * maxsz);
     r = min(r, rmax);
-    const int ldg = r + 1;
 
-    double* As = smem;
-    double* Bs = As + ALS_KC * ALS_LD;
-    double* Gs = Bs + ALS_KC * ALS_LD;
-    double* scratch = Gs + rmax * (rmax + 1);
-    int* s_grp = reinterpret_cast<int*>(scratch + 32);
+    double* pool = smem;                       // [AL_POOL] stages / inverse
+    double* scratch = pool + AL_POOL;          // [32]
+    int* s_grp = reinterpret_cast<int*>(scratch + 32);   // [N]
 
-    const size_t per = (size_t)5 * N * N + (size_t)3 * N * rmax;
-    double* W = ws + (size_t)b * per;
-    double* Z = W + (size_t)N * N;
-    double* Y = Z + (size_t)N * N;
-    double* Xt = Y + (size_t)N * N;
-    double* Xm = Xt + (size_t)N * N;
-    double* A = Xm + (size_t)N * N;
-    double* Bm = A + (size_t)N * rmax;
-    double* Tm = Bm + (size_t)N * rmax;
+    const AlsLayout L(N, rmax);
+    const int ldn = L.ldn, ldr = L.ldr;
+    double* W = ws + (size_t)b * L.per;
+    double* Z = W + (size_t)N * ldn;
+    double* Y = Z + (size_t)N * ldn;
+    double* Xm = Y + (size_t)N * ldn;
+    double* Xt = Xm + (size_t)N * ldn;
+    double* A = Xt + (size_t)N * ldn;          // [n][ldr]
+    double* Bm = A + (size_t)N * ldr;          // [n][ldr]
+    double* Tm = Bm + (size_t)N * ldr;         // [r][ldn]
+    double* Gg = Tm + (size_t)ldr * ldn;       // [r][ldr]
 
     const double* S = sim + (size_t)b * N * N;
     const bool f32 = f32_first_iter != nullptr && f32_first_iter[b] != 0;
@@ -138,107 +264,97 @@ __global__ void __launch_bounds__(ALS_THREADS)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         int g = 0;
         for (int q = 0; q < n_groups; q++)
-            if (dg[q] <= i) g = q;  // last group whose offset is <= i (empty groups share an offset)
-        // an index belongs to the group whose [start,end) contains it
-        for (int q = 0; q < n_groups; q++)
-            if (i >= dg[q] && i < dg[q + 1]) g = q;
+            if (i >= dg[q] && i < dg[q + 1]) g = q;  // an index belongs to the group whose [start, end) contains it
         s_grp[i] = g;
     }
+    double mu = 64.0;
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
         const int i = e / n, j = e % n;
+        const size_t o = (size_t)i * ldn + j;
         double w;
         if (f32) w = (double)(0.5f * ((float)S[(size_t)i * N + j] + (float)S[(size_t)j * N + i]));
         else w = 0.5 * (S[(size_t)i * N + j] + S[(size_t)j * N + i]);
-        W[e] = w;
-        Z[e] = w;
-        Xm[e] = w;
-        Y[e] = 0.0;
+        W[o] = w;
+        Z[o] = w;
+        Xm[o] = w;
+        Y[o] = 0.0;
+        // first Xt (Z = W, Y = 0); the float32 no-track path of the reference keeps float32 through this expression
+        if (f32) Xt[o] = (double)((float)w - ((0.0f - (float)w) + (float)beta) / (float)mu);
+        else Xt[o] = w - (0.0 - w + beta) / mu;
     }
-    for (int e = threadIdx.x; e < n * r; e += blockDim.x) A[e] = rand_stream[e];
+    for (int e = threadIdx.x; e < n * r; e += blockDim.x) A[(size_t)(e / r) * ldr + (e % r)] = rand_stream[e];
     __syncthreads();
 
-    double mu = 64.0;
     int it = 0;
     for (it = 0; it < max_iter; it++) {
         const double reg = alpha / mu;
-        const bool first_f32 = f32 && it == 0;
-        // ---- G = A^T A + reg I ----
-        gemm_tiles(r, r, n,
-                   [&](double* Sm, int m0, int k0) { load_kmajor(Sm, A, r, m0, k0, r, n); },
-                   [&](double* Sm, int n0, int k0, int) { load_kmajor(Sm, A, r, n0, k0, r, n); },
-                   [&](int m, int nn, double v) { Gs[m * ldg + nn] = (m == nn) ? v + reg * 1.0 : v + reg * 0.0; }, As,
-                   Bs);
-        __syncthreads();
-        invert_spd(Gs, r, ldg);
-        // ---- T = A^T Xt, with Xt = Z - (Y - W + beta)/mu formed on the fly (and stored once) ----
-        gemm_tiles(r, n, n,
-                   [&](double* Sm, int m0, int k0) { load_kmajor(Sm, A, r, m0, k0, r, n); },
-                   [&](double* Sm, int n0, int k0, int m0) {
-                       const int ii = threadIdx.x & 63;
-                       for (int kk = threadIdx.x >> 6; kk < ALS_KC; kk += 4) {
-                           const int k = k0 + kk, i = n0 + ii;
-                           double v = 0.0;
-                           if (k < n && i < n) {
-                               const size_t o = (size_t)k * n + i;
-                               if (first_f32)
-                                   v = (double)((float)Z[o] - (((float)Y[o] - (float)W[o]) + (float)beta) / (float)mu);
-                               else
-                                   v = Z[o] - (Y[o] - W[o] + beta) / mu;
-                               if (m0 == 0) Xt[o] = v;
-                           }
-                           Sm[kk * ALS_LD + ii] = v;
-                       }
-                   },
-                   [&](int m, int nn, double v) { Tm[(size_t)m * n + nn] = v; }, As, Bs);
+        // ---- G = A^T A + reg I, inverted ----
+        {
+            const Operand opA{A, ldr, r, true};
+            cta_gemm(opA, opA, n, pool, [&](int m, int nn, double v0, double v1) {
+                Gg[(size_t)m * ldr + nn] = (m == nn) ? v0 + reg * 1.0 : v0 + reg * 0.0;
+                if (nn + 1 < r) Gg[(size_t)m * ldr + nn + 1] = (m == nn + 1) ? v1 + reg * 1.0 : v1 + reg * 0.0;
+            });
+        }
+        invert_normal_matrix(Gg, r, ldr, pool);
+        // ---- T = A^T Xt ----
+        cta_gemm(Operand{A, ldr, r, true}, Operand{Xt, ldn, n, true}, n, pool, [&](int m, int nn, double v0, double v1) {
+            Tm[(size_t)m * ldn + nn] = v0;
+            if (nn + 1 < n) Tm[(size_t)m * ldn + nn + 1] = v1;
+        });
         __syncthreads();
         // ---- B = (Ginv T)^T ----
-        gemm_tiles(r, n, r,
-                   [&](double* Sm, int m0, int k0) { load_kmajor(Sm, Gs, ldg, m0, k0, r, r); },
-                   [&](double* Sm, int n0, int k0, int) { load_kmajor(Sm, Tm, n, n0, k0, n, r); },
-                   [&](int m, int nn, double v) { Bm[(size_t)nn * r + m] = v; }, As, Bs);
+        cta_gemm(Operand{Gg, ldr, r, false}, Operand{Tm, ldn, n, true}, r, pool, [&](int m, int nn, double v0, double v1) {
+            Bm[(size_t)nn * ldr + m] = v0;
+            if (nn + 1 < n) Bm[(size_t)(nn + 1) * ldr + m] = v1;
+        });
         __syncthreads();
-        // ---- H = B^T B + reg I ----
-        gemm_tiles(r, r, n,
-                   [&](double* Sm, int m0, int k0) { load_kmajor(Sm, Bm, r, m0, k0, r, n); },
-                   [&](double* Sm, int n0, int k0, int) { load_kmajor(Sm, Bm, r, n0, k0, r, n); },
-                   [&](int m, int nn, double v) { Gs[m * ldg + nn] = (m == nn) ? v + reg : v; }, As, Bs);
-        __syncthreads();
-        invert_spd(Gs, r, ldg);
+        // ---- H = B^T B + reg I, inverted ----
+        {
+            const Operand opB{Bm, ldr, r, true};
+            cta_gemm(opB, opB, n, pool, [&](int m, int nn, double v0, double v1) {
+                Gg[(size_t)m * ldr + nn] = (m == nn) ? v0 + reg : v0;
+                if (nn + 1 < r) Gg[(size_t)m * ldr + nn + 1] = (m == nn + 1) ? v1 + reg : v1;
+            });
+        }
+        invert_normal_matrix(Gg, r, ldr, pool);
         // ---- T = B^T Xt^T : T[m][i] = sum_j B[j][m] Xt[i][j] ----
-        gemm_tiles(r, n, n,
-                   [&](double* Sm, int m0, int k0) { load_kmajor(Sm, Bm, r, m0, k0, r, n); },
-                   [&](double* Sm, int n0, int k0, int) { load_imajor(Sm, Xt, n, n0, k0, n, n); },
-                   [&](int m, int nn, double v) { Tm[(size_t)m * n + nn] = v; }, As, Bs);
+        cta_gemm(Operand{Bm, ldr, r, true}, Operand{Xt, ldn, n, false}, n, pool, [&](int m, int nn, double v0, double v1) {
+            Tm[(size_t)m * ldn + nn] = v0;
+            if (nn + 1 < n) Tm[(size_t)m * ldn + nn + 1] = v1;
+        });
         __syncthreads();
         // ---- A = (Hinv T)^T ----
-        gemm_tiles(r, n, r,
-                   [&](double* Sm, int m0, int k0) { load_kmajor(Sm, Gs, ldg, m0, k0, r, r); },
-                   [&](double* Sm, int n0, int k0, int) { load_kmajor(Sm, Tm, n, n0, k0, n, r); },
-                   [&](int m, int nn, double v) { A[(size_t)nn * r + m] = v; }, As, Bs);
+        cta_gemm(Operand{Gg, ldr, r, false}, Operand{Tm, ldn, n, true}, r, pool, [&](int m, int nn, double v0, double v1) {
+            A[(size_t)nn * ldr + m] = v0;
+            if (nn + 1 < n) A[(size_t)(nn + 1) * ldr + m] = v1;
+        });
         __syncthreads();
-        // ---- X = A B^T, fused with the Z / Y updates and both residual norms ----
+        // ---- X = A B^T, fused with the Z / Y / next-Xt updates and both residual norms ----
         double pacc = 0.0, dacc = 0.0;
-        gemm_tiles(n, n, r,
-                   [&](double* Sm, int m0, int k0) { load_imajor(Sm, A, r, m0, k0, n, r); },
-                   [&](double* Sm, int n0, int k0, int) { load_imajor(Sm, Bm, r, n0, k0, n, r); },
-                   [&](int i, int j, double x) {
-                       const size_t o = (size_t)i * n + j;
-                       const double x0 = Xm[o];
-                       const double dd = x - x0;
-                       dacc += dd * dd;
-                       const double y = Y[o];
-                       double z = x + y / mu;
-                       if (s_grp[i] == s_grp[j]) z = 0.0;
-                       if (i == j) z = 1.0;
-                       if (z < 0.0) z = 0.0;
-                       if (z > 1.0) z = 1.0;
-                       const double pd = x - z;
-                       pacc += pd * pd;
-                       Y[o] = y + mu * pd;
-                       Z[o] = z;
-                       Xm[o] = x;
-                   },
-                   As, Bs);
+        auto update = [&](int i, int j, double x) {
+            const size_t o = (size_t)i * ldn + j;
+            const double x0 = Xm[o];
+            const double dd = x - x0;
+            dacc += dd * dd;
+            const double y = Y[o];
+            double z = x + y / mu;
+            if (s_grp[i] == s_grp[j]) z = 0.0;
+            if (i == j) z = 1.0;
+            if (z < 0.0) z = 0.0;
+            if (z > 1.0) z = 1.0;
+            const double pd = x - z;
+            pacc += pd * pd;
+            const double yn = y + mu * pd;
+            Y[o] = yn;
+            Z[o] = z;
+            Xm[o] = x;
+            Xt[o] = z - (yn - W[o] + beta) / mu;   // next iteration's Xt if mu stays
+        };
+        cta_gemm(Operand{A, ldr, n, false}, Operand{Bm, ldr, n, false}, r, pool, [&](int i, int j, double v0, double v1) {
+            update(i, j, v0);
+            if (j + 1 < n) update(i, j + 1, v1);
+        });
         const double psum = block_sum(pacc, scratch);
         const double dsum = block_sum(dacc, scratch);
         const double p_res = sqrt(psum) / n;
@@ -247,8 +363,18 @@ __global__ void __launch_bounds__(ALS_THREADS)
             it++;
             break;
         }
-        if (p_res > 10.0 * d_res) mu = 2.0 * mu;
-        else if (d_res > 10.0 * p_res) mu = mu / 2.0;
+        double mu_new = mu;
+        if (p_res > 10.0 * d_res) mu_new = 2.0 * mu;
+        else if (d_res > 10.0 * p_res) mu_new = mu / 2.0;
+        if (mu_new != mu) {
+            mu = mu_new;
+            __syncthreads();
+            for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+                const size_t o = (size_t)(e / n) * ldn + (e % n);
+                Xt[o] = Z[o] - (Y[o] - W[o] + beta) / mu;
+            }
+        }
+        __syncthreads();
     }
     __syncthreads();
     if (threadIdx.x == 0) n_iter_out[b] = it;
@@ -259,7 +385,7 @@ __global__ void __launch_bounds__(ALS_THREADS)
         for (int q = 0; q < 32; q++) {
             const int j = w * 32 + q;
             if (j < n) {
-                const double v = 0.5 * (Xm[(size_t)i * n + j] + Xm[(size_t)j * n + i]);
+                const double v = 0.5 * (Xm[(size_t)i * ldn + j] + Xm[(size_t)j * ldn + i]);
                 if (v > 0.5) bits |= 1u << q;
             }
         }
@@ -267,143 +393,15 @@ __global__ void __launch_bounds__(ALS_THREADS)
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// A6: closure quirk, leader assignment, first-kept-column parse, group decoding. One warp per
-// instance; lane w owns bit-word w of every N-bit row (N <= 1024).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
-    k_assign(const uint32_t* __restrict__ xbin, const int* __restrict__ dim_groups, const int* __restrict__ idx_view,
-             const int* __restrict__ idx_pose, const int* __restrict__ n_trk, int C, int N, int Tmax, int max_new,
-             int* __restrict__ trk_nsel, int* __restrict__ trk_sel, int* __restrict__ new_n, int* __restrict__ new_nsel,
-             int* __restrict__ new_sel, int* __restrict__ counts, int* __restrict__ err) {
-    const int b = blockIdx.x, lane = threadIdx.x;
-    const int NW = (N + 31) / 32;
-    const int n = dim_groups[b * (C + 2) + C + 1];
-    const int T = min(n_trk[b], Tmax);
-    const uint32_t* xb = xbin + (size_t)b * N * NW;
-    const int* iv = idx_view + (size_t)b * N;
-    const int* ip = idx_pose + (size_t)b * N;
-    int* tn = trk_nsel + (size_t)b * Tmax;
-    int* ts = trk_sel + (size_t)b * Tmax * MVMC_MAX_SEL * 2;
-    int* nn_ = new_nsel + (size_t)b * max_new;
-    int* ns = new_sel + (size_t)b * max_new * MVMC_MAX_SEL * 2;
-    // members[c] (bit rows) of the kept leader columns are re-derived on the fly; we only need, per
-    // leader c, temp[c] = X[c] | (X[c][n-1] ? X[n-1] : 0).
-    __shared__ int s_members[MVMC_MAX_TRACKS + MVMC_MAX_VIEWS * MVMC_MAX_POSES];
-    for (int t = lane; t < Tmax; t += 32) tn[t] = -1;
-    if (lane == 0) {
-        new_n[b] = 0;
-        for (int q = 0; q < 4; q++) counts[4 * b + q] = 0;
-        err[b] = 0;
-    }
-    if (n <= 0) return;
-    const uint32_t last_row = (lane < NW) ? xb[(size_t)(n - 1) * NW + lane] : 0u;
-    uint32_t vis = 0;       // this lane's word of `vis`
-    uint32_t assigned = 0;  // this lane's word of "row already attached to a kept column"
-    int n_new = 0, dup = 0, error = 0, n_single = 0, n_trunc = 0;
-    const bool has_trk = T > 0;
-    for (int i = 0; i < n; i++) {
-        const uint32_t vw = __shfl_sync(MVMC_FULL, vis, i >> 5);
-        if ((vw >> (i & 31)) & 1u) continue;  // uniform across the warp
-        uint32_t row = (lane < NW) ? xb[(size_t)i * NW + lane] : 0u;
-        const uint32_t lw = __shfl_sync(MVMC_FULL, row, (n - 1) >> 5);
-        if ((lw >> ((n - 1) & 31)) & 1u) row |= last_row;  // temp[i] = X[i] | X[i][n-1] * X[n-1]
-        vis |= row;
-        const int cnt = warp_sum_i(__popc(row));
-        if (cnt < 2) continue;  // column kept only with >= 2 members (sum > 1.9)
-        // rows join the FIRST kept column they belong to
-        uint32_t mine = row & ~assigned;
-        assigned |= row;
-        // enumerate members in ascending order into shared memory
-        int base = 0;
-        for (int w = 0; w < NW; w++) {
-            const uint32_t word = __shfl_sync(MVMC_FULL, mine, w);
-            if (lane == 0) {
-                uint32_t x = word;
-                while (x) {
-                    const int bit = __ffs((int)x) - 1;
-                    s_members[base++] = w * 32 + bit;
-                    x &= x - 1;
-                }
-            }
-            base = __shfl_sync(MVMC_FULL, base, 0);
-        }
-        __syncwarp();
-        if (base == 0) continue;  // empty group (`if cur_matches:`)
-        if (lane == 0) {
-            int t_idx = -1;
-            if (has_trk)
-                for (int q = 0; q < base; q++)
-                    if (s_members[q] < T) {
-                        t_idx = s_members[q];
-                        break;
-                    }
-            int sel[MVMC_MAX_SEL][2];
-            int nsel = 0;
-            uint32_t seen_views = 0;
-            bool over = false;
-            for (int q = 0; q < base; q++) {
-                const int g = s_members[q];
-                if (has_trk && g < T) continue;
-                const int v = iv[g];
-                if (has_trk) {
-                    if ((seen_views >> v) & 1u) {
-                        dup++;
-                        continue;
-                    }
-                    seen_views |= 1u << v;
-                }
-                if (nsel < MVMC_MAX_SEL) {
-                    sel[nsel][0] = v;
-                    sel[nsel][1] = ip[g];
-                    nsel++;
-                } else {
-                    over = true;  // keep the first MVMC_MAX_SEL poses (include/mvmc.h: n_truncated)
-                }
-            }
-            if (over) n_trunc++;
-            if (nsel > 0) {
-                if (t_idx >= 0) {
-                    tn[t_idx] = nsel;
-                    for (int q = 0; q < nsel; q++) {
-                        ts[(t_idx * MVMC_MAX_SEL + q) * 2] = sel[q][0];
-                        ts[(t_idx * MVMC_MAX_SEL + q) * 2 + 1] = sel[q][1];
-                    }
-                } else if (nsel < 2) {
-                    n_single++;  // a 2D-only group the one-pose-per-view rule shrank to one pose: never born
-                } else if (n_new < max_new) {
-                    nn_[n_new] = nsel;
-                    for (int q = 0; q < nsel; q++) {
-                        ns[(n_new * MVMC_MAX_SEL + q) * 2] = sel[q][0];
-                        ns[(n_new * MVMC_MAX_SEL + q) * 2 + 1] = sel[q][1];
-                    }
-                    n_new++;
-                } else {
-                    error = MVMC_ERR_CAPACITY;
-                }
-            }
-        }
-        __syncwarp();
-    }
-    if (lane == 0) {
-        new_n[b] = n_new;
-        counts[4 * b] = dup;
-        counts[4 * b + 1] = n_single;
-        counts[4 * b + 2] = n_trunc;
-        err[b] = error;
-    }
-}
-
 }  // namespace mvmc
 
 using namespace mvmc;
 
-static size_t als_smem_bytes(int N, int rmax) {
-    return (size_t)(2 * ALS_KC * ALS_LD + rmax * (rmax + 1) + 32) * sizeof(double) + (size_t)N * sizeof(int);
-}
+static size_t als_smem_bytes(int N) { return (size_t)(AL_POOL + 32) * sizeof(double) + (size_t)N * sizeof(int); }
 
 extern "C" size_t mvmc_match_als_workspace_bytes(int B, int N, int rmax) {
-    return (size_t)B * ((size_t)5 * N * N + (size_t)3 * N * rmax) * sizeof(double);
+    const AlsLayout L(N, rmax);
+    return (size_t)B * L.per * sizeof(double);
 }
 
 extern "C" int mvmc_match_als(const double* sim, const int* dim_groups, int n_groups, const int* f32_first_iter,
@@ -412,25 +410,10 @@ extern "C" int mvmc_match_als(const double* sim, const int* dim_groups, int n_gr
     if (!sim || !dim_groups || !rand_stream || !workspace || !xbin || !n_iter) return MVMC_ERR_INVALID;
     if (B <= 0 || N <= 0 || N > 1024 || rmax <= 0 || rmax > 128 || n_groups <= 0 || n_groups > MVMC_MAX_VIEWS + 1)
         return MVMC_ERR_INVALID;
-    const size_t smem = als_smem_bytes(N, rmax);
+    const size_t smem = als_smem_bytes(N);
     MVMC_CUDA_OK(cudaFuncSetAttribute(k_als, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MVMC_LAUNCH(k_als, dim3(B), dim3(ALS_THREADS), smem, stream, sim, dim_groups, n_groups, f32_first_iter, rand_stream, N,
+    MVMC_LAUNCH(k_als, dim3(B), dim3(AL_THREADS), smem, stream, sim, dim_groups, n_groups, f32_first_iter, rand_stream, N,
                 rmax, (double*)workspace, xbin, n_iter, 50.0, 0.1, 1e-4, 1000);
     MVMC_CHECK_LAUNCH("k_als");
-    return MVMC_OK;
-}
-
-extern "C" int mvmc_assign(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose,
-                           const int* n_trk, int B, int C, int N, int Tmax, int max_new, int* trk_nsel, int* trk_sel,
-                           int* new_n, int* new_nsel, int* new_sel, int* counts, int* err, void* stream) {
-    if (!xbin || !dim_groups || !idx_view || !idx_pose || !n_trk || !trk_nsel || !trk_sel || !new_n || !new_nsel ||
-        !new_sel || !counts || !err)
-        return MVMC_ERR_INVALID;
-    if (B <= 0 || N <= 0 || N > 1024 || C <= 0 || C > MVMC_MAX_VIEWS || Tmax < 0 || Tmax > MVMC_MAX_TRACKS ||
-        max_new <= 0)
-        return MVMC_ERR_INVALID;
-    MVMC_LAUNCH(k_assign, dim3(B), dim3(32), 0, stream, xbin, dim_groups, idx_view, idx_pose, n_trk, C, N, Tmax, max_new,
-                trk_nsel, trk_sel, new_n, new_nsel, new_sel, counts, err);
-    MVMC_CHECK_LAUNCH("k_assign");
     return MVMC_OK;
 }

@@ -1,0 +1,153 @@
+// Closure quirk + leader assignment + first-kept-column parse + group decoding of the matcher's X_bin.
+//
+// Reference rows: A6 mv_association.py:99-121 (transform_closure) + motion_capture.py:417-446
+// (parse_match_result) + motion_capture.py:762-808 / :618-624 (group decoding). Integer/bit work, one warp per clip.
+#include "mvmc_common.cuh"
+
+namespace mvmc {
+
+// ------------------------------------------------------------------------------------------------
+// A6: closure quirk, leader assignment, first-kept-column parse, group decoding. One warp per
+// instance; lane w owns bit-word w of every N-bit row (N <= 1024).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+    k_assign(const uint32_t* __restrict__ xbin, const int* __restrict__ dim_groups, const int* __restrict__ idx_view,
+             const int* __restrict__ idx_pose, const int* __restrict__ n_trk, int C, int N, int Tmax, int max_new,
+             int* __restrict__ trk_nsel, int* __restrict__ trk_sel, int* __restrict__ new_n, int* __restrict__ new_nsel,
+             int* __restrict__ new_sel, int* __restrict__ counts, int* __restrict__ err) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int NW = (N + 31) / 32;
+    const int n = dim_groups[b * (C + 2) + C + 1];
+    const int T = min(n_trk[b], Tmax);
+    const uint32_t* xb = xbin + (size_t)b * N * NW;
+    const int* iv = idx_view + (size_t)b * N;
+    const int* ip = idx_pose + (size_t)b * N;
+    int* tn = trk_nsel + (size_t)b * Tmax;
+    int* ts = trk_sel + (size_t)b * Tmax * MVMC_MAX_SEL * 2;
+    int* nn_ = new_nsel + (size_t)b * max_new;
+    int* ns = new_sel + (size_t)b * max_new * MVMC_MAX_SEL * 2;
+    // members[c] (bit rows) of the kept leader columns are re-derived on the fly; we only need, per
+    // leader c, temp[c] = X[c] | (X[c][n-1] ? X[n-1] : 0).
+    __shared__ int s_members[MVMC_MAX_TRACKS + MVMC_MAX_VIEWS * MVMC_MAX_POSES];
+    for (int t = lane; t < Tmax; t += 32) tn[t] = -1;
+    if (lane == 0) {
+        new_n[b] = 0;
+        for (int q = 0; q < 4; q++) counts[4 * b + q] = 0;
+        err[b] = 0;
+    }
+    if (n <= 0) return;
+    const uint32_t last_row = (lane < NW) ? xb[(size_t)(n - 1) * NW + lane] : 0u;
+    uint32_t vis = 0;       // this lane's word of `vis`
+    uint32_t assigned = 0;  // this lane's word of "row already attached to a kept column"
+    int n_new = 0, dup = 0, error = 0, n_single = 0, n_trunc = 0;
+    const bool has_trk = T > 0;
+    for (int i = 0; i < n; i++) {
+        const uint32_t vw = __shfl_sync(MVMC_FULL, vis, i >> 5);
+        if ((vw >> (i & 31)) & 1u) continue;  // uniform across the warp
+        uint32_t row = (lane < NW) ? xb[(size_t)i * NW + lane] : 0u;
+        const uint32_t lw = __shfl_sync(MVMC_FULL, row, (n - 1) >> 5);
+        if ((lw >> ((n - 1) & 31)) & 1u) row |= last_row;  // temp[i] = X[i] | X[i][n-1] * X[n-1]
+        vis |= row;
+        const int cnt = warp_sum_i(__popc(row));
+        if (cnt < 2) continue;  // column kept only with >= 2 members (sum > 1.9)
+        // rows join the FIRST kept column they belong to
+        uint32_t mine = row & ~assigned;
+        assigned |= row;
+        // enumerate members in ascending order into shared memory
+        int base = 0;
+        for (int w = 0; w < NW; w++) {
+            const uint32_t word = __shfl_sync(MVMC_FULL, mine, w);
+            if (lane == 0) {
+                uint32_t x = word;
+                while (x) {
+                    const int bit = __ffs((int)x) - 1;
+                    s_members[base++] = w * 32 + bit;
+                    x &= x - 1;
+                }
+            }
+            base = __shfl_sync(MVMC_FULL, base, 0);
+        }
+        __syncwarp();
+        if (base == 0) continue;  // empty group (`if cur_matches:`)
+        if (lane == 0) {
+            int t_idx = -1;
+            if (has_trk)
+                for (int q = 0; q < base; q++)
+                    if (s_members[q] < T) {
+                        t_idx = s_members[q];
+                        break;
+                    }
+            int sel[MVMC_MAX_SEL][2];
+            int nsel = 0;
+            uint32_t seen_views = 0;
+            bool over = false;
+            for (int q = 0; q < base; q++) {
+                const int g = s_members[q];
+                if (has_trk && g < T) continue;
+                const int v = iv[g];
+                if (has_trk) {
+                    if ((seen_views >> v) & 1u) {
+                        dup++;
+                        continue;
+                    }
+                    seen_views |= 1u << v;
+                }
+                if (nsel < MVMC_MAX_SEL) {
+                    sel[nsel][0] = v;
+                    sel[nsel][1] = ip[g];
+                    nsel++;
+                } else {
+                    over = true;  // keep the first MVMC_MAX_SEL poses (include/mvmc.h: n_truncated)
+                }
+            }
+            if (over) n_trunc++;
+            if (nsel > 0) {
+                if (t_idx >= 0) {
+                    tn[t_idx] = nsel;
+                    for (int q = 0; q < nsel; q++) {
+                        ts[(t_idx * MVMC_MAX_SEL + q) * 2] = sel[q][0];
+                        ts[(t_idx * MVMC_MAX_SEL + q) * 2 + 1] = sel[q][1];
+                    }
+                } else if (nsel < 2) {
+                    n_single++;  // a 2D-only group the one-pose-per-view rule shrank to one pose: never born
+                } else if (n_new < max_new) {
+                    nn_[n_new] = nsel;
+                    for (int q = 0; q < nsel; q++) {
+                        ns[(n_new * MVMC_MAX_SEL + q) * 2] = sel[q][0];
+                        ns[(n_new * MVMC_MAX_SEL + q) * 2 + 1] = sel[q][1];
+                    }
+                    n_new++;
+                } else {
+                    error = MVMC_ERR_CAPACITY;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        new_n[b] = n_new;
+        counts[4 * b] = dup;
+        counts[4 * b + 1] = n_single;
+        counts[4 * b + 2] = n_trunc;
+        err[b] = error;
+    }
+}
+
+}  // namespace mvmc
+
+using namespace mvmc;
+
+extern "C" int mvmc_assign(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose,
+                           const int* n_trk, int B, int C, int N, int Tmax, int max_new, int* trk_nsel, int* trk_sel,
+                           int* new_n, int* new_nsel, int* new_sel, int* counts, int* err, void* stream) {
+    if (!xbin || !dim_groups || !idx_view || !idx_pose || !n_trk || !trk_nsel || !trk_sel || !new_n || !new_nsel ||
+        !new_sel || !counts || !err)
+        return MVMC_ERR_INVALID;
+    if (B <= 0 || N <= 0 || N > 1024 || C <= 0 || C > MVMC_MAX_VIEWS || Tmax < 0 || Tmax > MVMC_MAX_TRACKS ||
+        max_new <= 0)
+        return MVMC_ERR_INVALID;
+    MVMC_LAUNCH(k_assign, dim3(B), dim3(32), 0, stream, xbin, dim_groups, idx_view, idx_pose, n_trk, C, N, Tmax, max_new,
+                trk_nsel, trk_sel, new_n, new_nsel, new_sel, counts, err);
+    MVMC_CHECK_LAUNCH("k_assign");
+    return MVMC_OK;
+}

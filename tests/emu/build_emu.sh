@@ -7,7 +7,7 @@ SRC="$ROOT/multiview_motion_capture_b200/csrc"
 OUT="$HERE/libmvmc_emu.so"
 FLAGS="-O1 -g -fPIC -std=c++17 -DMVMC_EMU -ffp-contract=off -I$ROOT/include -I$HERE -I$SRC -Wno-unused-variable"
 objs=""
-for f in affinity als ik pipeline; do
+for f in affinity als assign ik pipeline; do
   g++ $FLAGS -x c++ -c "$SRC/$f.cu" -o "$HERE/$f.emu.o" &
   objs="$objs $HERE/$f.emu.o"
 done

@@ -59,6 +59,7 @@ struct BlockCtx {
     dim3 bdim, gdim;
     std::function<void()> body;
     uint64_t warp_slot[64][32];
+    uint64_t warp_slot2[64][32];
 };
 
 extern BlockCtx* g_blk;
@@ -115,6 +116,22 @@ inline T shfl_idx(T v, int src) {
     T r = from_bits<T>(g_blk->warp_slot[w][src & 31]);
     warp_sync();
     return r;
+}
+// mma.sync.aligned.m8n8k4.row.col.f64: lane holds a = A[lane/4][lane%4], b = B[lane%4][lane/4],
+// c0/c1 = C[lane/4][2*(lane%4) + {0,1}]
+inline void dmma_884(double& c0, double& c1, double a, double b) {
+    Fiber& f = me();
+    const int w = f.linear / 32, l = f.linear % 32;
+    g_blk->warp_slot[w][l] = to_bits(a);
+    g_blk->warp_slot2[w][l] = to_bits(b);
+    warp_sync();
+    const int row = l / 4, col = 2 * (l % 4);
+    for (int k = 0; k < 4; k++) {
+        const double av = from_bits<double>(g_blk->warp_slot[w][row * 4 + k]);
+        c0 = fma(av, from_bits<double>(g_blk->warp_slot2[w][col * 4 + k]), c0);
+        c1 = fma(av, from_bits<double>(g_blk->warp_slot2[w][(col + 1) * 4 + k]), c1);
+    }
+    warp_sync();
 }
 }  // namespace emu
 
