@@ -43,7 +43,6 @@ struct alignas(16) TrfWarp {
     double Jc[WS_CH * WS_LDJ];      // current chunk of J, row major
     double x[MVMC_N_PARAM], xn[MVMC_N_PARAM];
     double g[WS_NC], gt[WS_NC], p[WS_NC], pt[WS_NC], d[WS_NC], e[WS_NC], tau[WS_NC], w[WS_NC], u[WS_NC], dx[WS_NC];
-    double dl[WS_NC], ll[WS_NC], yy[WS_NC], zz[WS_NC];
     double sc[8];
     int act[WS_NC];                 // parameter index behind each Jacobian column
 };
@@ -242,126 +241,194 @@ __device__ void warp_apply_q(const TrfWarp& s, int n, double* y, bool transpose)
     }
 }
 
-// LDL^T of T + alpha I (lane 0); returns false when a pivot is not positive (clamped to keep going).
-__device__ __forceinline__ bool tri_factor(TrfWarp& s, int n, double alpha, double floor_) {
+// ---- (T + alpha I) y = b for the symmetric tridiagonal T (d, e), n <= 64, by parallel cyclic reduction -------------
+// Lane l holds rows l and l + 32 (rows >= n are identity padding). Six reduction levels (strides 1..32) decouple every
+// row; neighbours come through warp shuffles, nothing touches shared memory. The per-level elimination factors are kept
+// so that a second right-hand side costs six fused multiply-add levels only. PCR is Gaussian elimination without
+// pivoting in a different order: stable for the positive definite T + alpha I it is used on.
+struct PcrFactors {
+    double k1[6][2], k2[6][2];   // elimination factors per level and row slot
+    double binv[2];              // 1 / final diagonal
+    bool pd;                     // every intermediate diagonal stayed positive
+};
+
+__device__ __forceinline__ void pcr_neigh(double v0, double v1, int s, int lane, double& lo0, double& lo1, double& hi0,
+                                          double& hi1, double fill) {
+    // values of rows (i - s) -> lo, (i + s) -> hi for i = lane (slot 0) and i = lane + 32 (slot 1); out of range -> fill
+    if (s == 32) {
+        lo0 = fill;
+        lo1 = v0;
+        hi0 = v1;
+        hi1 = fill;
+        return;
+    }
+    const double d0 = __shfl_sync(MVMC_FULL, v0, (lane - s) & 31), d1 = __shfl_sync(MVMC_FULL, v1, (lane - s) & 31);
+    const double u0 = __shfl_sync(MVMC_FULL, v0, (lane + s) & 31), u1 = __shfl_sync(MVMC_FULL, v1, (lane + s) & 31);
+    const bool wrap_lo = lane - s < 0, wrap_hi = lane + s >= 32;
+    lo0 = wrap_lo ? fill : d0;       // row lane - s
+    lo1 = wrap_lo ? d0 : d1;         // row lane + 32 - s: slot 0 of lane - s + 32 when it wraps, else slot 1 of lane - s
+    hi0 = wrap_hi ? u1 : u0;         // row lane + s: slot 1 of lane + s - 32 when it wraps
+    hi1 = wrap_hi ? fill : u1;       // row lane + 32 + s
+}
+
+// factor + solve: b0/b1 = right-hand side rows (lane, lane+32) -> y0/y1
+__device__ __forceinline__ void pcr_solve(const TrfWarp& s, int n, double alpha, double floor_, double& r0, double& r1,
+                                          PcrFactors& F) {
+    const int lane = threadIdx.x & 31;
+    const int i0 = lane, i1 = lane + 32;
+    double a0 = (i0 > 0 && i0 < n) ? s.e[i0 - 1] : 0.0, a1 = (i1 < n) ? s.e[i1 - 1] : 0.0;
+    double c0 = (i0 + 1 < n) ? s.e[i0] : 0.0, c1 = (i1 + 1 < n) ? s.e[i1] : 0.0;
+    double b0 = (i0 < n) ? s.d[i0] + alpha : 1.0, b1 = (i1 < n) ? s.d[i1] + alpha : 1.0;
     bool pd = true;
-    double piv = s.d[0] + alpha;
-    for (int i = 0; i < n; i++) {
-        if (!(piv > floor_)) {
+#pragma unroll
+    for (int lv = 0; lv < 6; lv++) {
+        const int st = 1 << lv;
+        if (!(b0 > floor_)) {
             pd = false;
-            piv = floor_;
+            b0 = floor_;
         }
-        s.dl[i] = piv;
-        if (i + 1 < n) {
-            const double l = s.e[i] / piv;
-            s.ll[i] = l;
-            piv = (s.d[i + 1] + alpha) - l * s.e[i];
+        if (!(b1 > floor_)) {
+            pd = false;
+            b1 = floor_;
         }
+        double bl0, bl1, bh0, bh1, al0, al1, ah0, ah1, cl0, cl1, ch0, ch1, rl0, rl1, rh0, rh1;
+        pcr_neigh(b0, b1, st, lane, bl0, bl1, bh0, bh1, 1.0);
+        pcr_neigh(a0, a1, st, lane, al0, al1, ah0, ah1, 0.0);
+        pcr_neigh(c0, c1, st, lane, cl0, cl1, ch0, ch1, 0.0);
+        pcr_neigh(r0, r1, st, lane, rl0, rl1, rh0, rh1, 0.0);
+        const double k10 = a0 / bl0, k20 = c0 / bh0, k11 = a1 / bl1, k21 = c1 / bh1;
+        F.k1[lv][0] = k10;
+        F.k2[lv][0] = k20;
+        F.k1[lv][1] = k11;
+        F.k2[lv][1] = k21;
+        b0 = b0 - cl0 * k10 - ah0 * k20;
+        b1 = b1 - cl1 * k11 - ah1 * k21;
+        r0 = r0 - rl0 * k10 - rh0 * k20;
+        r1 = r1 - rl1 * k11 - rh1 * k21;
+        a0 = -al0 * k10;
+        a1 = -al1 * k11;
+        c0 = -ch0 * k20;
+        c1 = -ch1 * k21;
     }
-    return pd;
+    if (!(b0 > floor_)) {
+        pd = false;
+        b0 = floor_;
+    }
+    if (!(b1 > floor_)) {
+        pd = false;
+        b1 = floor_;
+    }
+    F.binv[0] = 1.0 / b0;
+    F.binv[1] = 1.0 / b1;
+    r0 *= F.binv[0];
+    r1 *= F.binv[1];
+    F.pd = __all_sync(MVMC_FULL, pd);
 }
-// y = (T + alpha I)^-1 b, returns ||y||^2; also w with L w = b left in `wout` when not null
-__device__ __forceinline__ double tri_solve(const TrfWarp& s, int n, const double* b, double* y) {
-    y[0] = b[0];
-    for (int i = 1; i < n; i++) y[i] = b[i] - s.ll[i - 1] * y[i - 1];
-    double nn = 0.0;
-    y[n - 1] = y[n - 1] / s.dl[n - 1];
-    nn = y[n - 1] * y[n - 1];
-    for (int i = n - 2; i >= 0; i--) {
-        y[i] = y[i] / s.dl[i] - s.ll[i] * y[i + 1];
-        nn = fma(y[i], y[i], nn);
+// another right-hand side for the matrix factored by pcr_solve
+__device__ __forceinline__ void pcr_resolve(const PcrFactors& F, double& r0, double& r1) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int lv = 0; lv < 6; lv++) {
+        double rl0, rl1, rh0, rh1;
+        pcr_neigh(r0, r1, 1 << lv, lane, rl0, rl1, rh0, rh1, 0.0);
+        r0 = r0 - rl0 * F.k1[lv][0] - rh0 * F.k2[lv][0];
+        r1 = r1 - rl1 * F.k1[lv][1] - rh1 * F.k2[lv][1];
     }
-    return nn;
-}
-// b^T (T + alpha I)^-1 b through L w = b, sum w_i^2 / dl_i
-__device__ __forceinline__ double tri_quad(const TrfWarp& s, int n, const double* b, double* w) {
-    w[0] = b[0];
-    double q = w[0] * w[0] / s.dl[0];
-    for (int i = 1; i < n; i++) {
-        w[i] = b[i] - s.ll[i - 1] * w[i - 1];
-        q += w[i] * w[i] / s.dl[i];
-    }
-    return q;
+    r0 *= F.binv[0];
+    r1 *= F.binv[1];
 }
 
 // SciPy solve_lsq_trust_region in the Q basis. In: s.d, s.e, s.gt (= Q^T g), delta, alpha (warm start), full_rank.
 // Out: s.pt (step in the Q basis, already rescaled), returns alpha; sc[1] = ||p||, sc[2] = predicted reduction.
+// Every lane computes the same scalars (butterfly reductions), so the control flow is warp uniform.
 __device__ double trf_subproblem(TrfWarp& s, int n, double delta, double alpha, bool full_rank) {
     const int lane = threadIdx.x & 31;
+    const int i0 = lane, i1 = lane + 32;
+    const double g0 = i0 < n ? s.gt[i0] : 0.0, g1 = i1 < n ? s.gt[i1] : 0.0;
+    const double gn2 = warp_sum(g0 * g0 + g1 * g1);
+    const double dmax = warp_max(fmax(i0 < n ? fabs(s.d[i0]) : 0.0, i1 < n ? fabs(s.d[i1]) : 0.0));
+    const double floor_ = kEps * kEps * fmax(dmax, 1e-300);  // only guards against non-positive pivots
+    // SciPy works from singular values, so exactly rank-deficient directions (s = 0, s*uf = 0) drop out even when the
+    // Moré iteration ends at alpha ~ 0 (e.g. the 2-view triangulation refine, where phi(alpha) < 0 for every alpha and
+    // the pseudo-inverse step gets stretched to the radius). J^T J + alpha I has no such luxury: keep the linear algebra
+    // numerically positive definite with a floor on alpha far below anything the data resolves (16 eps lambda_max),
+    // which turns the alpha -> 0 limit into the same pseudo-inverse step. The iteration on alpha itself is unchanged.
+    const double amin = 16.0 * kEps * dmax;
+    PcrFactors F;
+    double y0 = 0.0, y1 = 0.0;
+    bool done = false;
+    double scale_to = 0.0;
+    double a_lo = 0.0, a_hi = sqrt(gn2) / delta;
+    if (full_rank) {
+        y0 = g0;
+        y1 = g1;
+        pcr_solve(s, n, amin, floor_, y0, y1, F);
+        const double nn = warp_sum(y0 * y0 + y1 * y1);
+        if (F.pd && sqrt(nn) <= delta) {
+            alpha = 0.0;
+            done = true;  // Gauss-Newton step
+        } else if (F.pd) {
+            const double pn = sqrt(nn);
+            double z0 = y0, z1 = y1;
+            pcr_resolve(F, z0, z1);
+            const double q = warp_sum(y0 * z0 + y1 * z1);
+            a_lo = -(pn - delta) / (-q / pn);
+        } else {
+            full_rank = false;
+        }
+    }
+    if (!done) {
+        if (!full_rank && alpha == 0.0) alpha = fmax(0.001 * a_hi, sqrt(a_lo * a_hi));
+        for (int it = 0; it < 10; it++) {
+            if (alpha < a_lo || alpha > a_hi) alpha = fmax(0.001 * a_hi, sqrt(a_lo * a_hi));
+            y0 = g0;
+            y1 = g1;
+            pcr_solve(s, n, fmax(alpha, amin), floor_, y0, y1, F);
+            const double pn = sqrt(warp_sum(y0 * y0 + y1 * y1));
+            double z0 = y0, z1 = y1;
+            pcr_resolve(F, z0, z1);
+            const double q = warp_sum(y0 * z0 + y1 * z1);
+            const double phi = pn - delta, dphi = -q / pn;
+            if (phi < 0.0) a_hi = alpha;
+            const double ratio = phi / dphi;
+            a_lo = fmax(a_lo, alpha - ratio);
+            alpha -= (phi + delta) * ratio / delta;
+            if (fabs(phi) < 0.01 * delta) break;
+        }
+        y0 = g0;
+        y1 = g1;
+        pcr_solve(s, n, fmax(alpha, amin), floor_, y0, y1, F);
+        scale_to = delta;
+    }
+    // p~ = -y (rescaled to the radius unless it is the Gauss-Newton step)
+    double nn = warp_sum(y0 * y0 + y1 * y1);
+    double sc = -1.0;
+    if (scale_to > 0.0) sc = -scale_to / sqrt(nn);
+    const double p0 = y0 * sc, p1 = y1 * sc;
+    nn = warp_sum(p0 * p0 + p1 * p1);
+    __syncwarp();
+    if (i0 < n) s.pt[i0] = p0;
+    if (i1 < n) s.pt[i1] = p1;
+    __syncwarp();
+    // predicted reduction -(0.5 p^T A p + g^T p) = -(0.5 p~^T T p~ + g~^T p~)
+    double tp = 0.0, gp = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        const double pi = s.pt[i];
+        double t = s.d[i] * pi;
+        if (i > 0) t = fma(s.e[i - 1], s.pt[i - 1], t);
+        if (i + 1 < n) t = fma(s.e[i], s.pt[i + 1], t);
+        tp = fma(pi, t, tp);
+        gp = fma(s.gt[i], pi, gp);
+    }
+    tp = warp_sum(tp);
+    gp = warp_sum(gp);
     if (lane == 0) {
-        double gn2 = 0.0, dmax = 0.0;
-        for (int i = 0; i < n; i++) {
-            gn2 = fma(s.gt[i], s.gt[i], gn2);
-            dmax = fmax(dmax, fabs(s.d[i]));
-        }
-        const double floor_ = kEps * kEps * fmax(dmax, 1e-300);  // only guards against non-positive pivots
-        // SciPy works from singular values, so exactly rank-deficient directions (s = 0, s*uf = 0) drop out even when the
-        // Moré iteration ends at alpha ~ 0 (e.g. the 2-view triangulation refine, where phi(alpha) < 0 for every alpha and
-        // the pseudo-inverse step gets stretched to the radius). J^T J + alpha I has no such luxury: keep the linear algebra
-        // numerically positive definite with a floor on alpha far below anything the data resolves (16 eps lambda_max),
-        // which turns the alpha -> 0 limit into the same pseudo-inverse step. The iteration on alpha itself is unchanged.
-        const double amin = 16.0 * kEps * dmax;
-        bool done = false;
-        double scale_to = 0.0;
-        double a_lo = 0.0, a_hi = sqrt(gn2) / delta;
-        if (full_rank) {
-            const bool pd = tri_factor(s, n, amin, floor_);
-            const double nn = tri_solve(s, n, s.gt, s.yy);
-            if (pd && sqrt(nn) <= delta) {
-                alpha = 0.0;
-                done = true;  // Gauss-Newton step
-            } else if (pd) {
-                const double pn = sqrt(nn);
-                const double q = tri_quad(s, n, s.yy, s.zz);
-                a_lo = -(pn - delta) / (-q / pn);
-            } else {
-                full_rank = false;
-            }
-        }
-        if (!done) {
-            if (!full_rank && alpha == 0.0) alpha = fmax(0.001 * a_hi, sqrt(a_lo * a_hi));
-            for (int it = 0; it < 10; it++) {
-                if (alpha < a_lo || alpha > a_hi) alpha = fmax(0.001 * a_hi, sqrt(a_lo * a_hi));
-                tri_factor(s, n, fmax(alpha, amin), floor_);
-                const double pn = sqrt(tri_solve(s, n, s.gt, s.yy));
-                const double q = tri_quad(s, n, s.yy, s.zz);
-                const double phi = pn - delta, dphi = -q / pn;
-                if (phi < 0.0) a_hi = alpha;
-                const double ratio = phi / dphi;
-                a_lo = fmax(a_lo, alpha - ratio);
-                alpha -= (phi + delta) * ratio / delta;
-                if (fabs(phi) < 0.01 * delta) break;
-            }
-            tri_factor(s, n, fmax(alpha, amin), floor_);
-            tri_solve(s, n, s.gt, s.yy);
-            scale_to = delta;
-        }
-        // p~ = -y (rescaled to the radius unless it is the Gauss-Newton step)
-        double nn = 0.0;
-        for (int i = 0; i < n; i++) nn = fma(s.yy[i], s.yy[i], nn);
-        double sc = -1.0;
-        if (scale_to > 0.0) sc = -scale_to / sqrt(nn);
-        nn = 0.0;
-        for (int i = 0; i < n; i++) {
-            const double v = s.yy[i] * sc;
-            s.pt[i] = v;
-            nn = fma(v, v, nn);
-        }
-        // predicted reduction -(0.5 p^T A p + g^T p) = -(0.5 p~^T T p~ + g~^T p~)
-        double tp = 0.0, gp = 0.0;
-        for (int i = 0; i < n; i++) {
-            double t = s.d[i] * s.pt[i];
-            if (i > 0) t = fma(s.e[i - 1], s.pt[i - 1], t);
-            if (i + 1 < n) t = fma(s.e[i], s.pt[i + 1], t);
-            tp = fma(s.pt[i], t, tp);
-            gp = fma(s.gt[i], s.pt[i], gp);
-        }
         s.sc[0] = alpha;
         s.sc[1] = sqrt(nn);
         s.sc[2] = -(0.5 * tp + gp);
     }
     __syncwarp();
-    return s.sc[0];
+    return alpha;
 }
 
 // scipy.optimize.least_squares(fun, x0, max_nfev=...), method='trf', jac='2-point', unbounded.
