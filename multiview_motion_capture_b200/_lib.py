@@ -100,6 +100,9 @@ def use_library(path):
 def get_lib():
     """The CUDA library. Raises if it has not been built (run `python __graft_entry__.py` / build())."""
     global _lib, _lib_path
+    if _lib is None and os.environ.get("MVMC_LIBRARY"):
+        # explicit override of the shared object (the test tier points CLI subprocesses at the kernel emulator with it)
+        return use_library(os.environ["MVMC_LIBRARY"])
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise MvmcError(f"{LIB_PATH} is missing: the CUDA extension has not been built "

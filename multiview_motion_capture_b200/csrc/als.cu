@@ -79,30 +79,74 @@ struct Operand {
     bool kmajor;   // true: element(k, i) = p[k*ld + i];  false: element(k, i) = p[i*ld + k]
 };
 
-// Stage the [k0, k0+KC) x [i0, i0+TI) block of `op` into shared memory (zero filled outside K x I).
+// Staging of the [k0, k0+KC) x [i0, i0+TI) block of an operand into shared memory (zero filled outside K x I), 16 bytes
+// per cp.async. The (shared offset, global pointer, validity) of the <= 4 pieces a thread copies are computed once per
+// CTA tile; advancing to the next k-chunk is one pointer increment per piece.
 template <int TI>
-__device__ __forceinline__ void stage_operand(double* S, const Operand& op, int i0, int k0, int K) {
-    constexpr int SK = TI + 8;
-    if (op.kmajor) {
-        // S[kk*SK + ii], 16-byte pieces along i
-        for (int e = threadIdx.x; e < AL_KC * (TI / 2); e += AL_THREADS) {
-            const int kk = e / (TI / 2), ii = (e % (TI / 2)) * 2;
-            const int k = k0 + kk, i = i0 + ii;
-            int nv = (k < K) ? op.I - i : 0;
-            nv = nv < 0 ? 0 : (nv > 2 ? 2 : nv);
-            cp16(S + kk * SK + ii, nv > 0 ? op.p + (size_t)k * op.ld + i : op.p, nv);
-        }
-    } else {
-        // S[ii*SI + kk], 16-byte pieces along k
-        for (int e = threadIdx.x; e < TI * (AL_KC / 2); e += AL_THREADS) {
-            const int ii = e / (AL_KC / 2), kk = (e % (AL_KC / 2)) * 2;
-            const int k = k0 + kk, i = i0 + ii;
-            int nv = (i < op.I) ? K - k : 0;
-            nv = nv < 0 ? 0 : (nv > 2 ? 2 : nv);
-            cp16(S + ii * AL_SI + kk, nv > 0 ? op.p + (size_t)i * op.ld + k : op.p, nv);
+struct Stager {
+    static constexpr int NP = (AL_KC * (TI / 2) + AL_THREADS - 1) / AL_THREADS;   // pieces per thread (3 or 4)
+    const double* base;
+    int goff[NP];     // offset (doubles) of the piece in chunk 0 from `base`
+    unsigned valid;   // 2 bits per piece: k-major = valid doubles along i (0..2); i-major = 2 if row i is inside I
+    int step;         // offset increment per k-chunk
+    bool kmajor;
+
+    // piece q of this thread -> (shared offset, k offset inside the chunk); constant divisors only
+    __device__ __forceinline__ static void where(bool kmaj, int q, int& soff, int& kk) {
+        const int e = threadIdx.x + q * AL_THREADS;
+        if (kmaj) {
+            kk = e / (TI / 2);
+            soff = kk * (TI + 8) + (e % (TI / 2)) * 2;
+        } else {
+            kk = (e % (AL_KC / 2)) * 2;
+            soff = (e / (AL_KC / 2)) * AL_SI + kk;
         }
     }
-}
+    __device__ __forceinline__ void init(const Operand& op, int i0) {
+        kmajor = op.kmajor;
+        base = op.p;
+        step = op.kmajor ? AL_KC * op.ld : AL_KC;
+        valid = 0;
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            const int e = threadIdx.x + q * AL_THREADS;
+            goff[q] = 0;
+            if (e >= AL_KC * (TI / 2)) continue;
+            if (op.kmajor) {
+                const int k = e / (TI / 2), i = i0 + (e % (TI / 2)) * 2;
+                int nv = op.I - i;
+                nv = nv < 0 ? 0 : (nv > 2 ? 2 : nv);
+                valid |= (unsigned)nv << (2 * q);
+                goff[q] = k * op.ld + (nv > 0 ? i : 0);
+            } else {
+                const int i = i0 + e / (AL_KC / 2), k = (e % (AL_KC / 2)) * 2;
+                const bool in = i < op.I;
+                valid |= (in ? 2u : 0u) << (2 * q);
+                goff[q] = (in ? i * op.ld : 0) + k;
+            }
+        }
+    }
+    // copy chunk kc (k0 = kc * KC) into S
+    __device__ __forceinline__ void issue(double* S, int kc, int K) const {
+        const int k0 = kc * AL_KC;
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            if (threadIdx.x + q * AL_THREADS >= AL_KC * (TI / 2)) continue;
+            int soff, kk;
+            where(kmajor, q, soff, kk);
+            const int nvi = (valid >> (2 * q)) & 3;
+            int nv;
+            if (kmajor) {
+                nv = (k0 + kk < K) ? nvi : 0;
+            } else {
+                nv = K - (k0 + kk);
+                nv = nv < 0 ? 0 : (nv > 2 ? 2 : nv);
+                nv = nvi ? nv : 0;
+            }
+            cp16(S + soff, nv > 0 ? base + goff[q] + kc * step : base, nv);
+        }
+    }
+};
 
 template <int TI>
 __device__ __forceinline__ double frag(const double* S, bool kmajor, int i8, int kk, int lane) {
@@ -111,9 +155,11 @@ __device__ __forceinline__ double frag(const double* S, bool kmajor, int i8, int
 }
 
 // C[m][n] = sum_k Mop(k, m) * Nop(k, n) for m < Mop.I, n < Nop.I; ep(m, n, v0, v1) receives C[m][n], C[m][n+1]
-// (n even; the caller guards n+1 < N). All threads of the CTA must call it. `pool` holds the two stages.
-template <class EP>
-__device__ void cta_gemm(const Operand& Mop, const Operand& Nop, int K, double* pool, EP ep) {
+// (n even; the caller guards n+1 < N); slot = 0/1 tells which of the two fragments of the row it is, and pre(slot, m, n)
+// is called for both fragments before either ep so that an epilogue can issue its global loads together.
+// All threads of the CTA must call it. `pool` holds the two stages.
+template <class EP, class PRE>
+__device__ __noinline__ void cta_gemm(const Operand& Mop, const Operand& Nop, int K, double* pool, EP ep, PRE pre) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int M = Mop.I, N = Nop.I;
     const int nk = (K + AL_KC - 1) / AL_KC;
@@ -127,16 +173,20 @@ __device__ void cta_gemm(const Operand& Mop, const Operand& Nop, int K, double* 
             for (int a = 0; a < 8; a++)
 #pragma unroll
                 for (int b = 0; b < 2; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+            Stager<AL_TM> sm_;
+            Stager<AL_TN> sn_;
+            sm_.init(Mop, m0);
+            sn_.init(Nop, n0);
             __syncthreads();   // the pool may still be read by the previous tile / another phase
-            stage_operand<AL_TM>(pool, Mop, m0, 0, K);
-            stage_operand<AL_TN>(pool + AL_STAGE_M, Nop, n0, 0, K);
+            sm_.issue(pool, 0, K);
+            sn_.issue(pool + AL_STAGE_M, 0, K);
             cp_commit();
             for (int kc = 0; kc < nk; kc++) {
                 double* cur = pool + (kc & 1) * AL_STAGE;
                 if (kc + 1 < nk) {
                     double* nxt = pool + ((kc + 1) & 1) * AL_STAGE;
-                    stage_operand<AL_TM>(nxt, Mop, m0, (kc + 1) * AL_KC, K);
-                    stage_operand<AL_TN>(nxt + AL_STAGE_M, Nop, n0, (kc + 1) * AL_KC, K);
+                    sm_.issue(nxt, kc + 1, K);
+                    sn_.issue(nxt + AL_STAGE_M, kc + 1, K);
                     cp_commit();
                     cp_wait<1>();
                 } else {
@@ -163,50 +213,63 @@ __device__ void cta_gemm(const Operand& Mop, const Operand& Nop, int K, double* 
                 __syncthreads();
             }
 #pragma unroll
-            for (int a = 0; a < 8; a++)
-#pragma unroll
-                for (int b = 0; b < 2; b++) {
-                    if (a < mt && b < nt) {
-                        const int m = m0 + a * 8 + (lane >> 2), n = nw0 + b * 8 + 2 * (lane & 3);
-                        if (m < M && n < N) ep(m, n, acc[a][b][0], acc[a][b][1]);
-                    }
+            for (int a = 0; a < 8; a++) {
+                if (a < mt) {
+                    const int m = m0 + a * 8 + (lane >> 2);
+                    const int na = nw0 + 2 * (lane & 3), nb = na + 8;
+                    const bool oka = nt > 0 && m < M && na < N, okb = nt > 1 && m < M && nb < N;
+                    // loads of both fragments of the row first, then the arithmetic and the stores
+                    if (oka) pre(0, m, na);
+                    if (okb) pre(1, m, nb);
+                    if (oka) ep(0, m, na, acc[a][0][0], acc[a][0][1]);
+                    if (okb) ep(1, m, nb, acc[a][1][0], acc[a][1][1]);
                 }
+            }
         }
     }
 }
+struct NoPre {
+    __device__ __forceinline__ void operator()(int, int, int) const {}
+};
 
-// In-place inverse of the SPD r x r matrix G (leading dimension ldg) by Gauss-Jordan without pivoting.
-__device__ void invert_spd(double* G, int r, int ldg) {
+// In-place inverse of the SPD r x r matrix G (leading dimension ldg) by Gauss-Jordan without pivoting. Thread t owns
+// the columns j = t % 32 + 32 q of the rows i = t / 32 + nw p (nw = warps of the CTA): no index division in the loop, and
+// two barriers per pivot (the scaled pivot row and the pivot column are parked in `aux` [2 r] first).
+__device__ void invert_spd(double* G, int r, int ldg, double* aux) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double* rk = aux;        // pivot row * (1 / pivot)
+    double* ck = aux + r;    // pivot column
     for (int k = 0; k < r; k++) {
         const double p = 1.0 / G[k * ldg + k];
-        __syncthreads();
-        for (int j = threadIdx.x; j < r; j += blockDim.x)
-            if (j != k) G[k * ldg + j] *= p;
-        __syncthreads();
-        for (int e = threadIdx.x; e < r * r; e += blockDim.x) {
-            const int i = e / r, j = e % r;
-            if (i != k && j != k) G[i * ldg + j] -= G[i * ldg + k] * G[k * ldg + j];
+        for (int j = threadIdx.x; j < r; j += blockDim.x) {
+            rk[j] = G[k * ldg + j] * p;
+            ck[j] = G[j * ldg + k];
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < r; i += blockDim.x) {
-            if (i != k) G[i * ldg + k] = -G[i * ldg + k] * p;
-            else G[k * ldg + k] = p;
+        for (int i = w; i < r; i += nw) {
+            const double f = ck[i];
+            double* row = G + i * ldg;
+            if (i == k) {
+                for (int j = lane; j < r; j += 32) row[j] = (j == k) ? p : rk[j];
+            } else {
+                for (int j = lane; j < r; j += 32) row[j] = (j == k) ? -f * p : row[j] - f * rk[j];
+            }
         }
         __syncthreads();
     }
 }
 
 // Gg (r x r, ld ldr, global) <- inverse of Gg; through shared memory when it fits
-__device__ void invert_normal_matrix(double* Gg, int r, int ldr, double* pool) {
+__device__ void invert_normal_matrix(double* Gg, int r, int ldr, double* pool, double* aux) {
     __syncthreads();
     if (r <= AL_RSMEM) {
         const int ldg = r + 1;
         for (int e = threadIdx.x; e < r * r; e += blockDim.x) pool[(e / r) * ldg + (e % r)] = Gg[(size_t)(e / r) * ldr + (e % r)];
         __syncthreads();
-        invert_spd(pool, r, ldg);
+        invert_spd(pool, r, ldg, aux);
         for (int e = threadIdx.x; e < r * r; e += blockDim.x) Gg[(size_t)(e / r) * ldr + (e % r)] = pool[(e / r) * ldg + (e % r)];
     } else {
-        invert_spd(Gg, r, ldr);
+        invert_spd(Gg, r, ldr, aux);
     }
     __syncthreads();
 }
@@ -244,7 +307,8 @@ __global__ void __launch_bounds__(AL_THREADS, 3)
 
     double* pool = smem;                       // [AL_POOL] stages / inverse
     double* scratch = pool + AL_POOL;          // [32]
-    int* s_grp = reinterpret_cast<int*>(scratch + 32);   // [N]
+    double* inv_aux = scratch + 32;            // [2 * 128] pivot row / column of the Gauss-Jordan inverse
+    int* s_grp = reinterpret_cast<int*>(inv_aux + 256);   // [N]
 
     const AlsLayout L(N, rmax);
     const int ldn = L.ldn, ldr = L.ldr;
@@ -291,70 +355,84 @@ __global__ void __launch_bounds__(AL_THREADS, 3)
         // ---- G = A^T A + reg I, inverted ----
         {
             const Operand opA{A, ldr, r, true};
-            cta_gemm(opA, opA, n, pool, [&](int m, int nn, double v0, double v1) {
+            cta_gemm(opA, opA, n, pool, [&](int, int m, int nn, double v0, double v1) {
                 Gg[(size_t)m * ldr + nn] = (m == nn) ? v0 + reg * 1.0 : v0 + reg * 0.0;
                 if (nn + 1 < r) Gg[(size_t)m * ldr + nn + 1] = (m == nn + 1) ? v1 + reg * 1.0 : v1 + reg * 0.0;
-            });
+            }, NoPre());
         }
-        invert_normal_matrix(Gg, r, ldr, pool);
+        invert_normal_matrix(Gg, r, ldr, pool, inv_aux);
         // ---- T = A^T Xt ----
-        cta_gemm(Operand{A, ldr, r, true}, Operand{Xt, ldn, n, true}, n, pool, [&](int m, int nn, double v0, double v1) {
+        cta_gemm(Operand{A, ldr, r, true}, Operand{Xt, ldn, n, true}, n, pool, [&](int, int m, int nn, double v0, double v1) {
             Tm[(size_t)m * ldn + nn] = v0;
             if (nn + 1 < n) Tm[(size_t)m * ldn + nn + 1] = v1;
-        });
+        }, NoPre());
         __syncthreads();
         // ---- B = (Ginv T)^T ----
-        cta_gemm(Operand{Gg, ldr, r, false}, Operand{Tm, ldn, n, true}, r, pool, [&](int m, int nn, double v0, double v1) {
+        cta_gemm(Operand{Gg, ldr, r, false}, Operand{Tm, ldn, n, true}, r, pool, [&](int, int m, int nn, double v0, double v1) {
             Bm[(size_t)nn * ldr + m] = v0;
             if (nn + 1 < n) Bm[(size_t)(nn + 1) * ldr + m] = v1;
-        });
+        }, NoPre());
         __syncthreads();
         // ---- H = B^T B + reg I, inverted ----
         {
             const Operand opB{Bm, ldr, r, true};
-            cta_gemm(opB, opB, n, pool, [&](int m, int nn, double v0, double v1) {
+            cta_gemm(opB, opB, n, pool, [&](int, int m, int nn, double v0, double v1) {
                 Gg[(size_t)m * ldr + nn] = (m == nn) ? v0 + reg : v0;
                 if (nn + 1 < r) Gg[(size_t)m * ldr + nn + 1] = (m == nn + 1) ? v1 + reg : v1;
-            });
+            }, NoPre());
         }
-        invert_normal_matrix(Gg, r, ldr, pool);
+        invert_normal_matrix(Gg, r, ldr, pool, inv_aux);
         // ---- T = B^T Xt^T : T[m][i] = sum_j B[j][m] Xt[i][j] ----
-        cta_gemm(Operand{Bm, ldr, r, true}, Operand{Xt, ldn, n, false}, n, pool, [&](int m, int nn, double v0, double v1) {
+        cta_gemm(Operand{Bm, ldr, r, true}, Operand{Xt, ldn, n, false}, n, pool, [&](int, int m, int nn, double v0, double v1) {
             Tm[(size_t)m * ldn + nn] = v0;
             if (nn + 1 < n) Tm[(size_t)m * ldn + nn + 1] = v1;
-        });
+        }, NoPre());
         __syncthreads();
         // ---- A = (Hinv T)^T ----
-        cta_gemm(Operand{Gg, ldr, r, false}, Operand{Tm, ldn, n, true}, r, pool, [&](int m, int nn, double v0, double v1) {
+        cta_gemm(Operand{Gg, ldr, r, false}, Operand{Tm, ldn, n, true}, r, pool, [&](int, int m, int nn, double v0, double v1) {
             A[(size_t)nn * ldr + m] = v0;
             if (nn + 1 < n) A[(size_t)(nn + 1) * ldr + m] = v1;
-        });
+        }, NoPre());
         __syncthreads();
         // ---- X = A B^T, fused with the Z / Y / next-Xt updates and both residual norms ----
         double pacc = 0.0, dacc = 0.0;
-        auto update = [&](int i, int j, double x) {
-            const size_t o = (size_t)i * ldn + j;
-            const double x0 = Xm[o];
+        double2 ex0[2], ey[2], ew[2];   // X_prev, Y, W of the two fragments of a row (16-byte loads, issued together)
+        auto one = [&](int i, int j, double x, double x0, double y, double w, bool live, double& yn, double& z, double& xt) {
             const double dd = x - x0;
-            dacc += dd * dd;
-            const double y = Y[o];
-            double z = x + y / mu;
-            if (s_grp[i] == s_grp[j]) z = 0.0;
+            z = x + y / mu;
+            if (s_grp[i] == s_grp[live ? j : i]) z = 0.0;
             if (i == j) z = 1.0;
             if (z < 0.0) z = 0.0;
             if (z > 1.0) z = 1.0;
             const double pd = x - z;
-            pacc += pd * pd;
-            const double yn = y + mu * pd;
-            Y[o] = yn;
-            Z[o] = z;
-            Xm[o] = x;
-            Xt[o] = z - (yn - W[o] + beta) / mu;   // next iteration's Xt if mu stays
+            yn = y + mu * pd;
+            xt = z - (yn - w + beta) / mu;   // next iteration's Xt if mu stays
+            if (live) {
+                dacc += dd * dd;
+                pacc += pd * pd;
+            }
         };
-        cta_gemm(Operand{A, ldr, n, false}, Operand{Bm, ldr, n, false}, r, pool, [&](int i, int j, double v0, double v1) {
-            update(i, j, v0);
-            if (j + 1 < n) update(i, j + 1, v1);
-        });
+        cta_gemm(Operand{A, ldr, n, false}, Operand{Bm, ldr, n, false}, r, pool,
+                 [&](int slot, int i, int j, double v0, double v1) {
+                     const size_t o = (size_t)i * ldn + j;
+                     const bool live1 = j + 1 < n;   // the odd column of the last pair may be padding (written, never read)
+                     double2 yn, z, xt;
+                     one(i, j, v0, ex0[slot].x, ey[slot].x, ew[slot].x, true, yn.x, z.x, xt.x);
+                     one(i, j + 1, v1, ex0[slot].y, ey[slot].y, ew[slot].y, live1, yn.y, z.y, xt.y);
+                     *reinterpret_cast<double2*>(Y + o) = yn;
+                     *reinterpret_cast<double2*>(Z + o) = z;
+                     double2 xv;
+                     xv.x = v0;
+                     xv.y = v1;
+                     *reinterpret_cast<double2*>(Xm + o) = xv;
+                     *reinterpret_cast<double2*>(Xt + o) = xt;
+                 },
+                 [&](int slot, int i, int j) {
+                     const size_t o = (size_t)i * ldn + j;
+                     ex0[slot] = *reinterpret_cast<const double2*>(Xm + o);
+                     ey[slot] = *reinterpret_cast<const double2*>(Y + o);
+                     ew[slot] = *reinterpret_cast<const double2*>(W + o);
+                 });
         const double psum = block_sum(pacc, scratch);
         const double dsum = block_sum(dacc, scratch);
         const double p_res = sqrt(psum) / n;
@@ -397,7 +475,7 @@ __global__ void __launch_bounds__(AL_THREADS, 3)
 
 using namespace mvmc;
 
-static size_t als_smem_bytes(int N) { return (size_t)(AL_POOL + 32) * sizeof(double) + (size_t)N * sizeof(int); }
+static size_t als_smem_bytes(int N) { return (size_t)(AL_POOL + 32 + 256) * sizeof(double) + (size_t)N * sizeof(int); }
 
 extern "C" size_t mvmc_match_als_workspace_bytes(int B, int N, int rmax) {
     const AlsLayout L(N, rmax);

@@ -22,6 +22,8 @@ struct SkelConst {
     double dirs[MVMC_N_B18][3];
     double ref_side_lens[11];
     unsigned char param_dead[MVMC_N_PARAM];   // 1: the parameter cannot move any joint (leaf rotations, root bone length)
+    unsigned char leaf[MVMC_N_B18];
+    signed char ik_slot[MVMC_N_B18];           // slot among the 16 observed joints, -1 for Mid_Hip / Neck
 };
 __constant__ SkelConst c_skel;
 __constant__ int c_ik_obs_idx[MVMC_N_IKJ] = {11, 13, 15, 12, 14, 16, 17, 5, 7, 9, 6, 8, 10, 0, 3, 4};
@@ -96,48 +98,73 @@ __device__ void fk_b18(const double* x, const double* lens, double (*pos)[3]) {
     }
 }
 
-// The same chain fully unrolled over the compile-time topology, everything in registers: getx(i) supplies parameter
-// i of [root | euler | side lengths] (68), emit(j, x, y, z) receives joint j. Leaf rotations are never formed
-// (no joint position depends on them).
-template <int J, class GetX, class Emit>
-struct FkStep {
-    static __device__ __forceinline__ void run(GetX& getx, Emit& emit, double (&G)[MVMC_N_B18][9], double (&pos)[MVMC_N_B18][3]) {
-        constexpr int p = Topo::parent(J);
-        double m[9];
-        if (!Topo::leaf(J)) euler_to_mat(getx(3 + 3 * J), getx(4 + 3 * J), getx(5 + 3 * J), m);
-        if (J == 0) {
+// The same chain as a compact rolled loop with everything in registers: getx(i) supplies parameter i of
+// [root | euler | side lengths] (68), emit(j, x, y, z) receives joint j. Only three global rotations are ever live -
+// the root's, the neck's (joint 8, parent of both arms and the head) and the current chain's - so the parent of a
+// joint is a 3-way select instead of an indexed (local-memory) array. Leaf rotations are never formed (no joint
+// position depends on them). Kept rolled on purpose: unrolled it is ~4.5k instructions per call site and the solver
+// kernel outgrew the instruction cache.
+__constant__ unsigned char c_fk_psel[MVMC_N_B18] = {0, 1, 0, 0, 1, 0, 0, 1, 0, 2, 0, 0, 2, 0, 0, 2, 0, 0};   // 0 cur, 1 root, 2 neck
+template <class GetX, class Emit>
+__device__ __forceinline__ void fk_rolled(GetX getx, Emit emit) {
+    double Gc[9], Gr[9], Gn[9], pc[3], pr[3], pn[3];
+    {
+        euler_to_mat(getx(3), getx(4), getx(5), Gr);
+        pr[0] = getx(0);
+        pr[1] = getx(1);
+        pr[2] = getx(2);
 #pragma unroll
-            for (int q = 0; q < 9; q++) G[0][q] = m[q];
-            pos[0][0] = getx(0);
-            pos[0][1] = getx(1);
-            pos[0][2] = getx(2);
-        } else {
-            const double len = getx(57 + Topo::s2f(J));
-            const double o0 = c_skel.dirs[J][0] * len, o1 = c_skel.dirs[J][1] * len, o2 = c_skel.dirs[J][2] * len;
-            const double* Rp = G[p < 0 ? 0 : p];
+        for (int q = 0; q < 9; q++) Gc[q] = Gn[q] = Gr[q];
 #pragma unroll
-            for (int r = 0; r < 3; r++) {
-                if (!Topo::leaf(J)) {
+        for (int q = 0; q < 3; q++) pc[q] = pn[q] = pr[q];
+        emit(0, pr[0], pr[1], pr[2]);
+    }
+#pragma unroll 1
+    for (int j = 1; j < MVMC_N_B18; j++) {
+        const int sel = c_fk_psel[j];
+        double Rp[9], pp[3];
 #pragma unroll
-                    for (int c = 0; c < 3; c++)
-                        G[J][r * 3 + c] = Rp[r * 3] * m[c] + Rp[r * 3 + 1] * m[3 + c] + Rp[r * 3 + 2] * m[6 + c];
-                }
-                pos[J][r] = Rp[r * 3] * o0 + Rp[r * 3 + 1] * o1 + Rp[r * 3 + 2] * o2 + pos[p < 0 ? 0 : p][r];
+        for (int q = 0; q < 9; q++) Rp[q] = sel == 0 ? Gc[q] : (sel == 1 ? Gr[q] : Gn[q]);
+#pragma unroll
+        for (int q = 0; q < 3; q++) pp[q] = sel == 0 ? pc[q] : (sel == 1 ? pr[q] : pn[q]);
+        const double len = getx(57 + c_skel.side_to_full[j]);
+        const double o0 = c_skel.dirs[j][0] * len, o1 = c_skel.dirs[j][1] * len, o2 = c_skel.dirs[j][2] * len;
+        double pj[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) pj[r] = Rp[r * 3] * o0 + Rp[r * 3 + 1] * o1 + Rp[r * 3 + 2] * o2 + pp[r];
+        emit(j, pj[0], pj[1], pj[2]);
+        if (!c_skel.leaf[j]) {   // uniform branch
+            double m[9];
+            euler_to_mat(getx(3 + 3 * j), getx(4 + 3 * j), getx(5 + 3 * j), m);
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) Gc[r * 3 + c] = Rp[r * 3] * m[c] + Rp[r * 3 + 1] * m[3 + c] + Rp[r * 3 + 2] * m[6 + c];
+#pragma unroll
+            for (int q = 0; q < 3; q++) pc[q] = pj[q];
+            if (j == 8) {
+#pragma unroll
+                for (int q = 0; q < 9; q++) Gn[q] = Gc[q];
+#pragma unroll
+                for (int q = 0; q < 3; q++) pn[q] = pj[q];
             }
         }
-        emit(J, pos[J][0], pos[J][1], pos[J][2]);
-        FkStep<J + 1, GetX, Emit>::run(getx, emit, G, pos);
     }
-};
-template <class GetX, class Emit>
-struct FkStep<MVMC_N_B18, GetX, Emit> {
-    static __device__ __forceinline__ void run(GetX&, Emit&, double (&)[MVMC_N_B18][9], double (&)[MVMC_N_B18][3]) {}
-};
-template <class GetX, class Emit>
-__device__ __forceinline__ void fk_unrolled(GetX getx, Emit emit) {
-    double G[MVMC_N_B18][9];
-    double pos[MVMC_N_B18][3];
-    FkStep<0, GetX, Emit>::run(getx, emit, G, pos);
+}
+
+// One copy of the chain for the whole kernel: evaluates the pose x (with parameter `prm` replaced by `xp` when
+// prm >= 0) and stores joint j at out[j*3*stride + k*stride] - the 16 observed joints only (slot order) when
+// `ik_slots`, else all 18.
+__device__ __noinline__ void fk_store(const double* x, int prm, double xp, double* out, int stride, bool ik_slots, bool on) {
+    fk_rolled([&](int i) { return i == prm ? xp : x[i]; },
+              [&](int j, double px, double py, double pz) {
+                  const int sl = ik_slots ? c_skel.ik_slot[j] : j;
+                  if (sl >= 0 && on) {
+                      out[(sl * 3) * stride] = px;
+                      out[(sl * 3 + 1) * stride] = py;
+                      out[(sl * 3 + 2) * stride] = pz;
+                  }
+              });
 }
 
 __device__ __forceinline__ void project3(const double* Pv, double X, double Y, double Z, double& pu, double& pv, double& pw) {
@@ -158,19 +185,11 @@ struct IkRes {
     __device__ int chunk_rows(int) const { return 16; }
     __device__ int chunk_row0(int c) const { return 16 * c; }
 
-    __device__ void eval(const double* x, double* f) {
+    __device__ __noinline__ void eval(const double* x, double* f) {
         const int lane = threadIdx.x & 31;
         double* pb = posb;
         // the chain is evaluated redundantly by every lane (uniform control flow); lane 0 parks the positions
-        fk_unrolled([&](int i) { return x[i]; },
-                    [&](int j, double px, double py, double pz) {
-                        const int sl = Topo::ik_slot(j);
-                        if (sl >= 0 && lane == 0) {
-                            pb[sl * 3] = px;
-                            pb[sl * 3 + 1] = py;
-                            pb[sl * 3 + 2] = pz;
-                        }
-                    });
+        fk_store(x, -1, 0.0, pb, 1, true, lane == 0);
         __syncwarp();
         for (int it = lane; it < V * MVMC_N_IKJ; it += 32) {
             const int v = it >> 4, q = it & 15;
@@ -192,19 +211,10 @@ struct IkRes {
             const bool on = c < ncol;
             const int prm = on ? s.act[c] : -1;
             const double xp = on ? s.w[c] : 0.0;
-            const double* x = s.x;
-            fk_unrolled([&](int i) { return i == prm ? xp : x[i]; },
-                        [&](int j, double px, double py, double pz) {
-                            const int sl = Topo::ik_slot(j);
-                            if (sl >= 0 && on) {
-                                S[(sl * 3) * WS_NC + c] = px;
-                                S[(sl * 3 + 1) * WS_NC + c] = py;
-                                S[(sl * 3 + 2) * WS_NC + c] = pz;
-                            }
-                        });
+            fk_store(s.x, prm, xp, S + c, WS_NC, true, on);
         }
     }
-    __device__ void fd_chunk(TrfWarp& s, int ncol, int ch, const double* f) {
+    __device__ __noinline__ void fd_chunk(TrfWarp& s, int ncol, int ch, const double* f) {
         const int lane = threadIdx.x & 31;
         const int v = ch >> 1, q0 = (ch & 1) * 8;
         const double* S = s.A;
@@ -421,7 +431,7 @@ __device__ int ik_columns(TrfWarp& t, const uint8_t* free_mask, int npar, int& n
     return ncol;
 }
 
-template <int VMAX>
+template <int VMAX, bool WITH_BIRTH>
 __global__ void __launch_bounds__(32)
     k_ik_solve(const double* __restrict__ kps2d, const double* __restrict__ Psel, const int* __restrict__ n_views,
                const double* __restrict__ x0, const uint8_t* __restrict__ birth, const int* __restrict__ max_nfev,
@@ -444,6 +454,10 @@ __global__ void __launch_bounds__(32)
             continue;
         }
         const bool is_birth = birth != nullptr && birth[mI] != 0;
+        if (is_birth && !WITH_BIRTH) {   // births go through the WITH_BIRTH instantiation (separate launch in the pipeline)
+            if (lane < 8) inf[lane] = -1;
+            continue;
+        }
         const int nfev_cap = max_nfev[mI];
         __syncwarp();
         // stage observations (+ mid spine) and projection matrices
@@ -460,9 +474,11 @@ __global__ void __launch_bounds__(32)
             sh.obs16[e] = sh.obs18[v * 54 + c_ik_obs_idx[q] * 3 + c];
         }
         __syncwarp();
-        if (is_birth) {
+        bool born = false;
+        if constexpr (WITH_BIRTH) born = is_birth;
+        if (born) {
             // triangulate 18 joints (min score 0.01), refine with a 2-nfev TRF, inverse_kinematics.py:389-396
-            warp_triangulate(sh, sh.obs18, nv, 18, 0.01, 2);
+            if constexpr (WITH_BIRTH) warp_triangulate(sh, sh.obs18, nv, 18, 0.01, 2);
             if (lane == 0) {
                 double root[3];
                 for (int c = 0; c < 3; c++) root[c] = 0.5 * (sh.p3[kCocoLHip * 4 + c] + sh.p3[kCocoRHip * 4 + c]);
@@ -497,18 +513,7 @@ __global__ void __launch_bounds__(32)
             __syncwarp();
         }
         for (int e = lane; e < MVMC_N_PARAM; e += 32) x_out[(size_t)mI * MVMC_N_PARAM + e] = sh.t.x[e];
-        {
-            const double* x = sh.t.x;
-            double* jout = joints + (size_t)mI * MVMC_N_B18 * 3;
-            fk_unrolled([&](int i) { return x[i]; },
-                        [&](int j, double px, double py, double pz) {
-                            if (lane == 0) {
-                                jout[j * 3] = px;
-                                jout[j * 3 + 1] = py;
-                                jout[j * 3 + 2] = pz;
-                            }
-                        });
-        }
+        fk_store(sh.t.x, -1, 0.0, joints + (size_t)mI * MVMC_N_B18 * 3, 1, false, lane == 0);
         if (lane == 0) {
             for (int q = 0; q < 2; q++) {
                 inf[4 * q] = r[q].nfev;
@@ -630,6 +635,10 @@ static int ensure_skeleton() {
     // that only the root uses (the root's own offset is replaced by the root translation)
     for (int e = 0; e < MVMC_N_PARAM; e++) h.param_dead[e] = 0;
     for (int j = 0; j < MVMC_N_B18; j++) {
+        h.leaf[j] = Topo::leaf(j) ? 1 : 0;
+        h.ik_slot[j] = (signed char)Topo::ik_slot(j);
+    }
+    for (int j = 0; j < MVMC_N_B18; j++) {
         if (has_child[j] != !Topo::leaf(j)) return MVMC_ERR_INVALID;
         if (!has_child[j])
             for (int c = 0; c < 3; c++) h.param_dead[3 + 3 * j + c] = 1;
@@ -661,15 +670,16 @@ int mvmc_ik_launch(const double* kps2d, const double* Psel, const int* n_views, 
     int rc = ensure_skeleton();
     if (rc) return rc;
     MVMC_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
-    if (vmax <= 8) {
-        MVMC_CUDA_OK(cudaFuncSetAttribute(k_ik_solve<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IkWarpSh<8>)));
-        MVMC_LAUNCH(k_ik_solve<8>, dim3(ik_grid(n_items)), dim3(32), sizeof(IkWarpSh<8>), stream, kps2d, Psel, n_views, x0, birth,
+    if (vmax <= 8 && birth == nullptr) {
+        auto kern = k_ik_solve<8, false>;
+        MVMC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IkWarpSh<8>)));
+        MVMC_LAUNCH(kern, dim3(ik_grid(n_items)), dim3(32), sizeof(IkWarpSh<8>), stream, kps2d, Psel, n_views, x0, birth,
                     max_nfev, free_mask, n_items, cnt, S, s0, V, counter, x_out, joints, info, cost);
     } else {
-        MVMC_CUDA_OK(cudaFuncSetAttribute(k_ik_solve<MVMC_MAX_SEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(IkWarpSh<MVMC_MAX_SEL>)));
-        MVMC_LAUNCH(k_ik_solve<MVMC_MAX_SEL>, dim3(ik_grid(n_items)), dim3(32), sizeof(IkWarpSh<MVMC_MAX_SEL>), stream, kps2d,
-                    Psel, n_views, x0, birth, max_nfev, free_mask, n_items, cnt, S, s0, V, counter, x_out, joints, info, cost);
+        auto kern = k_ik_solve<MVMC_MAX_SEL, true>;
+        MVMC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IkWarpSh<MVMC_MAX_SEL>)));
+        MVMC_LAUNCH(kern, dim3(ik_grid(n_items)), dim3(32), sizeof(IkWarpSh<MVMC_MAX_SEL>), stream, kps2d, Psel, n_views, x0,
+                    birth, max_nfev, free_mask, n_items, cnt, S, s0, V, counter, x_out, joints, info, cost);
     }
     MVMC_CHECK_LAUNCH("k_ik_solve");
     return MVMC_OK;

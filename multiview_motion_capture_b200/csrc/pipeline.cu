@@ -601,7 +601,7 @@ extern "C" int mvmc_clips_step(mvmc_clips* h, const double* kps, const int* n_po
     MVMC_CHECK_LAUNCH("k_gather");
     MVMC_EV(3);
     // track updates use one pose per view (<= C observations); births of no-track frames may group more (<= MVMC_MAX_SEL)
-    rc = mvmc_ik_launch(h->w_kps, h->w_P, h->w_nv, h->w_x0, h->w_birth, h->w_nfev, nullptr, B * Tmax, Tmax, h->S, 0,
+    rc = mvmc_ik_launch(h->w_kps, h->w_P, h->w_nv, h->w_x0, nullptr, h->w_nfev, nullptr, B * Tmax, Tmax, h->S, 0,
                         MVMC_MAX_SEL, C, (int*)h->ik_ws, h->w_xout, h->w_joints, h->w_info, h->w_cost, stream);
     if (rc) return rc;
     rc = mvmc_ik_launch(h->w_kps, h->w_P, h->w_nv, h->w_x0, h->w_birth, h->w_nfev, nullptr, B * h->cfg.max_new, h->cfg.max_new,

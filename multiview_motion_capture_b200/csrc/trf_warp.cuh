@@ -74,7 +74,7 @@ __device__ __forceinline__ void lane_tile(int lane, int& ti, int& tj) {
 //   void fd_prepare(TrfWarp& s, int ncol);                 per column: perturb, evaluate the model, park the state in s.A
 //   void fd_chunk(TrfWarp& s, int ncol, int c, const double* f);   fill s.Jc[r][col] = (r'(x + h e_col) - f) / dx for chunk c
 template <class Res>
-__device__ void trf_jacobian(TrfWarp& s, Res& res, int ncol, const double* f) {
+__device__ __noinline__ void trf_jacobian(TrfWarp& s, Res& res, int ncol, const double* f) {
     const int lane = threadIdx.x & 31;
     for (int e = lane; e < WS_CH * WS_LDJ; e += 32) s.Jc[e] = 0.0;
     // SciPy's 2-point rule: h = sqrt(eps) * sign(x) * max(1, |x|) with sign(0) = +1, dx = (x + h) - x
@@ -150,7 +150,7 @@ __device__ void trf_jacobian(TrfWarp& s, Res& res, int ncol, const double* f) {
 
 // A (n x n, symmetric, full storage) -> tridiagonal T = Q^T A Q: d[0..n), e[0..n-1); reflector k is stored in
 // A[k+2.., k] (v[k+1] = 1 implicit) with s.tau[k]. LAPACK dsytd2 (lower) arithmetic, one warp.
-__device__ void warp_tridiagonalise(TrfWarp& s, int n) {
+__device__ __noinline__ void warp_tridiagonalise(TrfWarp& s, int n) {
     const int lane = threadIdx.x & 31;
     for (int k = 0; k + 1 < n; k++) {
         const int r0 = k + 1 + lane, r1 = r0 + 32;
@@ -223,7 +223,7 @@ __device__ void warp_tridiagonalise(TrfWarp& s, int n) {
 }
 
 // y <- H_k y for k = 0..n-3 (forward = true: y <- Q^T y) or k = n-3..0 (y <- Q y). y in shared memory.
-__device__ void warp_apply_q(const TrfWarp& s, int n, double* y, bool transpose) {
+__device__ __noinline__ void warp_apply_q(const TrfWarp& s, int n, double* y, bool transpose) {
     const int lane = threadIdx.x & 31;
     for (int q = 0; q + 2 < n; q++) {
         const int k = transpose ? q : n - 3 - q;
@@ -341,7 +341,7 @@ __device__ __forceinline__ void pcr_resolve(const PcrFactors& F, double& r0, dou
 // SciPy solve_lsq_trust_region in the Q basis. In: s.d, s.e, s.gt (= Q^T g), delta, alpha (warm start), full_rank.
 // Out: s.pt (step in the Q basis, already rescaled), returns alpha; sc[1] = ||p||, sc[2] = predicted reduction.
 // Every lane computes the same scalars (butterfly reductions), so the control flow is warp uniform.
-__device__ double trf_subproblem(TrfWarp& s, int n, double delta, double alpha, bool full_rank) {
+__device__ __noinline__ double trf_subproblem(TrfWarp& s, int n, double delta, double alpha, bool full_rank) {
     const int lane = threadIdx.x & 31;
     const int i0 = lane, i1 = lane + 32;
     const double g0 = i0 < n ? s.gt[i0] : 0.0, g1 = i1 < n ? s.gt[i1] : 0.0;
@@ -356,50 +356,50 @@ __device__ double trf_subproblem(TrfWarp& s, int n, double delta, double alpha, 
     const double amin = 16.0 * kEps * dmax;
     PcrFactors F;
     double y0 = 0.0, y1 = 0.0;
-    bool done = false;
-    double scale_to = 0.0;
     double a_lo = 0.0, a_hi = sqrt(gn2) / delta;
-    if (full_rank) {
+    // One loop, one call site of the solver (code size): phase 0 = Gauss-Newton probe at alpha = 0 (full rank only),
+    // phase 1 = SciPy's <= 10 Newton iterations on alpha, phase 2 = the step at the final alpha.
+    int phase = full_rank ? 0 : 1, it = 0;
+    bool gn_step = false;
+    if (phase == 1 && alpha == 0.0) alpha = fmax(0.001 * a_hi, sqrt(a_lo * a_hi));
+#pragma unroll 1
+    for (;;) {
+        if (phase == 1 && (alpha < a_lo || alpha > a_hi)) alpha = fmax(0.001 * a_hi, sqrt(a_lo * a_hi));
+        const double a_eval = phase == 0 ? amin : fmax(alpha, amin);
         y0 = g0;
         y1 = g1;
-        pcr_solve(s, n, amin, floor_, y0, y1, F);
-        const double nn = warp_sum(y0 * y0 + y1 * y1);
-        if (F.pd && sqrt(nn) <= delta) {
-            alpha = 0.0;
-            done = true;  // Gauss-Newton step
-        } else if (F.pd) {
-            const double pn = sqrt(nn);
-            double z0 = y0, z1 = y1;
-            pcr_resolve(F, z0, z1);
-            const double q = warp_sum(y0 * z0 + y1 * z1);
-            a_lo = -(pn - delta) / (-q / pn);
-        } else {
-            full_rank = false;
+        pcr_solve(s, n, a_eval, floor_, y0, y1, F);
+        if (phase == 2) break;
+        const double pn = sqrt(warp_sum(y0 * y0 + y1 * y1));
+        if (phase == 0) {
+            if (F.pd && pn <= delta) {
+                alpha = 0.0;
+                gn_step = true;  // Gauss-Newton step
+                break;
+            }
+            if (!F.pd) {         // numerically rank deficient after all
+                if (alpha == 0.0) alpha = fmax(0.001 * a_hi, sqrt(a_lo * a_hi));
+                phase = 1;
+                continue;
+            }
         }
-    }
-    if (!done) {
-        if (!full_rank && alpha == 0.0) alpha = fmax(0.001 * a_hi, sqrt(a_lo * a_hi));
-        for (int it = 0; it < 10; it++) {
-            if (alpha < a_lo || alpha > a_hi) alpha = fmax(0.001 * a_hi, sqrt(a_lo * a_hi));
-            y0 = g0;
-            y1 = g1;
-            pcr_solve(s, n, fmax(alpha, amin), floor_, y0, y1, F);
-            const double pn = sqrt(warp_sum(y0 * y0 + y1 * y1));
-            double z0 = y0, z1 = y1;
-            pcr_resolve(F, z0, z1);
-            const double q = warp_sum(y0 * z0 + y1 * z1);
-            const double phi = pn - delta, dphi = -q / pn;
-            if (phi < 0.0) a_hi = alpha;
-            const double ratio = phi / dphi;
-            a_lo = fmax(a_lo, alpha - ratio);
-            alpha -= (phi + delta) * ratio / delta;
-            if (fabs(phi) < 0.01 * delta) break;
+        double z0 = y0, z1 = y1;
+        pcr_resolve(F, z0, z1);
+        const double q = warp_sum(y0 * z0 + y1 * z1);
+        const double phi = pn - delta, dphi = -q / pn;
+        if (phase == 0) {
+            a_lo = -phi / dphi;
+            phase = 1;
+            continue;
         }
-        y0 = g0;
-        y1 = g1;
-        pcr_solve(s, n, fmax(alpha, amin), floor_, y0, y1, F);
-        scale_to = delta;
+        if (phi < 0.0) a_hi = alpha;
+        const double ratio = phi / dphi;
+        a_lo = fmax(a_lo, alpha - ratio);
+        alpha -= (phi + delta) * ratio / delta;
+        it++;
+        if (fabs(phi) < 0.01 * delta || it == 10) phase = 2;
     }
+    const double scale_to = gn_step ? 0.0 : delta;
     // p~ = -y (rescaled to the radius unless it is the Gauss-Newton step)
     double nn = warp_sum(y0 * y0 + y1 * y1);
     double sc = -1.0;
