@@ -5,11 +5,11 @@
 //     X = A B^T;  Z = clip(X + Y/mu) with same-group blocks zeroed and unit diagonal;  Y += mu (X - Z)
 // until ||X - Z||_F / n < tol and mu ||X - X_prev||_F / n < tol, mu doubled / halved on a 10x imbalance.
 //
-// k_als: ONE CTA (6 warps) PER CLIP-FRAME, 3 resident CTAs per SM. The n x n iterates (W, Z, Y, X, Xt) and the
+// k_als: ONE CTA (8 warps) PER CLIP-FRAME, 2 resident CTAs per SM. The n x n iterates (W, Z, Y, X, Xt) and the
 // n x r factors live in a per-clip global workspace; the seven products of an iteration (three of them 2 r n^2
 // flops: the dominant cost of the whole capture path) run as tiled FP64 tensor-core GEMMs:
 //   * CTA tile 64 x 96, k-chunks of 16 staged in shared memory by 16-byte cp.async (LDGSTS) with zero fill, double buffered;
-//   * each warp owns 16 output columns x up to 8 row tiles and issues mma.sync.m8n8k4.f64 (DMMA) from conflict-free
+//   * each warp owns a 32 x 24 piece of the tile (12 accumulator fragments) and issues mma.sync.m8n8k4.f64 (DMMA) from conflict-free
 //     fragment loads (row strides chosen so the 4 x 8 fragment footprint covers every bank once);
 //   * the Z / Y / X / next-Xt update and both residual norms are the epilogue of the X = A B^T product, so an
 //     iteration makes three passes over n x n data (Xt twice, the epilogue's X, Y, W once) instead of seven;
@@ -21,11 +21,10 @@
 
 namespace mvmc {
 
-constexpr int AL_THREADS = 192;
-constexpr int AL_WARPS = 6;
+constexpr int AL_THREADS = 256;           // 8 warps: 2 along M x 4 along N, warp tile 32 x 24
 constexpr int AL_KC = 16;                 // k-chunk
 constexpr int AL_TM = 64;                 // CTA tile rows
-constexpr int AL_TN = 96;                 // CTA tile columns (6 warps x 16)
+constexpr int AL_TN = 96;                 // CTA tile columns (4 warp columns x 24)
 constexpr int AL_SKM = AL_TM + 8;         // k-major tile row stride, M operand  (= 64 B mod 128 B)
 constexpr int AL_SKN = AL_TN + 8;         // k-major tile row stride, N operand
 constexpr int AL_SI = AL_KC + 4;          // i-major tile row stride               (= 32 B mod 128 B)
@@ -76,25 +75,25 @@ struct Operand {
     const double* p;
     int ld;
     int I;
-    bool kmajor;   // true: element(k, i) = p[k*ld + i];  false: element(k, i) = p[i*ld + k]
 };
+// layout of an operand (template argument): k-major: element(k, i) = p[k*ld + i];  i-major: element(k, i) = p[i*ld + k]
+constexpr bool KMAJ = true, IMAJ = false;
 
 // Staging of the [k0, k0+KC) x [i0, i0+TI) block of an operand into shared memory (zero filled outside K x I), 16 bytes
 // per cp.async. The (shared offset, global pointer, validity) of the <= 4 pieces a thread copies are computed once per
 // CTA tile; advancing to the next k-chunk is one pointer increment per piece.
-template <int TI>
+template <int TI, bool kmajor>
 struct Stager {
     static constexpr int NP = (AL_KC * (TI / 2) + AL_THREADS - 1) / AL_THREADS;   // pieces per thread (3 or 4)
     const double* base;
     int goff[NP];     // offset (doubles) of the piece in chunk 0 from `base`
     unsigned valid;   // 2 bits per piece: k-major = valid doubles along i (0..2); i-major = 2 if row i is inside I
     int step;         // offset increment per k-chunk
-    bool kmajor;
 
     // piece q of this thread -> (shared offset, k offset inside the chunk); constant divisors only
-    __device__ __forceinline__ static void where(bool kmaj, int q, int& soff, int& kk) {
+    __device__ __forceinline__ static void where(int q, int& soff, int& kk) {
         const int e = threadIdx.x + q * AL_THREADS;
-        if (kmaj) {
+        if (kmajor) {
             kk = e / (TI / 2);
             soff = kk * (TI + 8) + (e % (TI / 2)) * 2;
         } else {
@@ -103,16 +102,15 @@ struct Stager {
         }
     }
     __device__ __forceinline__ void init(const Operand& op, int i0) {
-        kmajor = op.kmajor;
         base = op.p;
-        step = op.kmajor ? AL_KC * op.ld : AL_KC;
+        step = kmajor ? AL_KC * op.ld : AL_KC;
         valid = 0;
 #pragma unroll
         for (int q = 0; q < NP; q++) {
             const int e = threadIdx.x + q * AL_THREADS;
             goff[q] = 0;
             if (e >= AL_KC * (TI / 2)) continue;
-            if (op.kmajor) {
+            if (kmajor) {
                 const int k = e / (TI / 2), i = i0 + (e % (TI / 2)) * 2;
                 int nv = op.I - i;
                 nv = nv < 0 ? 0 : (nv > 2 ? 2 : nv);
@@ -133,7 +131,7 @@ struct Stager {
         for (int q = 0; q < NP; q++) {
             if (threadIdx.x + q * AL_THREADS >= AL_KC * (TI / 2)) continue;
             int soff, kk;
-            where(kmajor, q, soff, kk);
+            where(q, soff, kk);
             const int nvi = (valid >> (2 * q)) & 3;
             int nv;
             if (kmajor) {
@@ -148,8 +146,8 @@ struct Stager {
     }
 };
 
-template <int TI>
-__device__ __forceinline__ double frag(const double* S, bool kmajor, int i8, int kk, int lane) {
+template <int TI, bool kmajor>
+__device__ __forceinline__ double frag(const double* S, int i8, int kk, int lane) {
     // element(k = kk + lane%4, i = i8 + lane/4)
     return kmajor ? S[(kk + (lane & 3)) * (TI + 8) + i8 + (lane >> 2)] : S[(i8 + (lane >> 2)) * AL_SI + kk + (lane & 3)];
 }
@@ -158,23 +156,26 @@ __device__ __forceinline__ double frag(const double* S, bool kmajor, int i8, int
 // (n even; the caller guards n+1 < N); slot = 0/1 tells which of the two fragments of the row it is, and pre(slot, m, n)
 // is called for both fragments before either ep so that an epilogue can issue its global loads together.
 // All threads of the CTA must call it. `pool` holds the two stages.
-template <class EP, class PRE>
-__device__ __noinline__ void cta_gemm(const Operand& Mop, const Operand& Nop, int K, double* pool, EP ep, PRE pre) {
+#define MVMC_ALS_GEMM_ATTR __forceinline__   // (a non-inlined copy per product measured 35 % slower: operand structs through memory)
+template <bool MK, bool NK, class EP, class PRE>
+__device__ MVMC_ALS_GEMM_ATTR void cta_gemm(const Operand Mop, const Operand Nop, int K, double* pool, EP ep, PRE pre) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp & 1, wn = warp >> 1;               // warp tile: rows 32*wm.., columns 24*wn..
     const int M = Mop.I, N = Nop.I;
     const int nk = (K + AL_KC - 1) / AL_KC;
     for (int m0 = 0; m0 < M; m0 += AL_TM) {
-        const int mt = min(8, (M - m0 + 7) >> 3);           // live row tiles of this CTA tile
+        const int mw0 = m0 + 32 * wm;
+        const int mt = mw0 >= M ? 0 : min(4, (M - mw0 + 7) >> 3);       // live row tiles of this warp
         for (int n0 = 0; n0 < N; n0 += AL_TN) {
-            const int nw0 = n0 + warp * 16;                   // this warp's 16 columns
-            const int nt = nw0 >= N ? 0 : min(2, (N - nw0 + 7) >> 3);
-            double acc[8][2][2];
+            const int nw0 = n0 + 24 * wn;
+            const int nt = (nw0 >= N || mt == 0) ? 0 : min(3, (N - nw0 + 7) >> 3);
+            double acc[4][3][2];
 #pragma unroll
-            for (int a = 0; a < 8; a++)
+            for (int a = 0; a < 4; a++)
 #pragma unroll
-                for (int b = 0; b < 2; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-            Stager<AL_TM> sm_;
-            Stager<AL_TN> sn_;
+                for (int b = 0; b < 3; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+            Stager<AL_TM, MK> sm_;
+            Stager<AL_TN, NK> sn_;
             sm_.init(Mop, m0);
             sn_.init(Nop, n0);
             __syncthreads();   // the pool may still be read by the previous tile / another phase
@@ -198,14 +199,16 @@ __device__ __noinline__ void cta_gemm(const Operand& Mop, const Operand& Nop, in
                     const double* Sn = cur + AL_STAGE_M;
 #pragma unroll
                     for (int kk = 0; kk < AL_KC; kk += 4) {
-                        const double b0 = frag<AL_TN>(Sn, Nop.kmajor, warp * 16, kk, lane);
-                        const double b1 = nt > 1 ? frag<AL_TN>(Sn, Nop.kmajor, warp * 16 + 8, kk, lane) : 0.0;
+                        double bf[3];
 #pragma unroll
-                        for (int a = 0; a < 8; a++) {
+                        for (int b = 0; b < 3; b++) bf[b] = b < nt ? frag<AL_TN, NK>(Sn, 24 * wn + 8 * b, kk, lane) : 0.0;
+#pragma unroll
+                        for (int a = 0; a < 4; a++) {
                             if (a < mt) {
-                                const double av = frag<AL_TM>(Sm, Mop.kmajor, a * 8, kk, lane);
-                                dmma(acc[a][0][0], acc[a][0][1], av, b0);
-                                if (nt > 1) dmma(acc[a][1][0], acc[a][1][1], av, b1);
+                                const double av = frag<AL_TM, MK>(Sm, 32 * wm + 8 * a, kk, lane);
+#pragma unroll
+                                for (int b = 0; b < 3; b++)
+                                    if (b < nt) dmma(acc[a][b][0], acc[a][b][1], av, bf[b]);
                             }
                         }
                     }
@@ -213,16 +216,20 @@ __device__ __noinline__ void cta_gemm(const Operand& Mop, const Operand& Nop, in
                 __syncthreads();
             }
 #pragma unroll
-            for (int a = 0; a < 8; a++) {
+            for (int a = 0; a < 4; a++) {
                 if (a < mt) {
-                    const int m = m0 + a * 8 + (lane >> 2);
-                    const int na = nw0 + 2 * (lane & 3), nb = na + 8;
-                    const bool oka = nt > 0 && m < M && na < N, okb = nt > 1 && m < M && nb < N;
-                    // loads of both fragments of the row first, then the arithmetic and the stores
-                    if (oka) pre(0, m, na);
-                    if (okb) pre(1, m, nb);
-                    if (oka) ep(0, m, na, acc[a][0][0], acc[a][0][1]);
-                    if (okb) ep(1, m, nb, acc[a][1][0], acc[a][1][1]);
+                    const int m = mw0 + a * 8 + (lane >> 2);
+                    // loads of all fragments of the row first, then the arithmetic and the stores
+#pragma unroll
+                    for (int b = 0; b < 3; b++) {
+                        const int nn = nw0 + 8 * b + 2 * (lane & 3);
+                        if (b < nt && m < M && nn < N) pre(b, m, nn);
+                    }
+#pragma unroll
+                    for (int b = 0; b < 3; b++) {
+                        const int nn = nw0 + 8 * b + 2 * (lane & 3);
+                        if (b < nt && m < M && nn < N) ep(b, m, nn, acc[a][b][0], acc[a][b][1]);
+                    }
                 }
             }
         }
@@ -285,7 +292,7 @@ struct AlsLayout {
     }
 };
 
-__global__ void __launch_bounds__(AL_THREADS, 3)
+__global__ void __launch_bounds__(AL_THREADS, 2)
     k_als(const double* __restrict__ sim, const int* __restrict__ dim_groups, int n_groups,
           const int* __restrict__ f32_first_iter, const double* __restrict__ rand_stream, int N, int rmax,
           double* __restrict__ ws, uint32_t* __restrict__ xbin, int* __restrict__ n_iter_out, double alpha, double beta,
@@ -354,49 +361,49 @@ __global__ void __launch_bounds__(AL_THREADS, 3)
         const double reg = alpha / mu;
         // ---- G = A^T A + reg I, inverted ----
         {
-            const Operand opA{A, ldr, r, true};
-            cta_gemm(opA, opA, n, pool, [&](int, int m, int nn, double v0, double v1) {
+            const Operand opA{A, ldr, r};
+            cta_gemm<KMAJ, KMAJ>(opA, opA, n, pool, [&](int, int m, int nn, double v0, double v1) {
                 Gg[(size_t)m * ldr + nn] = (m == nn) ? v0 + reg * 1.0 : v0 + reg * 0.0;
                 if (nn + 1 < r) Gg[(size_t)m * ldr + nn + 1] = (m == nn + 1) ? v1 + reg * 1.0 : v1 + reg * 0.0;
             }, NoPre());
         }
         invert_normal_matrix(Gg, r, ldr, pool, inv_aux);
         // ---- T = A^T Xt ----
-        cta_gemm(Operand{A, ldr, r, true}, Operand{Xt, ldn, n, true}, n, pool, [&](int, int m, int nn, double v0, double v1) {
+        cta_gemm<KMAJ, KMAJ>(Operand{A, ldr, r}, Operand{Xt, ldn, n}, n, pool, [&](int, int m, int nn, double v0, double v1) {
             Tm[(size_t)m * ldn + nn] = v0;
             if (nn + 1 < n) Tm[(size_t)m * ldn + nn + 1] = v1;
         }, NoPre());
         __syncthreads();
         // ---- B = (Ginv T)^T ----
-        cta_gemm(Operand{Gg, ldr, r, false}, Operand{Tm, ldn, n, true}, r, pool, [&](int, int m, int nn, double v0, double v1) {
+        cta_gemm<IMAJ, KMAJ>(Operand{Gg, ldr, r}, Operand{Tm, ldn, n}, r, pool, [&](int, int m, int nn, double v0, double v1) {
             Bm[(size_t)nn * ldr + m] = v0;
             if (nn + 1 < n) Bm[(size_t)(nn + 1) * ldr + m] = v1;
         }, NoPre());
         __syncthreads();
         // ---- H = B^T B + reg I, inverted ----
         {
-            const Operand opB{Bm, ldr, r, true};
-            cta_gemm(opB, opB, n, pool, [&](int, int m, int nn, double v0, double v1) {
+            const Operand opB{Bm, ldr, r};
+            cta_gemm<KMAJ, KMAJ>(opB, opB, n, pool, [&](int, int m, int nn, double v0, double v1) {
                 Gg[(size_t)m * ldr + nn] = (m == nn) ? v0 + reg : v0;
                 if (nn + 1 < r) Gg[(size_t)m * ldr + nn + 1] = (m == nn + 1) ? v1 + reg : v1;
             }, NoPre());
         }
         invert_normal_matrix(Gg, r, ldr, pool, inv_aux);
         // ---- T = B^T Xt^T : T[m][i] = sum_j B[j][m] Xt[i][j] ----
-        cta_gemm(Operand{Bm, ldr, r, true}, Operand{Xt, ldn, n, false}, n, pool, [&](int, int m, int nn, double v0, double v1) {
+        cta_gemm<KMAJ, IMAJ>(Operand{Bm, ldr, r}, Operand{Xt, ldn, n}, n, pool, [&](int, int m, int nn, double v0, double v1) {
             Tm[(size_t)m * ldn + nn] = v0;
             if (nn + 1 < n) Tm[(size_t)m * ldn + nn + 1] = v1;
         }, NoPre());
         __syncthreads();
         // ---- A = (Hinv T)^T ----
-        cta_gemm(Operand{Gg, ldr, r, false}, Operand{Tm, ldn, n, true}, r, pool, [&](int, int m, int nn, double v0, double v1) {
+        cta_gemm<IMAJ, KMAJ>(Operand{Gg, ldr, r}, Operand{Tm, ldn, n}, r, pool, [&](int, int m, int nn, double v0, double v1) {
             A[(size_t)nn * ldr + m] = v0;
             if (nn + 1 < n) A[(size_t)(nn + 1) * ldr + m] = v1;
         }, NoPre());
         __syncthreads();
         // ---- X = A B^T, fused with the Z / Y / next-Xt updates and both residual norms ----
         double pacc = 0.0, dacc = 0.0;
-        double2 ex0[2], ey[2], ew[2];   // X_prev, Y, W of the two fragments of a row (16-byte loads, issued together)
+        double2 ex0[3], ey[3], ew[3];   // X_prev, Y, W of the three fragments of a row (16-byte loads, issued together)
         auto one = [&](int i, int j, double x, double x0, double y, double w, bool live, double& yn, double& z, double& xt) {
             const double dd = x - x0;
             z = x + y / mu;
@@ -412,7 +419,7 @@ __global__ void __launch_bounds__(AL_THREADS, 3)
                 pacc += pd * pd;
             }
         };
-        cta_gemm(Operand{A, ldr, n, false}, Operand{Bm, ldr, n, false}, r, pool,
+        cta_gemm<IMAJ, IMAJ>(Operand{A, ldr, n}, Operand{Bm, ldr, n}, r, pool,
                  [&](int slot, int i, int j, double v0, double v1) {
                      const size_t o = (size_t)i * ldn + j;
                      const bool live1 = j + 1 < n;   // the odd column of the last pair may be padding (written, never read)

@@ -1,0 +1,52 @@
+"""Multi-GPU sharding of the capture path: by clip, nothing else.
+
+Clips share no state and the frames of one clip are sequentially dependent (track table, IK warm start), so the only
+parallel axis across GPUs is the clip: rank r of G owns clips r, r+G, r+2G, ... One process per GPU
+(torch.distributed: NCCL on GPUs, gloo in the CPU test tier); there is no collective inside the per-frame loop. After a
+batch of frames the ranks exchange fixed-stride result records (or just their summaries) with one all_gather."""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_clips(n_clips: int, rank: int, world: int) -> np.ndarray:
+    """Global indices of the clips rank `rank` of `world` processes owns (round robin, as BASELINE config 5)."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world {world}")
+    return np.arange(rank, n_clips, world)
+
+
+def clip_owner(clip: int, world: int) -> int:
+    return clip % world
+
+
+def gather_records(local: np.ndarray, n_clips: int, device=None):
+    """all_gather of per-clip fixed-stride records. `local` [n_local, ...] holds this rank's clips in shard order; returns
+    [n_clips, ...] in global clip order on every rank. Works without an initialised process group (world of one)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return local.copy()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per = -(-n_clips // world)
+    item = local.dtype.itemsize * int(np.prod(local.shape[1:], dtype=np.int64))
+    buf = np.zeros((per, item), dtype=np.uint8)
+    buf[:len(local)] = np.ascontiguousarray(local).view(np.uint8).reshape(len(local), item)
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    t = torch.from_numpy(buf).to(dev)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    out = np.zeros((n_clips,) + local.shape[1:], dtype=local.dtype)
+    for r, p in enumerate(parts):
+        idx = shard_clips(n_clips, r, world)
+        rows = p.cpu().numpy()[:len(idx)]
+        out[idx] = rows.reshape(-1).view(local.dtype).reshape((len(idx),) + local.shape[1:])
+    return out
+
+
+def reduce_max(value: float, device=None) -> float:
+    """max over ranks (device timings are reported as the max over ranks)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

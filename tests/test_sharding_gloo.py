@@ -1,0 +1,81 @@
+"""Multi-process path on CPU: world_size 2 over gloo. Each rank tracks its shard of replicated/independent clips through
+the clip pipeline (kernel emulator), results are all_gathered and must equal a single-process run of all clips."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import EMU_LIB, ROOT, golden, pad_poses
+
+from multiview_motion_capture_b200 import sharding
+
+
+def test_shard_clips_partition():
+    for n, w in [(4096, 8), (7, 2), (5, 8), (0, 3)]:
+        parts = [sharding.shard_clips(n, r, w) for r in range(w)]
+        assert sorted(np.concatenate(parts).tolist()) == list(range(n))
+        assert all(sharding.clip_owner(int(c), w) == r for r, p in enumerate(parts) for c in p)
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_clips(4, 2, 2)
+
+
+def _inputs(n_clips):
+    """n_clips clips = the c4p3 synthetic golden scene with the frames rotated by clip index (so clips differ)."""
+    import mvmc_oracle as o
+    inp, _ = golden("synth_c4p3")
+    kps = o.body25_to_coco(inp["kps25"])
+    frames = [2 + (c % 3) for c in range(n_clips)]
+    return inp, kps, frames
+
+
+def _track(clip_ids):
+    """One tracked frame (births at frame f, update at f+1) for the given global clip ids; returns their records."""
+    from multiview_motion_capture_b200 import _lib
+    from multiview_motion_capture_b200.clips import ClipBatch
+    _lib.use_library(EMU_LIB)
+    inp, kps, frames = _inputs(max(clip_ids) + 1)
+    B = len(clip_ids)
+    cb = ClipBatch(B, 4, 4, max_tracks=8, max_new=4, device="cpu")
+    cb.set_calib(np.repeat(inp["K"][None], B, 0), np.repeat(inp["RT"][None], B, 0))
+    rec = None
+    for step in range(2):
+        k = np.stack([pad_poses(kps[frames[c] + step], 4) for c in clip_ids])
+        n = np.stack([inp["n_pose"][frames[c] + step] for c in clip_ids])
+        rec = cb.step(k, n, step + 1).copy()
+    cb.close()
+    return rec
+
+
+def _worker(rank, world, port, n_clips, out_dir):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = sharding.shard_clips(n_clips, rank, world)
+        rec = _track(mine.tolist())
+        allrec = sharding.gather_records(rec, n_clips)
+        slowest = sharding.reduce_max(float(rank + 1))
+        if rank == 0:
+            np.save(os.path.join(out_dir, "gathered.npy"), allrec.view(np.uint8))
+            np.save(os.path.join(out_dir, "max.npy"), np.array([slowest]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_equal_single_process(tmp_path, emu):
+    from multiview_motion_capture_b200._lib import STEP_OUT_DTYPE
+    n_clips, world = 3, 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, n_clips, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "gathered.npy").view(STEP_OUT_DTYPE).reshape(n_clips)
+    ref = _track(list(range(n_clips)))
+    assert float(np.load(tmp_path / "max.npy")[0]) == 2.0
+    for c in range(n_clips):
+        n = int(ref[c]["n_alive"])
+        assert n == int(got[c]["n_alive"]) and n >= 2
+        assert got[c].tobytes() == ref[c].tobytes(), c      # bit-identical records wherever a clip is tracked
