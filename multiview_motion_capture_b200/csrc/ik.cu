@@ -98,27 +98,61 @@ __device__ void fk_b18(const double* x, const double* lens, double (*pos)[3]) {
     }
 }
 
-// The same chain as a compact rolled loop with everything in registers: getx(i) supplies parameter i of
-// [root | euler | side lengths] (68), emit(j, x, y, z) receives joint j. Only three global rotations are ever live -
+// The chain inside the solver. A Jacobian column perturbs ONE parameter, so only one local rotation differs from the
+// unperturbed pose: the 12 non-leaf local rotations of the current x are formed once (one lane each, `local_rots`) and
+// parked in shared memory; every lane then walks the chain with its own override of a single joint (and of the root
+// translation / a bone length, through getx). Same arithmetic as evaluating the whole pose per column, 12x fewer
+// sincos. The walk is a compact rolled loop with everything in registers: only three global rotations are ever live -
 // the root's, the neck's (joint 8, parent of both arms and the head) and the current chain's - so the parent of a
 // joint is a 3-way select instead of an indexed (local-memory) array. Leaf rotations are never formed (no joint
 // position depends on them). Kept rolled on purpose: unrolled it is ~4.5k instructions per call site and the solver
 // kernel outgrew the instruction cache.
 __constant__ unsigned char c_fk_psel[MVMC_N_B18] = {0, 1, 0, 0, 1, 0, 0, 1, 0, 2, 0, 0, 2, 0, 0, 2, 0, 0};   // 0 cur, 1 root, 2 neck
-template <class GetX, class Emit>
-__device__ __forceinline__ void fk_rolled(GetX getx, Emit emit) {
-    double Gc[9], Gr[9], Gn[9], pc[3], pr[3], pn[3];
-    {
-        euler_to_mat(getx(3), getx(4), getx(5), Gr);
-        pr[0] = getx(0);
-        pr[1] = getx(1);
-        pr[2] = getx(2);
+
+// Rloc[j][9] <- local rotation of joint j at pose x, non-leaf joints only (lane j computes joint j)
+__device__ __noinline__ void local_rots(const double* x, double* Rloc) {
+    const int j = threadIdx.x & 31;
+    if (j < MVMC_N_B18 && !c_skel.leaf[j]) {
+        double m[9];
+        euler_to_mat(x[3 + 3 * j], x[4 + 3 * j], x[5 + 3 * j], m);
 #pragma unroll
-        for (int q = 0; q < 9; q++) Gc[q] = Gn[q] = Gr[q];
-#pragma unroll
-        for (int q = 0; q < 3; q++) pc[q] = pn[q] = pr[q];
-        emit(0, pr[0], pr[1], pr[2]);
+        for (int q = 0; q < 9; q++) Rloc[j * 9 + q] = m[q];
     }
+    __syncwarp();
+}
+
+// Walks the chain of pose x with parameter `prm` replaced by `xp` (prm < 0: no override) and stores joint j at
+// out[j*3*stride + k*stride] - the 16 observed joints only (slot order) when `ik_slots`, else all 18. One copy for the
+// whole kernel. `Rloc` must hold local_rots(x).
+__device__ __noinline__ void fk_store(const double* x, const double* Rloc, int prm, double xp, double* out, int stride,
+                                      bool ik_slots, bool on) {
+    auto getx = [&](int i) { return i == prm ? xp : x[i]; };
+    // the one local rotation this call overrides (computed by every lane to stay convergent; unused when jo < 0)
+    const int jo = (prm >= 3 && prm < 57) ? (prm - 3) / 3 : -1;
+    double mo[9];
+    {
+        const int jj = jo < 0 ? 0 : jo;
+        euler_to_mat(getx(3 + 3 * jj), getx(4 + 3 * jj), getx(5 + 3 * jj), mo);
+    }
+    double Gc[9], Gr[9], Gn[9], pc[3], pr[3], pn[3];
+#pragma unroll
+    for (int q = 0; q < 9; q++) Gr[q] = jo == 0 ? mo[q] : Rloc[q];
+    pr[0] = getx(0);
+    pr[1] = getx(1);
+    pr[2] = getx(2);
+#pragma unroll
+    for (int q = 0; q < 9; q++) Gc[q] = Gn[q] = Gr[q];
+#pragma unroll
+    for (int q = 0; q < 3; q++) pc[q] = pn[q] = pr[q];
+    auto emit = [&](int j, double px, double py, double pz) {
+        const int sl = ik_slots ? c_skel.ik_slot[j] : j;
+        if (sl >= 0 && on) {
+            out[(sl * 3) * stride] = px;
+            out[(sl * 3 + 1) * stride] = py;
+            out[(sl * 3 + 2) * stride] = pz;
+        }
+    };
+    emit(0, pr[0], pr[1], pr[2]);
 #pragma unroll 1
     for (int j = 1; j < MVMC_N_B18; j++) {
         const int sel = c_fk_psel[j];
@@ -135,7 +169,8 @@ __device__ __forceinline__ void fk_rolled(GetX getx, Emit emit) {
         emit(j, pj[0], pj[1], pj[2]);
         if (!c_skel.leaf[j]) {   // uniform branch
             double m[9];
-            euler_to_mat(getx(3 + 3 * j), getx(4 + 3 * j), getx(5 + 3 * j), m);
+#pragma unroll
+            for (int q = 0; q < 9; q++) m[q] = j == jo ? mo[q] : Rloc[j * 9 + q];
 #pragma unroll
             for (int r = 0; r < 3; r++)
 #pragma unroll
@@ -152,21 +187,6 @@ __device__ __forceinline__ void fk_rolled(GetX getx, Emit emit) {
     }
 }
 
-// One copy of the chain for the whole kernel: evaluates the pose x (with parameter `prm` replaced by `xp` when
-// prm >= 0) and stores joint j at out[j*3*stride + k*stride] - the 16 observed joints only (slot order) when
-// `ik_slots`, else all 18.
-__device__ __noinline__ void fk_store(const double* x, int prm, double xp, double* out, int stride, bool ik_slots, bool on) {
-    fk_rolled([&](int i) { return i == prm ? xp : x[i]; },
-              [&](int j, double px, double py, double pz) {
-                  const int sl = ik_slots ? c_skel.ik_slot[j] : j;
-                  if (sl >= 0 && on) {
-                      out[(sl * 3) * stride] = px;
-                      out[(sl * 3 + 1) * stride] = py;
-                      out[(sl * 3 + 2) * stride] = pz;
-                  }
-              });
-}
-
 __device__ __forceinline__ void project3(const double* Pv, double X, double Y, double Z, double& pu, double& pv, double& pw) {
     pu = Pv[0] * X + Pv[1] * Y + Pv[2] * Z + Pv[3];
     pv = Pv[4] * X + Pv[5] * Y + Pv[6] * Z + Pv[7];
@@ -179,6 +199,7 @@ struct IkRes {
     const double* obs;   // [V][16][3] gathered at c_ik_obs_idx (shared)
     const double* P;     // [V][12] (shared)
     double* posb;        // [16][3] scratch (shared)
+    double* Rloc;        // [18][9] local rotations of the pose being differentiated / evaluated (shared)
     int V;
     __device__ int m() const { return V * MVMC_N_IKJ * 2; }
     __device__ int n_chunks() const { return 2 * V; }
@@ -189,16 +210,19 @@ struct IkRes {
         const int lane = threadIdx.x & 31;
         double* pb = posb;
         // the chain is evaluated redundantly by every lane (uniform control flow); lane 0 parks the positions
-        fk_store(x, -1, 0.0, pb, 1, true, lane == 0);
+        local_rots(x, Rloc);
+        fk_store(x, Rloc, -1, 0.0, pb, 1, true, lane == 0);
         __syncwarp();
         for (int it = lane; it < V * MVMC_N_IKJ; it += 32) {
             const int v = it >> 4, q = it & 15;
             const double* o = obs + it * 3;
             double pu, pv, pw;
             project3(P + v * 12, pb[q * 3], pb[q * 3 + 1], pb[q * 3 + 2], pu, pv, pw);
-            const double den = 1e-5 + pw;
-            f[2 * it] = DMUL(DSUB(DDIV(pu, den), o[0]), o[2]);
-            f[2 * it + 1] = DMUL(DSUB(DDIV(pv, den), o[1]), o[2]);
+            // one reciprocal instead of two divisions - the same expression in eval and in the Jacobian columns, so the
+            // forward differences see a consistent rounding (the quotient differs from pu/den by <= 1 ulp)
+            const double inv = 1.0 / (1e-5 + pw);
+            f[2 * it] = DMUL(DSUB(DMUL(pu, inv), o[0]), o[2]);
+            f[2 * it + 1] = DMUL(DSUB(DMUL(pv, inv), o[1]), o[2]);
         }
         __syncwarp();
     }
@@ -206,12 +230,13 @@ struct IkRes {
     __device__ void fd_prepare(TrfWarp& s, int ncol) {
         const int lane = threadIdx.x & 31;
         double* S = s.A;
+        local_rots(s.x, Rloc);
         for (int c0 = 0; c0 < ncol; c0 += 32) {
             const int c = c0 + lane;
             const bool on = c < ncol;
             const int prm = on ? s.act[c] : -1;
             const double xp = on ? s.w[c] : 0.0;
-            fk_store(s.x, prm, xp, S + c, WS_NC, true, on);
+            fk_store(s.x, Rloc, prm, xp, S + c, WS_NC, true, on);
         }
     }
     __device__ __noinline__ void fd_chunk(TrfWarp& s, int ncol, int ch, const double* f) {
@@ -222,19 +247,19 @@ struct IkRes {
 #pragma unroll
         for (int e = 0; e < 12; e++) Pv[e] = P[v * 12 + e];
         for (int c = lane; c < ncol; c += 32) {
-            const double dx = s.dx[c];
+            const double rdx = 1.0 / s.dx[c];
 #pragma unroll
             for (int qq = 0; qq < 8; qq++) {
                 const int q = q0 + qq;
                 const double* o = obs + (v * MVMC_N_IKJ + q) * 3;
                 double pu, pv, pw;
                 project3(Pv, S[(q * 3) * WS_NC + c], S[(q * 3 + 1) * WS_NC + c], S[(q * 3 + 2) * WS_NC + c], pu, pv, pw);
-                const double den = 1e-5 + pw;
-                const double ru = DMUL(DSUB(DDIV(pu, den), o[0]), o[2]);
-                const double rv = DMUL(DSUB(DDIV(pv, den), o[1]), o[2]);
+                const double inv = 1.0 / (1e-5 + pw);
+                const double ru = DMUL(DSUB(DMUL(pu, inv), o[0]), o[2]);
+                const double rv = DMUL(DSUB(DMUL(pv, inv), o[1]), o[2]);
                 const int row = (v * MVMC_N_IKJ + q) * 2;
-                s.Jc[(2 * qq) * WS_LDJ + c] = DDIV(DSUB(ru, f[row]), dx);
-                s.Jc[(2 * qq + 1) * WS_LDJ + c] = DDIV(DSUB(rv, f[row + 1]), dx);
+                s.Jc[(2 * qq) * WS_LDJ + c] = DMUL(DSUB(ru, f[row]), rdx);
+                s.Jc[(2 * qq + 1) * WS_LDJ + c] = DMUL(DSUB(rv, f[row + 1]), rdx);
             }
         }
     }
@@ -379,6 +404,7 @@ struct alignas(16) IkWarpSh {
     double obs18[VMAX * 18 * 3];
     double P[VMAX * 12];
     double posb[MVMC_N_IKJ * 3];
+    double Rloc[MVMC_N_B18 * 9];
     double p3[18 * 4];
 };
 
@@ -490,7 +516,7 @@ __global__ void __launch_bounds__(32)
             for (int e = lane; e < MVMC_N_PARAM; e += 32) sh.t.x[e] = x0[(size_t)mI * MVMC_N_PARAM + e];
         }
         __syncwarp();
-        IkRes res{sh.obs16, sh.P, sh.posb, nv};
+        IkRes res{sh.obs16, sh.P, sh.posb, sh.Rloc, nv};
         TrfResult r[2];
         int ncols[2];
 #pragma unroll 1
@@ -513,7 +539,8 @@ __global__ void __launch_bounds__(32)
             __syncwarp();
         }
         for (int e = lane; e < MVMC_N_PARAM; e += 32) x_out[(size_t)mI * MVMC_N_PARAM + e] = sh.t.x[e];
-        fk_store(sh.t.x, -1, 0.0, joints + (size_t)mI * MVMC_N_B18 * 3, 1, false, lane == 0);
+        local_rots(sh.t.x, sh.Rloc);
+        fk_store(sh.t.x, sh.Rloc, -1, 0.0, joints + (size_t)mI * MVMC_N_B18 * 3, 1, false, lane == 0);
         if (lane == 0) {
             for (int q = 0; q < 2; q++) {
                 inf[4 * q] = r[q].nfev;
