@@ -232,6 +232,9 @@ int mvmc_clips_profile(mvmc_clips* h, int enable, double* out_ms, int* n_steps, 
 /* FP64 DFMA peak probe (roofline denominator for the FP64-issue-bound kernels): blocks x 256 threads x
  * iters x 8 FMAs. Time it with events on `stream`; flops = blocks*256*iters*16. */
 int mvmc_fp64_probe(int blocks, int iters, double* sink, void* stream);
+/* Same for the FP64 tensor cores (mma.sync.m8n8k4.f64, the instruction k_als runs on): blocks x 8 warps x iters x 8 DMMA;
+ * flops = blocks*8*iters*8*512. */
+int mvmc_fp64_tensor_probe(int blocks, int iters, double* sink, void* stream);
 
 /* number of kernel launches enqueued by this library since load (for bench.py's gpu_launches) */
 unsigned long long mvmc_launch_count(void);

@@ -65,6 +65,7 @@ _SIGNATURES = {
     "mvmc_clips_stats_host": (c_int, [c_void_p, _P, c_int, _P]),
     "mvmc_clips_profile": (c_int, [c_void_p, c_int, _P, _P, _P]),
     "mvmc_fp64_probe": (c_int, [c_int, c_int, _P, _P]),
+    "mvmc_fp64_tensor_probe": (c_int, [c_int, c_int, _P, _P]),
     "mvmc_launch_count": (c_ulonglong, []),
 }
 

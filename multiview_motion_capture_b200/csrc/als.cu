@@ -32,9 +32,8 @@ constexpr int AL_STAGE_M = (AL_KC * AL_SKM > AL_TM * AL_SI) ? AL_KC * AL_SKM : A
 constexpr int AL_STAGE_N = (AL_KC * AL_SKN > AL_TN * AL_SI) ? AL_KC * AL_SKN : AL_TN * AL_SI;
 constexpr int AL_STAGE = AL_STAGE_M + AL_STAGE_N;
 constexpr int AL_POOL = 8192;             // doubles of shared memory shared by the two stages and the r x r inverse
-constexpr int AL_RSMEM = 88;              // largest r whose normal matrix is inverted in shared memory
+constexpr int AL_RSMEM = 88;              // largest r whose normal matrix is inverted in registers (11 rows x 8 warps)
 static_assert(2 * AL_STAGE <= AL_POOL, "stages must fit the pool");
-static_assert(AL_RSMEM * (AL_RSMEM + 1) <= AL_POOL, "inverse must fit the pool");
 
 // ---- asynchronous 16-byte global -> shared copies with zero fill ----
 __device__ __forceinline__ void cp16(double* dst, const double* src, int n_valid /*0,1,2 doubles*/) {
@@ -239,15 +238,70 @@ struct NoPre {
     __device__ __forceinline__ void operator()(int, int, int) const {}
 };
 
-// In-place inverse of the SPD r x r matrix G (leading dimension ldg) by Gauss-Jordan without pivoting. Thread t owns
-// the columns j = t % 32 + 32 q of the rows i = t / 32 + nw p (nw = warps of the CTA): no index division in the loop, and
-// two barriers per pivot (the scaled pivot row and the pivot column are parked in `aux` [2 r] first).
+// Inverse of the SPD r x r matrix Gg (global, leading dimension ldr) by Gauss-Jordan without pivoting, REGISTER resident:
+// thread (warp w, lane l) owns the elements (i = w + 8a, j = l + 32b) for the whole elimination (<= 11 x 3 doubles), so
+// a pivot step is: the owners of row k / column k publish them (double-buffered in `aux`, [2][2][96]), ONE barrier, then
+// every thread updates its own registers - no shared-memory read-modify-write, no index arithmetic. r <= 88.
+constexpr int GJ_A = 11, GJ_B = 3, GJ_LD = 96;
+__device__ void invert_spd_regs(double* Gg, int r, int ldr, double* aux) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double g[GJ_A][GJ_B];
+#pragma unroll
+    for (int a = 0; a < GJ_A; a++)
+#pragma unroll
+        for (int b = 0; b < GJ_B; b++) {
+            const int i = w + 8 * a, j = lane + 32 * b;
+            g[a][b] = (i < r && j < r) ? Gg[(size_t)i * ldr + j] : 0.0;
+        }
+    for (int k = 0; k < r; k++) {
+        double* rk = aux + (k & 1) * 2 * GJ_LD;   // pivot row (raw)
+        double* ck = rk + GJ_LD;                  // pivot column (raw)
+        // publish row k (owned by warp k % 8, slot a = k / 8) and column k (lane k % 32, slot b = k / 32)
+#pragma unroll
+        for (int a = 0; a < GJ_A; a++)
+#pragma unroll
+            for (int b = 0; b < GJ_B; b++) {
+                const int i = w + 8 * a, j = lane + 32 * b;
+                if (i == k && j < r) rk[j] = g[a][b];
+                if (j == k && i < r) ck[i] = g[a][b];
+            }
+        __syncthreads();
+        const double p = 1.0 / rk[k];
+#pragma unroll
+        for (int a = 0; a < GJ_A; a++) {
+            const int i = w + 8 * a;
+            if (i < r) {   // uniform per warp
+                const double f = ck[i];
+#pragma unroll
+                for (int b = 0; b < GJ_B; b++) {
+                    const int j = lane + 32 * b;
+                    if (j < r) {
+                        const double rkj = rk[j] * p;
+                        if (i == k) g[a][b] = (j == k) ? p : rkj;
+                        else g[a][b] = (j == k) ? -f * p : g[a][b] - f * rkj;
+                    }
+                }
+            }
+        }
+        // (the next pivot publishes into the other half of aux; the barrier after it orders the reuse of this half)
+    }
+#pragma unroll
+    for (int a = 0; a < GJ_A; a++)
+#pragma unroll
+        for (int b = 0; b < GJ_B; b++) {
+            const int i = w + 8 * a, j = lane + 32 * b;
+            if (i < r && j < r) Gg[(size_t)i * ldr + j] = g[a][b];
+        }
+}
+
+// Fallback for r > 88: in place in global memory, thread t owns columns t % 32 + 32q of rows t / 32 + nw p.
 __device__ void invert_spd(double* G, int r, int ldg, double* aux) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     double* rk = aux;        // pivot row * (1 / pivot)
-    double* ck = aux + r;    // pivot column
+    double* ck = aux + 128;  // pivot column
     for (int k = 0; k < r; k++) {
         const double p = 1.0 / G[k * ldg + k];
+        __syncthreads();
         for (int j = threadIdx.x; j < r; j += blockDim.x) {
             rk[j] = G[k * ldg + j] * p;
             ck[j] = G[j * ldg + k];
@@ -266,18 +320,11 @@ __device__ void invert_spd(double* G, int r, int ldg, double* aux) {
     }
 }
 
-// Gg (r x r, ld ldr, global) <- inverse of Gg; through shared memory when it fits
-__device__ void invert_normal_matrix(double* Gg, int r, int ldr, double* pool, double* aux) {
+// Gg (r x r, ld ldr, global) <- inverse of Gg
+__device__ void invert_normal_matrix(double* Gg, int r, int ldr, double* aux) {
     __syncthreads();
-    if (r <= AL_RSMEM) {
-        const int ldg = r + 1;
-        for (int e = threadIdx.x; e < r * r; e += blockDim.x) pool[(e / r) * ldg + (e % r)] = Gg[(size_t)(e / r) * ldr + (e % r)];
-        __syncthreads();
-        invert_spd(pool, r, ldg, aux);
-        for (int e = threadIdx.x; e < r * r; e += blockDim.x) Gg[(size_t)(e / r) * ldr + (e % r)] = pool[(e / r) * ldg + (e % r)];
-    } else {
-        invert_spd(Gg, r, ldr, aux);
-    }
+    if (r <= AL_RSMEM) invert_spd_regs(Gg, r, ldr, aux);
+    else invert_spd(Gg, r, ldr, aux);
     __syncthreads();
 }
 
@@ -314,8 +361,8 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
 
     double* pool = smem;                       // [AL_POOL] stages / inverse
     double* scratch = pool + AL_POOL;          // [32]
-    double* inv_aux = scratch + 32;            // [2 * 128] pivot row / column of the Gauss-Jordan inverse
-    int* s_grp = reinterpret_cast<int*>(inv_aux + 256);   // [N]
+    double* inv_aux = scratch + 32;            // [4 * 96] pivot row / column of the Gauss-Jordan inverse, double buffered
+    int* s_grp = reinterpret_cast<int*>(inv_aux + 4 * GJ_LD);   // [N]
 
     const AlsLayout L(N, rmax);
     const int ldn = L.ldn, ldr = L.ldr;
@@ -367,7 +414,7 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
                 if (nn + 1 < r) Gg[(size_t)m * ldr + nn + 1] = (m == nn + 1) ? v1 + reg * 1.0 : v1 + reg * 0.0;
             }, NoPre());
         }
-        invert_normal_matrix(Gg, r, ldr, pool, inv_aux);
+        invert_normal_matrix(Gg, r, ldr, inv_aux);
         // ---- T = A^T Xt ----
         cta_gemm<KMAJ, KMAJ>(Operand{A, ldr, r}, Operand{Xt, ldn, n}, n, pool, [&](int, int m, int nn, double v0, double v1) {
             Tm[(size_t)m * ldn + nn] = v0;
@@ -388,7 +435,7 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
                 if (nn + 1 < r) Gg[(size_t)m * ldr + nn + 1] = (m == nn + 1) ? v1 + reg : v1;
             }, NoPre());
         }
-        invert_normal_matrix(Gg, r, ldr, pool, inv_aux);
+        invert_normal_matrix(Gg, r, ldr, inv_aux);
         // ---- T = B^T Xt^T : T[m][i] = sum_j B[j][m] Xt[i][j] ----
         cta_gemm<KMAJ, IMAJ>(Operand{Bm, ldr, r}, Operand{Xt, ldn, n}, n, pool, [&](int, int m, int nn, double v0, double v1) {
             Tm[(size_t)m * ldn + nn] = v0;
@@ -482,7 +529,7 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
 
 using namespace mvmc;
 
-static size_t als_smem_bytes(int N) { return (size_t)(AL_POOL + 32 + 256) * sizeof(double) + (size_t)N * sizeof(int); }
+static size_t als_smem_bytes(int N) { return (size_t)(AL_POOL + 32 + 4 * GJ_LD) * sizeof(double) + (size_t)N * sizeof(int); }
 
 extern "C" size_t mvmc_match_als_workspace_bytes(int B, int N, int rmax) {
     const AlsLayout L(N, rmax);

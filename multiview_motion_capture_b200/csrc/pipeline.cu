@@ -345,9 +345,40 @@ __global__ void __launch_bounds__(256) k_fp64_probe(int iters, double* __restric
     if (r == 1.2345) sink[0] = r;  // never true; keeps the chains alive
 }
 
+// FP64 tensor-core (DMMA m8n8k4) peak probe: 8 independent accumulator fragments per warp, `iters` x 8 x 512 flops per warp.
+__global__ void __launch_bounds__(256) k_fp64_tensor_probe(int iters, double* __restrict__ sink) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i][0] = c[i][1] = 0.0;
+    const double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-6;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+#ifdef MVMC_EMU
+            emu::dmma_884(c[i][0], c[i][1], a, b);
+#else
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1])
+                         : "d"(a), "d"(b));
+#endif
+        }
+    }
+    double r = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r += c[i][0] + c[i][1];
+    if (r == 1.2345) sink[0] = r;  // never true; keeps the chains alive
+}
+
 }  // namespace mvmc
 
 using namespace mvmc;
+
+extern "C" int mvmc_fp64_tensor_probe(int blocks, int iters, double* sink, void* stream) {
+    if (blocks <= 0 || iters <= 0 || !sink) return MVMC_ERR_INVALID;
+    MVMC_LAUNCH(k_fp64_tensor_probe, dim3(blocks), dim3(256), 0, stream, iters, sink);
+    MVMC_CHECK_LAUNCH("k_fp64_tensor_probe");
+    return MVMC_OK;
+}
 
 extern "C" int mvmc_fp64_probe(int blocks, int iters, double* sink, void* stream) {
     if (blocks <= 0 || iters <= 0 || !sink) return MVMC_ERR_INVALID;
