@@ -239,56 +239,75 @@ struct NoPre {
 };
 
 // Inverse of the SPD r x r matrix Gg (global, leading dimension ldr) by Gauss-Jordan without pivoting, REGISTER resident:
-// thread (warp w, lane l) owns the elements (i = w + 8a, j = l + 32b) for the whole elimination (<= 11 x 3 doubles), so
-// a pivot step is: the owners of row k / column k publish them (double-buffered in `aux`, [2][2][96]), ONE barrier, then
-// every thread updates its own registers - no shared-memory read-modify-write, no index arithmetic. r <= 88.
-constexpr int GJ_A = 11, GJ_B = 3, GJ_LD = 96;
+// thread (warp w, lane l) owns the elements (i = w + 8a, j = l + 32b), a < NA, b < NB, for the whole elimination, so a
+// pivot step is: the owners of row k / column k publish them (double-buffered in `aux`, [2][2][96]), ONE barrier, then
+// every thread does NA*NB fused multiply-adds on its own registers - no shared-memory read-modify-write, no index
+// arithmetic; the pivot row / column themselves are patched afterwards under (nearly) uniform branches.
+constexpr int GJ_LD = 96;
+template <int NA, int NB>
 __device__ void invert_spd_regs(double* Gg, int r, int ldr, double* aux) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double g[GJ_A][GJ_B];
+    double g[NA][NB];
 #pragma unroll
-    for (int a = 0; a < GJ_A; a++)
+    for (int a = 0; a < NA; a++)
 #pragma unroll
-        for (int b = 0; b < GJ_B; b++) {
+        for (int b = 0; b < NB; b++) {
             const int i = w + 8 * a, j = lane + 32 * b;
             g[a][b] = (i < r && j < r) ? Gg[(size_t)i * ldr + j] : 0.0;
         }
     for (int k = 0; k < r; k++) {
         double* rk = aux + (k & 1) * 2 * GJ_LD;   // pivot row (raw)
         double* ck = rk + GJ_LD;                  // pivot column (raw)
-        // publish row k (owned by warp k % 8, slot a = k / 8) and column k (lane k % 32, slot b = k / 32)
+        const int ka = k >> 3, kb = k >> 5;
+        if (w == (k & 7)) {                       // this warp owns row k
 #pragma unroll
-        for (int a = 0; a < GJ_A; a++)
+            for (int a = 0; a < NA; a++)
+                if (a == ka) {
 #pragma unroll
-            for (int b = 0; b < GJ_B; b++) {
-                const int i = w + 8 * a, j = lane + 32 * b;
-                if (i == k && j < r) rk[j] = g[a][b];
-                if (j == k && i < r) ck[i] = g[a][b];
-            }
+                    for (int b = 0; b < NB; b++) rk[lane + 32 * b] = g[a][b];
+                }
+        }
+        if (lane == (k & 31)) {                   // this lane owns column k (in every warp)
+#pragma unroll
+            for (int b = 0; b < NB; b++)
+                if (b == kb) {
+#pragma unroll
+                    for (int a = 0; a < NA; a++) ck[w + 8 * a] = g[a][b];
+                }
+        }
         __syncthreads();
         const double p = 1.0 / rk[k];
+        double rkp[NB], f[NA];
 #pragma unroll
-        for (int a = 0; a < GJ_A; a++) {
-            const int i = w + 8 * a;
-            if (i < r) {   // uniform per warp
-                const double f = ck[i];
+        for (int b = 0; b < NB; b++) rkp[b] = rk[lane + 32 * b] * p;
 #pragma unroll
-                for (int b = 0; b < GJ_B; b++) {
-                    const int j = lane + 32 * b;
-                    if (j < r) {
-                        const double rkj = rk[j] * p;
-                        if (i == k) g[a][b] = (j == k) ? p : rkj;
-                        else g[a][b] = (j == k) ? -f * p : g[a][b] - f * rkj;
-                    }
+        for (int a = 0; a < NA; a++) f[a] = ck[w + 8 * a];
+#pragma unroll
+        for (int a = 0; a < NA; a++)
+#pragma unroll
+            for (int b = 0; b < NB; b++) g[a][b] = g[a][b] - f[a] * rkp[b];
+        if (w == (k & 7)) {                       // row k becomes the scaled pivot row
+#pragma unroll
+            for (int a = 0; a < NA; a++)
+                if (a == ka) {
+#pragma unroll
+                    for (int b = 0; b < NB; b++) g[a][b] = rkp[b];
                 }
-            }
+        }
+        if (lane == (k & 31)) {                   // column k becomes -f p, the pivot itself p
+#pragma unroll
+            for (int b = 0; b < NB; b++)
+                if (b == kb) {
+#pragma unroll
+                    for (int a = 0; a < NA; a++) g[a][b] = (w + 8 * a == k) ? p : -f[a] * p;
+                }
         }
         // (the next pivot publishes into the other half of aux; the barrier after it orders the reuse of this half)
     }
 #pragma unroll
-    for (int a = 0; a < GJ_A; a++)
+    for (int a = 0; a < NA; a++)
 #pragma unroll
-        for (int b = 0; b < GJ_B; b++) {
+        for (int b = 0; b < NB; b++) {
             const int i = w + 8 * a, j = lane + 32 * b;
             if (i < r && j < r) Gg[(size_t)i * ldr + j] = g[a][b];
         }
@@ -323,7 +342,9 @@ __device__ void invert_spd(double* G, int r, int ldg, double* aux) {
 // Gg (r x r, ld ldr, global) <- inverse of Gg
 __device__ void invert_normal_matrix(double* Gg, int r, int ldr, double* aux) {
     __syncthreads();
-    if (r <= AL_RSMEM) invert_spd_regs(Gg, r, ldr, aux);
+    if (r <= 32) invert_spd_regs<4, 1>(Gg, r, ldr, aux);
+    else if (r <= 64) invert_spd_regs<8, 2>(Gg, r, ldr, aux);
+    else if (r <= AL_RSMEM) invert_spd_regs<11, 3>(Gg, r, ldr, aux);
     else invert_spd(Gg, r, ldr, aux);
     __syncthreads();
 }
