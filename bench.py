@@ -190,7 +190,7 @@ def run_ours(args):
     from multiview_motion_capture_b200._lib import STEP_OUT_DTYPE, check, ptr
     lib = _lib.get_lib()
 
-    B, K, W = args.clips, args.steps, args.warmup
+    B, K, W = args.clips, args.steps, args.warmup + args.preroll
     n_frames = W + K + 1
     t_gen = time.time()
     kps, n_pose, Kc, RT, _ = make_inputs(B, n_frames, seed=1000 + 7919 * rank, distinct=args.distinct)
@@ -241,17 +241,22 @@ def run_ours(args):
     st = cb.stats(reset=True)
     value = world * B * K / (ms * 1e-3)
 
-    # ---------------- FP64 DFMA peak probe ----------------
+    # ---------------- FP64 peak probes (CUDA-core DFMA and tensor-core DMMA), timed in this run ----------------
     sink = torch.zeros(8, dtype=torch.float64, device=dev)
-    blocks, iters = 148 * 8, 200000
-    check(lib.mvmc_fp64_probe(blocks, 1000, ptr(sink), stream.cuda_stream), "probe")
-    torch.cuda.synchronize(dev)
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record(stream)
-    check(lib.mvmc_fp64_probe(blocks, iters, ptr(sink), stream.cuda_stream), "probe")
-    p1.record(stream)
-    torch.cuda.synchronize(dev)
-    fp64_peak_tflops = blocks * 256 * iters * 16.0 / (p0.elapsed_time(p1) * 1e-3) / 1e12
+    blocks = 148 * 8
+
+    def probe(fn, iters, flops_per_iter_block):
+        check(fn(blocks, 1000, ptr(sink), stream.cuda_stream), "probe")
+        torch.cuda.synchronize(dev)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        check(fn(blocks, iters, ptr(sink), stream.cuda_stream), "probe")
+        p1.record(stream)
+        torch.cuda.synchronize(dev)
+        return blocks * iters * flops_per_iter_block / (p0.elapsed_time(p1) * 1e-3) / 1e12
+
+    fp64_dfma_tflops = probe(lib.mvmc_fp64_probe, 200000, 256 * 16.0)
+    fp64_dmma_tflops = probe(lib.mvmc_fp64_tensor_probe, 100000, 8 * 8 * 512.0)
 
     # ---------------- end-to-end through the host-buffer C-ABI call ----------------
     e2e = None
@@ -298,38 +303,53 @@ def run_ours(args):
     dom = "k_als" if als_ms >= ik_ms else "k_ik_solve"
     dom_ms = max(als_ms, ik_ms)
     dom_flops = (st["als_flops"] if dom == "k_als" else st["ik_flops"]) / K
+    # k_als runs on the FP64 tensor cores (DMMA), k_ik_solve on the FP64 CUDA cores: each against its own probed peak
+    peak_tf = fp64_dmma_tflops if dom == "k_als" else fp64_dfma_tflops
     # algorithmic bytes per launch: inputs (BODY_25 detections as float64 COCO) + outputs (params + joints + assignments)
     bytes_per_clip_frame = N_VIEWS * N_PEOPLE * 17 * 3 * 8 + N_PEOPLE * (68 + 54) * 8 + 288 * 4
     alg_bytes = B * bytes_per_clip_frame
     achieved_tf = dom_flops / (dom_ms * 1e-3) / 1e12
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_summary.json)
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            ns = json.load(f)[dom]
+        traffic = {"dram_bytes_per_launch": ns["dram_bytes"], "clips_in_capture": ns["clips"],
+                   "dram_bytes_per_clip_frame": ns["dram_bytes"] / ns["clips"], "source": ns["source"]}
+    except Exception:
+        pass
     roofline = {
-        "kernel": dom, "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
-        "frac": achieved_tf / fp64_peak_tflops if fp64_peak_tflops > 0 else None, "traffic": None,
-        "peak_source": "FP64 DFMA probe kernel timed in this run (not in MEASURED_PEAKS.json; SURVEY.md 8d)",
+        "kernel": dom, "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": traffic,
+        "peak_source": "FP64 tensor-core (mma.sync m8n8k4 f64 = DMMA) probe kernel timed in this run; MEASURED_PEAKS.json holds "
+                       "only HBM and bf16 peaks and this path is FP64 (SURVEY.md 8d). FP64 CUDA-core (DFMA) probe: "
+                       f"{fp64_dfma_tflops:.1f} TFLOP/s",
         "kernel_ms_per_launch": dom_ms, "algorithmic_flops_per_launch": dom_flops,
-        "hbm": {"achieved": alg_bytes / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": alg_bytes / (dom_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
-                "algorithmic_bytes_per_launch": alg_bytes},
+        "hbm": {"achieved": alg_bytes / (ms / K * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes / (ms / K * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                "algorithmic_bytes_per_step": alg_bytes,
+                "note": "whole step; the path is FP64-compute bound (about 25 kFLOP per algorithmic byte), not HBM bound"},
         "stage_ms_per_step": {k: v / n_prof for k, v in stage_ms.items()},
+        "ik": {"achieved": st["ik_flops"] / K / (ik_ms * 1e-3) / 1e12 if ik_ms > 0 else None, "peak": fp64_dfma_tflops,
+               "unit": "TFLOP/s", "note": "k_ik_solve, SURVEY.md 8d flop formula on the run's own (nfev, njev) counts"},
     }
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = args.cpu_cores or os.cpu_count() or 1
         try:
-            fps, step_wall, mean_frame_s, wall = cpu_arm(1, 0, cores)
+            fps, step_wall, mean_frame_s, wall = cpu_arm(3, 0, cores)
             cpu_baseline = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                            "sample": f"{cores} clips x 1 steady-state frame of the same 8x32 workload, one process per core, "
+                            "sample": f"{cores} clips x 3 steady-state frames of the same 8x32 workload, one process per core, "
                                       f"OMP_NUM_THREADS=1, mean {mean_frame_s:.2f} s per clip-frame, wall {wall:.0f} s"}
         except Exception as e:  # pragma: no cover
             cpu_baseline = {"value": None, "unit": "frames/s", "cores": cores, "kind": "port", "sample": f"failed: {e}"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "clips_per_gpu": B, "distinct_clips": min(args.distinct, B), "n_views": N_VIEWS,
-                   "n_people": N_PEOPLE, "max_tracks": args.max_tracks,
+                   "n_people": N_PEOPLE, "max_tracks": args.max_tracks, "preroll_frames": args.preroll,
                    "l2": "each step reads a new frame for every clip and sweeps the per-clip ALS workspaces "
                          f"({cb.device_bytes / 2**20:.0f} MiB on device, far larger than the 126 MB L2)",
                    "als_iters_per_clip_frame": st["als_iters"] / max(st["clip_frames"], 1),
@@ -348,9 +368,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--clips", type=int, default=296, help="clips per GPU (2 per SM)")
-    ap.add_argument("--distinct", type=int, default=37, help="distinct synthetic clips generated per rank (tiled to --clips)")
+    ap.add_argument("--clips", type=int, default=1184, help="clips per GPU (8 per SM = 4 waves of resident k_als CTAs)")
+    ap.add_argument("--distinct", type=int, default=148, help="distinct synthetic clips generated per rank (tiled to --clips)")
     ap.add_argument("--max-tracks", type=int, default=40)
+    ap.add_argument("--preroll", type=int, default=4, help="untimed frames before the warm-up (track births happen here)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cores", type=int, default=0)
