@@ -6,57 +6,148 @@
 // until ||X - Z||_F / n < tol and mu ||X - X_prev||_F / n < tol, mu doubled / halved on a 10x imbalance.
 //
 // k_als: ONE CTA (8 warps) PER CLIP-FRAME, 2 resident CTAs per SM. The n x n iterates (W, Z, Y, X, Xt) and the
-// n x r factors live in a per-clip global workspace; the seven products of an iteration (three of them 2 r n^2
-// flops: the dominant cost of the whole capture path) run as tiled FP64 tensor-core GEMMs:
-//   * CTA tile 64 x 96, k-chunks of 16 staged in shared memory by 16-byte cp.async (LDGSTS) with zero fill, double buffered;
-//   * each warp owns a 32 x 24 piece of the tile (12 accumulator fragments) and issues mma.sync.m8n8k4.f64 (DMMA) from conflict-free
-//     fragment loads (row strides chosen so the 4 x 8 fragment footprint covers every bank once);
-//   * the Z / Y / X / next-Xt update and both residual norms are the epilogue of the X = A B^T product, so an
-//     iteration makes three passes over n x n data (Xt twice, the epilogue's X, Y, W once) instead of seven;
+// n x r factors live in a per-clip global workspace (zero padded to multiples of 16 so that no copy needs a
+// tail case); the seven products of an iteration (three of them 2 r n^2 flops: the dominant cost of the whole
+// capture path) run as tiled FP64 tensor-core GEMMs:
+//   * CTA tile 64 x 96, k-chunks of 16. Operand chunks are staged by the bulk-copy engine (cp.async.bulk, one
+//     instruction per operand row, completion counted on an mbarrier) into a 4-stage ring of shared memory. One warp
+//     per chunk (rotating) issues the refill of the stage it has just finished with after waiting on the stage's
+//     "empty" mbarrier; the ring runs ahead across tiles, so only the first chunks of a product see memory latency and
+//     there is no block-wide barrier inside a product;
+//   * each warp owns a 32 x 24 piece of the tile (12 accumulator fragments) and issues mma.sync.m8n8k4.f64 (DMMA) from
+//     conflict-free fragment loads (row strides chosen so the 4 x 8 fragment footprint covers every bank once);
+//   * the Z / Y / X / next-Xt update and both residual norms are the epilogue of the X = A B^T product (its X_prev, Y, W
+//     loads run two fragments ahead of the arithmetic), so an iteration makes three passes over n x n data;
+//   * mu is a power of two throughout (64 doubled / halved), so the reference's divisions by mu are exact
+//     multiplications by 1/mu here - the same bits, ~40 instructions fewer per element;
 //   * Xt for the next iteration is written by that epilogue assuming mu stays (it changes a handful of times per
 //     solve; then one element-wise pass rebuilds Xt from Z, Y, W with the new mu) - same arithmetic, same values.
-// FP64 DMMA and DFMA have the same peak on B200 (37 TFLOP/s measured, tools/micro/dmma_probe.cu); DMMA is used because it
-// needs 8x fewer issue slots and 4x less shared-memory bandwidth per flop, which is what bounds a small-tile GEMM.
+// FP64 DMMA and DFMA share one pipe on B200 (37 TFLOP/s measured alone or mixed, tools/micro/dmma_probe.cu); DMMA is
+// used because it needs 8x fewer issue slots and 4x less shared-memory bandwidth per flop.
 #include "mvmc_common.cuh"
+#ifndef MVMC_EMU
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
+#endif
 
 namespace mvmc {
 
 constexpr int AL_THREADS = 256;           // 8 warps: 2 along M x 4 along N, warp tile 32 x 24
-constexpr int AL_KC = 16;                 // k-chunk
+constexpr int AL_WARPS = AL_THREADS / 32;
+constexpr int AL_KC = 16;                 // k-chunk (one 128-byte swizzle row of doubles)
 constexpr int AL_TM = 64;                 // CTA tile rows
 constexpr int AL_TN = 96;                 // CTA tile columns (4 warp columns x 24)
-constexpr int AL_SKM = AL_TM + 8;         // k-major tile row stride, M operand  (= 64 B mod 128 B)
-constexpr int AL_SKN = AL_TN + 8;         // k-major tile row stride, N operand
-constexpr int AL_SI = AL_KC + 4;          // i-major tile row stride               (= 32 B mod 128 B)
-constexpr int AL_STAGE_M = (AL_KC * AL_SKM > AL_TM * AL_SI) ? AL_KC * AL_SKM : AL_TM * AL_SI;   // doubles
-constexpr int AL_STAGE_N = (AL_KC * AL_SKN > AL_TN * AL_SI) ? AL_KC * AL_SKN : AL_TN * AL_SI;
+constexpr int AL_STAGE_M = AL_TM * AL_KC; // doubles: 8 KB
+constexpr int AL_STAGE_N = AL_TN * AL_KC; // 12 KB
 constexpr int AL_STAGE = AL_STAGE_M + AL_STAGE_N;
-constexpr int AL_POOL = 8192;             // doubles of shared memory shared by the two stages and the r x r inverse
+constexpr int AL_NS = 4;                  // stages of the operand ring
 constexpr int AL_RSMEM = 88;              // largest r whose normal matrix is inverted in registers (11 rows x 8 warps)
-static_assert(2 * AL_STAGE <= AL_POOL, "stages must fit the pool");
+constexpr int AL_PAD = 16;                // every matrix dimension of the workspace is padded (with zeros) to this
 
-// ---- asynchronous 16-byte global -> shared copies with zero fill ----
-__device__ __forceinline__ void cp16(double* dst, const double* src, int n_valid /*0,1,2 doubles*/) {
+// ---- tensor maps, mbarriers, TMA loads (emulated synchronously under the CPU emulator) ----
+// Two views of a row-major FP64 matrix [rows][ld] of every clip (clip stride = workspace per clip), both with the
+// 128-byte shared-memory swizzle (16-byte unit u of 128-byte row r lands at unit u ^ (r % 8)):
+//   i-major  (rank 3: k = column, i = row, clip):            box {16, TI, 1}        -> smem [TI][16]
+//   k-major  (rank 4: i % 16, k = row, i / 16, clip):         box {16, 16, TI/16, 1} -> smem [TI/16][16][16]
+// (the second one walks the matrix in 16-column blocks: its dimension-2 stride, 128 B, is smaller than its dimension-1
+// stride, the row pitch - the TMA unit does not mind; tools/micro/tma_probe.cu checks the landing pattern on the GPU).
 #ifdef MVMC_EMU
-    dst[0] = n_valid > 0 ? src[0] : 0.0;
-    dst[1] = n_valid > 1 ? src[1] : 0.0;
+#define AL_EMU_SYNC() __syncthreads()
+#define AL_GRID_CONSTANT
+typedef uint64_t mbar_t;
+struct TMap {
+    const double* base;
+    int rank;
+    long long dim[4], stride[4];   // stride in doubles (stride[0] = 1)
+    int box[4];
+};
+__device__ __forceinline__ void mbar_init(mbar_t*, int) {}
+__device__ __forceinline__ void mbar_fence_init() {}
+__device__ __forceinline__ void mbar_expect_tx(mbar_t*, unsigned) {}
+__device__ __forceinline__ void mbar_arrive(mbar_t*) {}
+__device__ __forceinline__ void mbar_wait(mbar_t*, unsigned) {}
+__device__ __forceinline__ void fence_proxy_async() {}
+// box copy with the 128-byte swizzle and zero fill outside the tensor, as the TMA unit does it
+inline void emu_tma(double* dst, const TMap* m, const int* crd) {
+    const int b0 = m->box[0], b1 = m->box[1], b2 = m->rank > 3 ? m->box[2] : 1;
+    for (int z = 0; z < b2; z++)
+        for (int y = 0; y < b1; y++)
+            for (int x = 0; x < b0; x++) {
+                long long c[4] = {crd[0] + x, crd[1] + y, 0, 0};
+                if (m->rank > 3) {
+                    c[2] = crd[2] + z;
+                    c[3] = crd[3];
+                } else {
+                    c[2] = crd[2];
+                }
+                bool in = true;
+                long long off = 0;
+                for (int d = 0; d < m->rank; d++) {
+                    in = in && c[d] >= 0 && c[d] < m->dim[d];
+                    off += c[d] * m->stride[d];
+                }
+                const int row = z * b1 + y;                       // 128-byte rows of the box, in landing order
+                const int unit = (x >> 1) ^ (row & 7);
+                dst[row * 16 + unit * 2 + (x & 1)] = in ? m->base[off] : 0.0;
+            }
+}
+__device__ __forceinline__ void tma_load3(double* dst, const TMap* m, int c0, int c1, int c2, mbar_t*) {
+    const int crd[4] = {c0, c1, c2, 0};
+    emu_tma(dst, m, crd);
+}
+__device__ __forceinline__ void tma_load4(double* dst, const TMap* m, int c0, int c1, int c2, int c3, mbar_t*) {
+    const int crd[4] = {c0, c1, c2, c3};
+    emu_tma(dst, m, crd);
+}
 #else
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    const int bytes = n_valid * 8;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
-#endif
+#define AL_EMU_SYNC() ((void)0)
+#define AL_GRID_CONSTANT __grid_constant__
+typedef unsigned long long mbar_t;
+typedef CUtensorMap TMap;
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(mbar_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_commit() {
-#ifndef MVMC_EMU
-    asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(mbar_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-template <int N>
-__device__ __forceinline__ void cp_wait() {
-#ifndef MVMC_EMU
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-#endif
+__device__ __forceinline__ void mbar_arrive(mbar_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_wait(mbar_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "AL_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra AL_DONE;\n"
+        "bra AL_WAIT;\n"
+        "AL_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load3(double* dst, const TMap* m, int c0, int c1, int c2, mbar_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load4(double* dst, const TMap* m, int c0, int c1, int c2, int c3, mbar_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// orders this thread's earlier generic-proxy writes before later async-proxy (TMA) reads of the same data
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#endif
+
+// the tensor maps of one launch (kernel parameter) and the bytes one box of each brings
+enum { MAP_A_KM = 0, MAP_A_KN, MAP_A_IM, MAP_B_KM, MAP_B_KN, MAP_B_IN, MAP_XT_KN, MAP_XT_IN, MAP_T_KN, MAP_G_IM, MAP_COUNT };
+struct AlsMaps {
+    TMap m[MAP_COUNT];
+    unsigned bytes[MAP_COUNT];
+};
 
 // D(8x8) += A(8x4) * B(4x8): lane holds a = A[lane/4][lane%4], b = B[lane%4][lane/4], c0/c1 = C[lane/4][2*(lane%4) + {0,1}]
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -69,99 +160,107 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 #endif
 }
 
-// An operand of a product, seen as element(k, i), 0 <= k < K (contraction index), 0 <= i < I.
+// layout of an operand (template argument), seen as element(k, i) with k the contraction index:
+// k-major: element(k, i) = p[k*ld + i];  i-major: element(k, i) = p[i*ld + k]. The storage behind an operand is zero for
+// K <= k < round16(K); whatever lies at I <= i only reaches outputs that are never stored.
+constexpr bool KMAJ = true, IMAJ = false;
 struct Operand {
-    const double* p;
-    int ld;
+    const TMap* map;
+    unsigned bytes;
     int I;
 };
-// layout of an operand (template argument): k-major: element(k, i) = p[k*ld + i];  i-major: element(k, i) = p[i*ld + k]
-constexpr bool KMAJ = true, IMAJ = false;
 
-// Staging of the [k0, k0+KC) x [i0, i0+TI) block of an operand into shared memory (zero filled outside K x I), 16 bytes
-// per cp.async. The (shared offset, global pointer, validity) of the <= 4 pieces a thread copies are computed once per
-// CTA tile; advancing to the next k-chunk is one pointer increment per piece.
-template <int TI, bool kmajor>
-struct Stager {
-    static constexpr int NP = (AL_KC * (TI / 2) + AL_THREADS - 1) / AL_THREADS;   // pieces per thread (3 or 4)
-    const double* base;
-    int goff[NP];     // offset (doubles) of the piece in chunk 0 from `base`
-    unsigned valid;   // 2 bits per piece: k-major = valid doubles along i (0..2); i-major = 2 if row i is inside I
-    int step;         // offset increment per k-chunk
-
-    // piece q of this thread -> (shared offset, k offset inside the chunk); constant divisors only
-    __device__ __forceinline__ static void where(int q, int& soff, int& kk) {
-        const int e = threadIdx.x + q * AL_THREADS;
-        if (kmajor) {
-            kk = e / (TI / 2);
-            soff = kk * (TI + 8) + (e % (TI / 2)) * 2;
-        } else {
-            kk = (e % (AL_KC / 2)) * 2;
-            soff = (e / (AL_KC / 2)) * AL_SI + kk;
-        }
-    }
-    __device__ __forceinline__ void init(const Operand& op, int i0) {
-        base = op.p;
-        step = kmajor ? AL_KC * op.ld : AL_KC;
-        valid = 0;
-#pragma unroll
-        for (int q = 0; q < NP; q++) {
-            const int e = threadIdx.x + q * AL_THREADS;
-            goff[q] = 0;
-            if (e >= AL_KC * (TI / 2)) continue;
-            if (kmajor) {
-                const int k = e / (TI / 2), i = i0 + (e % (TI / 2)) * 2;
-                int nv = op.I - i;
-                nv = nv < 0 ? 0 : (nv > 2 ? 2 : nv);
-                valid |= (unsigned)nv << (2 * q);
-                goff[q] = k * op.ld + (nv > 0 ? i : 0);
-            } else {
-                const int i = i0 + e / (AL_KC / 2), k = (e % (AL_KC / 2)) * 2;
-                const bool in = i < op.I;
-                valid |= (in ? 2u : 0u) << (2 * q);
-                goff[q] = (in ? i * op.ld : 0) + k;
-            }
-        }
-    }
-    // copy chunk kc (k0 = kc * KC) into S
-    __device__ __forceinline__ void issue(double* S, int kc, int K) const {
-        const int k0 = kc * AL_KC;
-#pragma unroll
-        for (int q = 0; q < NP; q++) {
-            if (threadIdx.x + q * AL_THREADS >= AL_KC * (TI / 2)) continue;
-            int soff, kk;
-            where(q, soff, kk);
-            const int nvi = (valid >> (2 * q)) & 3;
-            int nv;
-            if (kmajor) {
-                nv = (k0 + kk < K) ? nvi : 0;
-            } else {
-                nv = K - (k0 + kk);
-                nv = nv < 0 ? 0 : (nv > 2 ? 2 : nv);
-                nv = nvi ? nv : 0;
-            }
-            cp16(S + soff, nv > 0 ? base + goff[q] + kc * step : base, nv);
-        }
-    }
+// The operand ring: AL_NS stages, each [M-operand chunk | N-operand chunk]; full[s] counts the bytes landed in stage s,
+// empty[s] the warps (8) that are done reading it. `gc` = chunks consumed so far by this CTA (all products), from which
+// every thread derives stage and phase parity of a chunk without any shared state.
+struct Ring {
+    double* stages;
+    mbar_t* full;
+    mbar_t* empty;
+    unsigned gc;
+    int clip;
 };
 
-template <int TI, bool kmajor>
-__device__ __forceinline__ double frag(const double* S, int i8, int kk, int lane) {
-    // element(k = kk + lane%4, i = i8 + lane/4)
-    return kmajor ? S[(kk + (lane & 3)) * (TI + 8) + i8 + (lane >> 2)] : S[(i8 + (lane >> 2)) * AL_SI + kk + (lane & 3)];
+// The four DMMA steps of a 16-chunk take the k-sets {0,1,4,5}, {2,3,6,7}, {8,9,12,13}, {10,11,14,15} (lane%4 -> the
+// set's element): any partition works as long as both operands use it, and with this one the 32 lanes of a fragment load
+// hit every 8-byte bank pair exactly twice in BOTH swizzled layouts (the minimum for 256 bytes).
+struct FragLane {
+    int kq;       // (q & 1) + 4 (q >> 1), q = lane % 4: this lane's k inside the step's set
+    int p;        // lane / 4: this lane's i inside a fragment
+};
+// k-major stage [TI/16][16][16]: element (k, i) at (i>>4)*256 + k*16 + ((((i&15)>>1) ^ (k&7)) << 1) + (i&1)
+// i-major stage [TI][16]:        element (k, i) at i*16 + (((k>>1) ^ (i&7)) << 1) + (k&1)
+template <bool kmajor>
+__device__ __forceinline__ int frag_base(const FragLane& fl, int i8) {
+    const int i = i8 + fl.p;
+    if (kmajor) return (i >> 4) * 256 + fl.kq * 16 + (((((i & 15) >> 1) ^ fl.kq)) << 1) + (i & 1);
+    return i * 16 + ((((fl.kq >> 1) ^ fl.p)) << 1) + (fl.kq & 1);
+}
+// offset of step s relative to frag_base: k = kb + kq with kb = 8 (s >> 1) + 2 (s & 1); the bits of kb and kq are disjoint
+template <bool kmajor>
+__device__ __forceinline__ double frag_ld(const double* S, int base, int s) {
+    const int kb = 8 * (s >> 1) + 2 * (s & 1);
+    if (kmajor) return S[(base ^ ((kb & 7) << 1)) + kb * 16];     // unit ^= kb % 8, row += kb
+    return S[base ^ ((kb >> 1) << 1)];                            // unit ^= kb / 2
 }
 
-// C[m][n] = sum_k Mop(k, m) * Nop(k, n) for m < Mop.I, n < Nop.I; ep(m, n, v0, v1) receives C[m][n], C[m][n+1]
-// (n even; the caller guards n+1 < N); slot = 0/1 tells which of the two fragments of the row it is, and pre(slot, m, n)
-// is called for both fragments before either ep so that an epilogue can issue its global loads together.
-// All threads of the CTA must call it. `pool` holds the two stages.
-#define MVMC_ALS_GEMM_ATTR __forceinline__   // (a non-inlined copy per product measured 35 % slower: operand structs through memory)
-template <bool MK, bool NK, class EP, class PRE>
-__device__ MVMC_ALS_GEMM_ATTR void cta_gemm(const Operand Mop, const Operand Nop, int K, double* pool, EP ep, PRE pre) {
+// Shape of one product as the ring sees it.
+struct Tiling {
+    int nk, tn, total;   // k-chunks per tile, tiles along N, chunks of the whole product
+};
+
+// Loads chunk c (0-based inside the product) of both operands into its stage. Called by ONE converged warp.
+template <bool MK, bool NK>
+__device__ __forceinline__ void ring_issue(const Ring& rg, const Operand& Mop, const Operand& Nop, const Tiling& tl, int c) {
+    const int t = c / tl.nk, kc = c - t * tl.nk;
+    const int tm = t / tl.tn, tnn = t - tm * tl.tn;
+    const int m0 = tm * AL_TM, n0 = tnn * AL_TN, k0 = kc * AL_KC;
+    const unsigned g = rg.gc + (unsigned)c;
+    const int st = g % AL_NS;
+    const unsigned use = g / AL_NS;
+    if (use > 0) mbar_wait(&rg.empty[st], (use - 1) & 1);     // all 8 warps have finished with the stage's previous chunk
+    if ((threadIdx.x & 31) == 0) {
+        double* Sm = rg.stages + st * AL_STAGE;
+        double* Sn = Sm + AL_STAGE_M;
+        mbar_expect_tx(&rg.full[st], Mop.bytes + Nop.bytes);
+        if (MK) tma_load4(Sm, Mop.map, 0, k0, m0 >> 4, rg.clip, &rg.full[st]);
+        else tma_load3(Sm, Mop.map, k0, m0, rg.clip, &rg.full[st]);
+        if (NK) tma_load4(Sn, Nop.map, 0, k0, n0 >> 4, rg.clip, &rg.full[st]);
+        else tma_load3(Sn, Nop.map, k0, n0, rg.clip, &rg.full[st]);
+    }
+    __syncwarp();
+}
+
+// C[m][n] = sum_k Mop(k, m) * Nop(k, n) for m < Mop.I, n < Nop.I. The epilogue object receives the result fragment by
+// fragment: ep.apply(buf, m, n, v0, v1) gets C[m][n], C[m][n+1] (n even; the callee guards n+1 < N) after
+// ep.load(buf, m, n) was called for the same fragment two fragments earlier (its global loads overlap the arithmetic
+// of the fragments in between; the first two are issued before the k-loop of the tile).
+// All threads of the CTA must call it. Everything the operands point to must have been written before the call by
+// this CTA (generic stores) - the fence + barrier at the top publish it to the TMA unit.
+template <bool MK, bool NK, class EP>
+__device__ __forceinline__ void cta_gemm(Ring& rg, const Operand Mop, const Operand Nop, int K, EP& ep) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wm = warp & 1, wn = warp >> 1;               // warp tile: rows 32*wm.., columns 24*wn..
     const int M = Mop.I, N = Nop.I;
-    const int nk = (K + AL_KC - 1) / AL_KC;
+    Tiling tl;
+    tl.nk = (K + AL_KC - 1) / AL_KC;
+    tl.tn = (N + AL_TN - 1) / AL_TN;
+    tl.total = ((M + AL_TM - 1) / AL_TM) * tl.tn * tl.nk;
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) {
+        const int pre = min(AL_NS, tl.total);
+        for (int c = 0; c < pre; c++) ring_issue<MK, NK>(rg, Mop, Nop, tl, c);
+    }
+    FragLane fl;
+    fl.kq = (lane & 1) + 4 * ((lane >> 1) & 1);
+    fl.p = lane >> 2;
+    int fa[4], fb[3];   // fragment bases of this thread inside a stage (the same for every tile)
+#pragma unroll
+    for (int a = 0; a < 4; a++) fa[a] = frag_base<MK>(fl, 32 * wm + 8 * a);
+#pragma unroll
+    for (int b = 0; b < 3; b++) fb[b] = frag_base<NK>(fl, 24 * wn + 8 * b);
+    int c = 0;
     for (int m0 = 0; m0 < M; m0 += AL_TM) {
         const int mw0 = m0 + 32 * wm;
         const int mt = mw0 >= M ? 0 : min(4, (M - mw0 + 7) >> 3);       // live row tiles of this warp
@@ -173,38 +272,30 @@ __device__ MVMC_ALS_GEMM_ATTR void cta_gemm(const Operand Mop, const Operand Nop
             for (int a = 0; a < 4; a++)
 #pragma unroll
                 for (int b = 0; b < 3; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-            Stager<AL_TM, MK> sm_;
-            Stager<AL_TN, NK> sn_;
-            sm_.init(Mop, m0);
-            sn_.init(Nop, n0);
-            __syncthreads();   // the pool may still be read by the previous tile / another phase
-            sm_.issue(pool, 0, K);
-            sn_.issue(pool + AL_STAGE_M, 0, K);
-            cp_commit();
-            for (int kc = 0; kc < nk; kc++) {
-                double* cur = pool + (kc & 1) * AL_STAGE;
-                if (kc + 1 < nk) {
-                    double* nxt = pool + ((kc + 1) & 1) * AL_STAGE;
-                    sm_.issue(nxt, kc + 1, K);
-                    sn_.issue(nxt + AL_STAGE_M, kc + 1, K);
-                    cp_commit();
-                    cp_wait<1>();
-                } else {
-                    cp_wait<0>();
-                }
-                __syncthreads();
+            // fragment s = 3a + b of this thread: row, first column, liveness
+            auto f_m = [&](int s) { return mw0 + (s / 3) * 8 + (lane >> 2); };
+            auto f_n = [&](int s) { return nw0 + (s % 3) * 8 + 2 * (lane & 3); };
+            auto f_on = [&](int s) { return (s / 3) < mt && (s % 3) < nt && f_m(s) < M && f_n(s) < N; };
+            typename EP::Buf buf[3];
+            if (f_on(0)) ep.load(buf[0], f_m(0), f_n(0));
+            if (f_on(1)) ep.load(buf[1], f_m(1), f_n(1));
+            for (int kc = 0; kc < tl.nk; kc++, c++) {
+                const unsigned g = rg.gc + (unsigned)c;
+                const int st = g % AL_NS;
+                mbar_wait(&rg.full[st], (g / AL_NS) & 1);
+                AL_EMU_SYNC();
                 if (nt > 0) {
-                    const double* Sm = cur;
-                    const double* Sn = cur + AL_STAGE_M;
+                    const double* Sm = rg.stages + st * AL_STAGE;
+                    const double* Sn = Sm + AL_STAGE_M;
 #pragma unroll
-                    for (int kk = 0; kk < AL_KC; kk += 4) {
+                    for (int s = 0; s < 4; s++) {
                         double bf[3];
 #pragma unroll
-                        for (int b = 0; b < 3; b++) bf[b] = b < nt ? frag<AL_TN, NK>(Sn, 24 * wn + 8 * b, kk, lane) : 0.0;
+                        for (int b = 0; b < 3; b++) bf[b] = b < nt ? frag_ld<NK>(Sn, fb[b], s) : 0.0;
 #pragma unroll
                         for (int a = 0; a < 4; a++) {
                             if (a < mt) {
-                                const double av = frag<AL_TM, MK>(Sm, 32 * wm + 8 * a, kk, lane);
+                                const double av = frag_ld<MK>(Sm, fa[a], s);
 #pragma unroll
                                 for (int b = 0; b < 3; b++)
                                     if (b < nt) dmma(acc[a][b][0], acc[a][b][1], av, bf[b]);
@@ -212,31 +303,31 @@ __device__ MVMC_ALS_GEMM_ATTR void cta_gemm(const Operand Mop, const Operand Nop
                         }
                     }
                 }
-                __syncthreads();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&rg.empty[st]);
+                AL_EMU_SYNC();
+                if (warp == (c & (AL_WARPS - 1)) && c + AL_NS < tl.total) ring_issue<MK, NK>(rg, Mop, Nop, tl, c + AL_NS);
             }
 #pragma unroll
-            for (int a = 0; a < 4; a++) {
-                if (a < mt) {
-                    const int m = mw0 + a * 8 + (lane >> 2);
-                    // loads of all fragments of the row first, then the arithmetic and the stores
-#pragma unroll
-                    for (int b = 0; b < 3; b++) {
-                        const int nn = nw0 + 8 * b + 2 * (lane & 3);
-                        if (b < nt && m < M && nn < N) pre(b, m, nn);
-                    }
-#pragma unroll
-                    for (int b = 0; b < 3; b++) {
-                        const int nn = nw0 + 8 * b + 2 * (lane & 3);
-                        if (b < nt && m < M && nn < N) ep(b, m, nn, acc[a][b][0], acc[a][b][1]);
-                    }
-                }
+            for (int s = 0; s < 12; s++) {
+                if (s + 2 < 12 && f_on(s + 2)) ep.load(buf[(s + 2) % 3], f_m(s + 2), f_n(s + 2));
+                if (f_on(s)) ep.apply(buf[s % 3], f_m(s), f_n(s), acc[s / 3][s % 3][0], acc[s / 3][s % 3][1]);
             }
         }
     }
+    rg.gc += (unsigned)tl.total;
 }
-struct NoPre {
-    __device__ __forceinline__ void operator()(int, int, int) const {}
+
+// epilogue without operands of its own: F(m, n, v0, v1)
+template <class F>
+struct StoreEp {
+    struct Buf {};
+    F f;
+    __device__ __forceinline__ void load(Buf&, int, int) const {}
+    __device__ __forceinline__ void apply(const Buf&, int m, int n, double v0, double v1) { f(m, n, v0, v1); }
 };
+template <class F>
+__device__ __forceinline__ StoreEp<F> store_ep(F f) { return StoreEp<F>{f}; }
 
 // Inverse of the SPD r x r matrix Gg (global, leading dimension ldr) by Gauss-Jordan without pivoting, REGISTER resident:
 // thread (warp w, lane l) owns the elements (i = w + 8a, j = l + 32b), a < NA, b < NB, for the whole elimination, so a
@@ -340,7 +431,7 @@ __device__ void invert_spd(double* G, int r, int ldg, double* aux) {
 }
 
 // Gg (r x r, ld ldr, global) <- inverse of Gg
-__device__ void invert_normal_matrix(double* Gg, int r, int ldr, double* aux) {
+__device__ __noinline__ void invert_normal_matrix(double* Gg, int r, int ldr, double* aux) {
     __syncthreads();
     if (r <= 32) invert_spd_regs<4, 1>(Gg, r, ldr, aux);
     else if (r <= 64) invert_spd_regs<8, 2>(Gg, r, ldr, aux);
@@ -349,24 +440,82 @@ __device__ void invert_normal_matrix(double* Gg, int r, int ldr, double* aux) {
     __syncthreads();
 }
 
+// Per-clip workspace. Every dimension is padded to a multiple of 16 and the padding of everything a product reads
+// (Xt, A, B, T, G) is zero for the whole solve: chunks of 16 along any contraction index need no tail case.
 struct AlsLayout {
-    int N, ldn, ldr;
+    int N, NP, ldn, ldr;
+    size_t zero_span;   // doubles from Xt to the end (the part zeroed at the start of every solve)
     size_t per;
     __host__ __device__ AlsLayout(int N_, int rmax) {
         N = N_;
-        ldn = (N_ + 7) & ~7;
-        ldr = (rmax + 7) & ~7;
-        per = (size_t)5 * N * ldn + (size_t)2 * N * ldr + (size_t)ldr * ldn + (size_t)ldr * ldr;
+        NP = (N_ + AL_PAD - 1) / AL_PAD * AL_PAD;
+        ldn = NP;
+        ldr = (rmax + AL_PAD - 1) / AL_PAD * AL_PAD;
+        zero_span = (size_t)NP * ldn + (size_t)2 * NP * ldr + (size_t)ldr * ldn + (size_t)ldr * ldr;
+        per = (size_t)4 * NP * ldn + zero_span;
+    }
+};
+
+// epilogue of X = A B^T: Z / Y / next-Xt update and the two residual sums (mv_association.py:286-296)
+struct AdmmEp {
+    struct Buf {
+        double2 x0, y, w;
+    };
+    double *Xm, *Y, *Z, *Xt;
+    const double* W;
+    const int* grp;
+    int n, ldn;
+    double mu, inv_mu, beta;
+    double pacc, dacc;
+    __device__ __forceinline__ void load(Buf& b, int i, int j) const {
+        const size_t o = (size_t)i * ldn + j;
+        b.x0 = *reinterpret_cast<const double2*>(Xm + o);
+        b.y = *reinterpret_cast<const double2*>(Y + o);
+        b.w = *reinterpret_cast<const double2*>(W + o);
+    }
+    __device__ __forceinline__ void one(int gi, int i, int j, double x, double x0, double y, double w, bool live, double& yn,
+                                        double& z, double& xt) {
+        const double dd = x - x0;
+        z = x + y * inv_mu;                       // y / mu (mu is a power of two)
+        if (gi == grp[live ? j : i]) z = 0.0;
+        if (i == j) z = 1.0;
+        if (z < 0.0) z = 0.0;
+        if (z > 1.0) z = 1.0;
+        const double pd = x - z;
+        yn = y + mu * pd;
+        xt = z - (yn - w + beta) * inv_mu;        // next iteration's Xt if mu stays
+        if (live) {
+            dacc += dd * dd;
+            pacc += pd * pd;
+        } else {
+            xt = 0.0;                             // padding column of Xt stays zero (it is read by the next products)
+        }
+    }
+    __device__ __forceinline__ void apply(const Buf& b, int i, int j, double v0, double v1) {
+        const size_t o = (size_t)i * ldn + j;
+        const bool live1 = j + 1 < n;   // the odd column of the last pair may be padding
+        const int gi = grp[i];
+        double2 yn, z, xt, xv;
+        one(gi, i, j, v0, b.x0.x, b.y.x, b.w.x, true, yn.x, z.x, xt.x);
+        one(gi, i, j + 1, v1, b.x0.y, b.y.y, b.w.y, live1, yn.y, z.y, xt.y);
+        xv.x = v0;
+        xv.y = v1;
+        *reinterpret_cast<double2*>(Y + o) = yn;
+        *reinterpret_cast<double2*>(Z + o) = z;
+        *reinterpret_cast<double2*>(Xm + o) = xv;
+        *reinterpret_cast<double2*>(Xt + o) = xt;
     }
 };
 
 __global__ void __launch_bounds__(AL_THREADS, 2)
-    k_als(const double* __restrict__ sim, const int* __restrict__ dim_groups, int n_groups,
-          const int* __restrict__ f32_first_iter, const double* __restrict__ rand_stream, int N, int rmax,
-          double* __restrict__ ws, uint32_t* __restrict__ xbin, int* __restrict__ n_iter_out, double alpha, double beta,
-          double tol, int max_iter) {
-    MVMC_DYN_SMEM(double, smem);
-    const int b = blockIdx.x;
+    k_als(const AL_GRID_CONSTANT AlsMaps maps, const double* __restrict__ sim, const int* __restrict__ dim_groups, int n_groups,
+          const int* __restrict__ f32_first_iter, const double* __restrict__ rand_stream, const int* __restrict__ order,
+          int N, int rmax, double* __restrict__ ws, uint32_t* __restrict__ xbin, int* __restrict__ n_iter_out, double alpha,
+          double beta, double tol, int max_iter) {
+    MVMC_DYN_SMEM(unsigned char, smem_raw);
+    // the swizzle pattern is a function of the shared-memory address: stages start on a 1024-byte boundary
+    double* smem = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b = order ? order[blockIdx.x] : blockIdx.x;
     const int* dg = dim_groups + b * (n_groups + 1);
     const int n = dg[n_groups];
     const int NW = (N + 31) / 32;
@@ -380,136 +529,128 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
     int r = min(n, 2 * maxsz);
     r = min(r, rmax);
 
-    double* pool = smem;                       // [AL_POOL] stages / inverse
-    double* scratch = pool + AL_POOL;          // [32]
-    double* inv_aux = scratch + 32;            // [4 * 96] pivot row / column of the Gauss-Jordan inverse, double buffered
-    int* s_grp = reinterpret_cast<int*>(inv_aux + 4 * GJ_LD);   // [N]
+    Ring rg;
+    rg.stages = smem;                                             // [AL_NS * AL_STAGE]
+    double* scratch = smem + AL_NS * AL_STAGE;                    // [32]
+    double* inv_aux = scratch + 32;                               // [4 * 96] pivot row / column of the Gauss-Jordan inverse
+    rg.full = reinterpret_cast<mbar_t*>(inv_aux + 4 * GJ_LD);     // [AL_NS]
+    rg.empty = rg.full + AL_NS;                                   // [AL_NS]
+    rg.gc = 0;
+    rg.clip = b;
+    int* s_grp = reinterpret_cast<int*>(rg.empty + AL_NS);        // [N + 1]
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < AL_NS; s++) {
+            mbar_init(&rg.full[s], 1);
+            mbar_init(&rg.empty[s], AL_WARPS);
+        }
+        mbar_fence_init();
+    }
 
     const AlsLayout L(N, rmax);
     const int ldn = L.ldn, ldr = L.ldr;
     double* W = ws + (size_t)b * L.per;
-    double* Z = W + (size_t)N * ldn;
-    double* Y = Z + (size_t)N * ldn;
-    double* Xm = Y + (size_t)N * ldn;
-    double* Xt = Xm + (size_t)N * ldn;
-    double* A = Xt + (size_t)N * ldn;          // [n][ldr]
-    double* Bm = A + (size_t)N * ldr;          // [n][ldr]
-    double* Tm = Bm + (size_t)N * ldr;         // [r][ldn]
-    double* Gg = Tm + (size_t)ldr * ldn;       // [r][ldr]
+    double* Z = W + (size_t)L.NP * ldn;
+    double* Y = Z + (size_t)L.NP * ldn;
+    double* Xm = Y + (size_t)L.NP * ldn;
+    double* Xt = Xm + (size_t)L.NP * ldn;      // [NP][ldn]   (from here on: zeroed below, padding stays zero)
+    double* A = Xt + (size_t)L.NP * ldn;       // [NP][ldr]
+    double* Bm = A + (size_t)L.NP * ldr;       // [NP][ldr]
+    double* Tm = Bm + (size_t)L.NP * ldr;      // [ldr][ldn]
+    double* Gg = Tm + (size_t)ldr * ldn;       // [ldr][ldr]
 
     const double* S = sim + (size_t)b * N * N;
     const bool f32 = f32_first_iter != nullptr && f32_first_iter[b] != 0;
 
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = threadIdx.x; i <= N; i += blockDim.x) {
         int g = 0;
         for (int q = 0; q < n_groups; q++)
             if (i >= dg[q] && i < dg[q + 1]) g = q;  // an index belongs to the group whose [start, end) contains it
-        s_grp[i] = g;
+        s_grp[i] = i < n ? g : -1;
     }
-    double mu = 64.0;
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-        const int i = e / n, j = e % n;
-        const size_t o = (size_t)i * ldn + j;
-        double w;
-        if (f32) w = (double)(0.5f * ((float)S[(size_t)i * N + j] + (float)S[(size_t)j * N + i]));
-        else w = 0.5 * (S[(size_t)i * N + j] + S[(size_t)j * N + i]);
-        W[o] = w;
-        Z[o] = w;
-        Xm[o] = w;
-        Y[o] = 0.0;
-        // first Xt (Z = W, Y = 0); the float32 no-track path of the reference keeps float32 through this expression
-        if (f32) Xt[o] = (double)((float)w - ((0.0f - (float)w) + (float)beta) / (float)mu);
-        else Xt[o] = w - (0.0 - w + beta) / mu;
+    {
+        double2 zz;
+        zz.x = zz.y = 0.0;
+        double2* z2 = reinterpret_cast<double2*>(Xt);
+        for (size_t e = threadIdx.x; e < L.zero_span / 2; e += blockDim.x) z2[e] = zz;
     }
+    __syncthreads();
+    double mu = 64.0, inv_mu = 1.0 / 64.0;
+    for (int i = threadIdx.x >> 5; i < n; i += AL_WARPS)
+        for (int j = threadIdx.x & 31; j < n; j += 32) {
+            const size_t o = (size_t)i * ldn + j;
+            double w;
+            if (f32) w = (double)(0.5f * ((float)S[(size_t)i * N + j] + (float)S[(size_t)j * N + i]));
+            else w = 0.5 * (S[(size_t)i * N + j] + S[(size_t)j * N + i]);
+            W[o] = w;
+            Z[o] = w;
+            Xm[o] = w;
+            Y[o] = 0.0;
+            // first Xt (Z = W, Y = 0); the float32 no-track path of the reference keeps float32 through this expression
+            if (f32) Xt[o] = (double)((float)w - ((0.0f - (float)w) + (float)beta) / (float)mu);
+            else Xt[o] = w - (0.0 - w + beta) / mu;
+        }
     for (int e = threadIdx.x; e < n * r; e += blockDim.x) A[(size_t)(e / r) * ldr + (e % r)] = rand_stream[e];
     __syncthreads();
 
+    auto op = [&](int which, int I) { return Operand{&maps.m[which], maps.bytes[which], I}; };
     int it = 0;
     for (it = 0; it < max_iter; it++) {
         const double reg = alpha / mu;
         // ---- G = A^T A + reg I, inverted ----
         {
-            const Operand opA{A, ldr, r};
-            cta_gemm<KMAJ, KMAJ>(opA, opA, n, pool, [&](int, int m, int nn, double v0, double v1) {
+            auto ep = store_ep([&](int m, int nn, double v0, double v1) {
                 Gg[(size_t)m * ldr + nn] = (m == nn) ? v0 + reg * 1.0 : v0 + reg * 0.0;
                 if (nn + 1 < r) Gg[(size_t)m * ldr + nn + 1] = (m == nn + 1) ? v1 + reg * 1.0 : v1 + reg * 0.0;
-            }, NoPre());
+            });
+            cta_gemm<KMAJ, KMAJ>(rg, op(MAP_A_KM, r), op(MAP_A_KN, r), n, ep);
         }
         invert_normal_matrix(Gg, r, ldr, inv_aux);
         // ---- T = A^T Xt ----
-        cta_gemm<KMAJ, KMAJ>(Operand{A, ldr, r}, Operand{Xt, ldn, n}, n, pool, [&](int, int m, int nn, double v0, double v1) {
-            Tm[(size_t)m * ldn + nn] = v0;
-            if (nn + 1 < n) Tm[(size_t)m * ldn + nn + 1] = v1;
-        }, NoPre());
-        __syncthreads();
+        {
+            auto ep = store_ep([&](int m, int nn, double v0, double v1) {
+                Tm[(size_t)m * ldn + nn] = v0;
+                if (nn + 1 < n) Tm[(size_t)m * ldn + nn + 1] = v1;
+            });
+            cta_gemm<KMAJ, KMAJ>(rg, op(MAP_A_KM, r), op(MAP_XT_KN, n), n, ep);
+        }
         // ---- B = (Ginv T)^T ----
-        cta_gemm<IMAJ, KMAJ>(Operand{Gg, ldr, r}, Operand{Tm, ldn, n}, r, pool, [&](int, int m, int nn, double v0, double v1) {
-            Bm[(size_t)nn * ldr + m] = v0;
-            if (nn + 1 < n) Bm[(size_t)(nn + 1) * ldr + m] = v1;
-        }, NoPre());
-        __syncthreads();
+        {
+            auto ep = store_ep([&](int m, int nn, double v0, double v1) {
+                Bm[(size_t)nn * ldr + m] = v0;
+                if (nn + 1 < n) Bm[(size_t)(nn + 1) * ldr + m] = v1;
+            });
+            cta_gemm<IMAJ, KMAJ>(rg, op(MAP_G_IM, r), op(MAP_T_KN, n), r, ep);
+        }
         // ---- H = B^T B + reg I, inverted ----
         {
-            const Operand opB{Bm, ldr, r};
-            cta_gemm<KMAJ, KMAJ>(opB, opB, n, pool, [&](int, int m, int nn, double v0, double v1) {
+            auto ep = store_ep([&](int m, int nn, double v0, double v1) {
                 Gg[(size_t)m * ldr + nn] = (m == nn) ? v0 + reg : v0;
                 if (nn + 1 < r) Gg[(size_t)m * ldr + nn + 1] = (m == nn + 1) ? v1 + reg : v1;
-            }, NoPre());
+            });
+            cta_gemm<KMAJ, KMAJ>(rg, op(MAP_B_KM, r), op(MAP_B_KN, r), n, ep);
         }
         invert_normal_matrix(Gg, r, ldr, inv_aux);
         // ---- T = B^T Xt^T : T[m][i] = sum_j B[j][m] Xt[i][j] ----
-        cta_gemm<KMAJ, IMAJ>(Operand{Bm, ldr, r}, Operand{Xt, ldn, n}, n, pool, [&](int, int m, int nn, double v0, double v1) {
-            Tm[(size_t)m * ldn + nn] = v0;
-            if (nn + 1 < n) Tm[(size_t)m * ldn + nn + 1] = v1;
-        }, NoPre());
-        __syncthreads();
+        {
+            auto ep = store_ep([&](int m, int nn, double v0, double v1) {
+                Tm[(size_t)m * ldn + nn] = v0;
+                if (nn + 1 < n) Tm[(size_t)m * ldn + nn + 1] = v1;
+            });
+            cta_gemm<KMAJ, IMAJ>(rg, op(MAP_B_KM, r), op(MAP_XT_IN, n), n, ep);
+        }
         // ---- A = (Hinv T)^T ----
-        cta_gemm<IMAJ, KMAJ>(Operand{Gg, ldr, r}, Operand{Tm, ldn, n}, r, pool, [&](int, int m, int nn, double v0, double v1) {
-            A[(size_t)nn * ldr + m] = v0;
-            if (nn + 1 < n) A[(size_t)(nn + 1) * ldr + m] = v1;
-        }, NoPre());
-        __syncthreads();
+        {
+            auto ep = store_ep([&](int m, int nn, double v0, double v1) {
+                A[(size_t)nn * ldr + m] = v0;
+                if (nn + 1 < n) A[(size_t)(nn + 1) * ldr + m] = v1;
+            });
+            cta_gemm<IMAJ, KMAJ>(rg, op(MAP_G_IM, r), op(MAP_T_KN, n), r, ep);
+        }
         // ---- X = A B^T, fused with the Z / Y / next-Xt updates and both residual norms ----
-        double pacc = 0.0, dacc = 0.0;
-        double2 ex0[3], ey[3], ew[3];   // X_prev, Y, W of the three fragments of a row (16-byte loads, issued together)
-        auto one = [&](int i, int j, double x, double x0, double y, double w, bool live, double& yn, double& z, double& xt) {
-            const double dd = x - x0;
-            z = x + y / mu;
-            if (s_grp[i] == s_grp[live ? j : i]) z = 0.0;
-            if (i == j) z = 1.0;
-            if (z < 0.0) z = 0.0;
-            if (z > 1.0) z = 1.0;
-            const double pd = x - z;
-            yn = y + mu * pd;
-            xt = z - (yn - w + beta) / mu;   // next iteration's Xt if mu stays
-            if (live) {
-                dacc += dd * dd;
-                pacc += pd * pd;
-            }
-        };
-        cta_gemm<IMAJ, IMAJ>(Operand{A, ldr, n}, Operand{Bm, ldr, n}, r, pool,
-                 [&](int slot, int i, int j, double v0, double v1) {
-                     const size_t o = (size_t)i * ldn + j;
-                     const bool live1 = j + 1 < n;   // the odd column of the last pair may be padding (written, never read)
-                     double2 yn, z, xt;
-                     one(i, j, v0, ex0[slot].x, ey[slot].x, ew[slot].x, true, yn.x, z.x, xt.x);
-                     one(i, j + 1, v1, ex0[slot].y, ey[slot].y, ew[slot].y, live1, yn.y, z.y, xt.y);
-                     *reinterpret_cast<double2*>(Y + o) = yn;
-                     *reinterpret_cast<double2*>(Z + o) = z;
-                     double2 xv;
-                     xv.x = v0;
-                     xv.y = v1;
-                     *reinterpret_cast<double2*>(Xm + o) = xv;
-                     *reinterpret_cast<double2*>(Xt + o) = xt;
-                 },
-                 [&](int slot, int i, int j) {
-                     const size_t o = (size_t)i * ldn + j;
-                     ex0[slot] = *reinterpret_cast<const double2*>(Xm + o);
-                     ey[slot] = *reinterpret_cast<const double2*>(Y + o);
-                     ew[slot] = *reinterpret_cast<const double2*>(W + o);
-                 });
-        const double psum = block_sum(pacc, scratch);
-        const double dsum = block_sum(dacc, scratch);
+        AdmmEp ep{Xm, Y, Z, Xt, W, s_grp, n, ldn, mu, inv_mu, beta, 0.0, 0.0};
+        cta_gemm<IMAJ, IMAJ>(rg, op(MAP_A_IM, n), op(MAP_B_IN, n), r, ep);
+        const double psum = block_sum(ep.pacc, scratch);
+        const double dsum = block_sum(ep.dacc, scratch);
         const double p_res = sqrt(psum) / n;
         const double d_res = mu * sqrt(dsum) / n;
         if (p_res < tol && d_res < tol) {
@@ -521,13 +662,14 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
         else if (d_res > 10.0 * p_res) mu_new = mu / 2.0;
         if (mu_new != mu) {
             mu = mu_new;
+            inv_mu = 1.0 / mu;
             __syncthreads();
-            for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-                const size_t o = (size_t)(e / n) * ldn + (e % n);
-                Xt[o] = Z[o] - (Y[o] - W[o] + beta) / mu;
-            }
+            for (int i = threadIdx.x >> 5; i < n; i += AL_WARPS)
+                for (int j = threadIdx.x & 31; j < n; j += 32) {
+                    const size_t o = (size_t)i * ldn + j;
+                    Xt[o] = Z[o] - (Y[o] - W[o] + beta) * inv_mu;
+                }
         }
-        __syncthreads();
     }
     __syncthreads();
     if (threadIdx.x == 0) n_iter_out[b] = it;
@@ -546,27 +688,172 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
     }
 }
 
+// Longest-processing-time-first launch order: clips sorted by the iteration count of their previous frame (a good
+// predictor of this frame's), descending, so that the long solves start first and the tail of the launch is short ones.
+// One CTA; counting sort over 0..1023 iterations. The order only affects scheduling, never a result.
+__global__ void __launch_bounds__(1024) k_als_order(const int* __restrict__ prev_iter, int B, int* __restrict__ order) {
+    __shared__ int cnt[1024];
+    __shared__ int carry;
+    const int t = threadIdx.x;
+    cnt[t] = 0;
+    if (t == 0) carry = 0;
+    __syncthreads();
+    for (int b = t; b < B; b += 1024) atomicAdd(&cnt[1023 - min(max(prev_iter[b], 0), 1023)], 1);
+    __syncthreads();
+    // exclusive prefix sum of cnt (bucket 0 = the longest solves), 1024 entries, Hillis-Steele in place
+    int v = cnt[t];
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int add = t >= o ? cnt[t - o] : 0;
+        __syncthreads();
+        cnt[t] += add;
+        __syncthreads();
+    }
+    const int excl = cnt[t] - v;
+    __syncthreads();
+    cnt[t] = excl;
+    __syncthreads();
+    for (int b = t; b < B; b += 1024) {
+        const int pos = atomicAdd(&cnt[1023 - min(max(prev_iter[b], 0), 1023)], 1);
+        order[pos] = b;
+    }
+}
+
 }  // namespace mvmc
 
 using namespace mvmc;
 
-static size_t als_smem_bytes(int N) { return (size_t)(AL_POOL + 32 + 4 * GJ_LD) * sizeof(double) + (size_t)N * sizeof(int); }
+int mvmc_als_order(const int* prev_iter, int B, int* order, void* stream) {
+    if (!prev_iter || !order || B <= 0) return MVMC_ERR_INVALID;
+    MVMC_LAUNCH(k_als_order, dim3(1), dim3(1024), 0, stream, prev_iter, B, order);
+    MVMC_CHECK_LAUNCH("k_als_order");
+    return MVMC_OK;
+}
+
+static size_t als_smem_bytes(int N) {
+    return 1024 + (size_t)(AL_NS * AL_STAGE + 32 + 4 * GJ_LD) * sizeof(double) + 2 * AL_NS * sizeof(mbar_t) +
+           (size_t)(N + 2) * sizeof(int);
+}
 
 extern "C" size_t mvmc_match_als_workspace_bytes(int B, int N, int rmax) {
     const AlsLayout L(N, rmax);
     return (size_t)B * L.per * sizeof(double);
 }
 
-extern "C" int mvmc_match_als(const double* sim, const int* dim_groups, int n_groups, const int* f32_first_iter,
-                              const double* rand_stream, int B, int N, int rmax, void* workspace, uint32_t* xbin,
-                              int* n_iter, void* stream) {
+// ---- tensor maps over the workspace ----
+#ifndef MVMC_EMU
+typedef CUresult (*mvmc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static mvmc_encode_fn als_encoder() {
+    static mvmc_encode_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (mvmc_encode_fn)p;
+    }
+    return fn;
+}
+#endif
+
+// view of the matrix at `base` ([rows][ld] doubles per clip, clip stride `per` doubles); kmajor: box {16, 16, ti/16, 1}, else
+// box {16, ti, 1}. Box extents are clamped to the tensor so that no box is larger than what it is cut from.
+static int als_make_map(TMap* out, unsigned* bytes, double* base, int rows, int ld, size_t per, int B, bool kmajor, int ti) {
+#ifdef MVMC_EMU
+    TMap m;
+    m.base = base;
+    if (kmajor) {
+        m.rank = 4;
+        m.dim[0] = 16; m.dim[1] = rows; m.dim[2] = ld / 16; m.dim[3] = B;
+        m.stride[0] = 1; m.stride[1] = ld; m.stride[2] = 16; m.stride[3] = (long long)per;
+        m.box[0] = 16; m.box[1] = 16; m.box[2] = min(ti / 16, ld / 16); m.box[3] = 1;
+        *bytes = 16u * 16u * (unsigned)m.box[2] * 8u;
+    } else {
+        m.rank = 3;
+        m.dim[0] = ld; m.dim[1] = rows; m.dim[2] = B; m.dim[3] = 1;
+        m.stride[0] = 1; m.stride[1] = ld; m.stride[2] = (long long)per; m.stride[3] = 0;
+        m.box[0] = 16; m.box[1] = min(ti, rows); m.box[2] = 1; m.box[3] = 1;
+        *bytes = 16u * (unsigned)m.box[1] * 8u;
+    }
+    *out = m;
+    return MVMC_OK;
+#else
+    mvmc_encode_fn enc = als_encoder();
+    if (!enc) return mvmc_set_cuda_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point");
+    CUresult r;
+    if (kmajor) {
+        const cuuint64_t dims[4] = {16, (cuuint64_t)rows, (cuuint64_t)(ld / 16), (cuuint64_t)B};
+        const cuuint64_t strides[3] = {(cuuint64_t)ld * 8, 128, (cuuint64_t)per * 8};
+        const cuuint32_t blocks = (cuuint32_t)((ti / 16 < ld / 16) ? ti / 16 : ld / 16);
+        const cuuint32_t box[4] = {16, 16, blocks, 1}, es[4] = {1, 1, 1, 1};
+        r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        *bytes = 16u * 16u * blocks * 8u;
+    } else {
+        const cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)rows, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)per * 8};
+        const cuuint32_t brows = (cuuint32_t)(ti < rows ? ti : rows);
+        const cuuint32_t box[3] = {16, brows, 1}, es[3] = {1, 1, 1};
+        r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        *bytes = 16u * brows * 8u;
+    }
+    if (r != CUDA_SUCCESS) return mvmc_set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
+    return MVMC_OK;
+#endif
+}
+
+static int als_build_maps(AlsMaps* M, double* ws, int B, int N, int rmax) {
+    const AlsLayout L(N, rmax);
+    double* Xt = ws + (size_t)4 * L.NP * L.ldn;
+    double* A = Xt + (size_t)L.NP * L.ldn;
+    double* Bm = A + (size_t)L.NP * L.ldr;
+    double* Tm = Bm + (size_t)L.NP * L.ldr;
+    double* Gg = Tm + (size_t)L.ldr * L.ldn;
+    struct Spec {
+        int which;
+        double* base;
+        int rows, ld;
+        bool kmajor;
+        int ti;
+    } spec[MAP_COUNT] = {
+        {MAP_A_KM, A, L.NP, L.ldr, true, AL_TM},   {MAP_A_KN, A, L.NP, L.ldr, true, AL_TN},    {MAP_A_IM, A, L.NP, L.ldr, false, AL_TM},
+        {MAP_B_KM, Bm, L.NP, L.ldr, true, AL_TM},  {MAP_B_KN, Bm, L.NP, L.ldr, true, AL_TN},   {MAP_B_IN, Bm, L.NP, L.ldr, false, AL_TN},
+        {MAP_XT_KN, Xt, L.NP, L.ldn, true, AL_TN}, {MAP_XT_IN, Xt, L.NP, L.ldn, false, AL_TN}, {MAP_T_KN, Tm, L.ldr, L.ldn, true, AL_TN},
+        {MAP_G_IM, Gg, L.ldr, L.ldr, false, AL_TM},
+    };
+    for (int q = 0; q < MAP_COUNT; q++) {
+        const Spec& sp = spec[q];
+        const int rc = als_make_map(&M->m[sp.which], &M->bytes[sp.which], sp.base, sp.rows, sp.ld, L.per, B, sp.kmajor, sp.ti);
+        if (rc) return rc;
+    }
+    return MVMC_OK;
+}
+
+// `order` (device, [B], may be null): clip index solved by CTA i - the pipeline passes the clips sorted by their previous
+// frame's iteration count, longest first, so the last wave of CTAs is the short solves.
+int mvmc_match_als_ordered(const double* sim, const int* dim_groups, int n_groups, const int* f32_first_iter,
+                           const double* rand_stream, const int* order, int B, int N, int rmax, void* workspace, uint32_t* xbin,
+                           int* n_iter, void* stream) {
     if (!sim || !dim_groups || !rand_stream || !workspace || !xbin || !n_iter) return MVMC_ERR_INVALID;
     if (B <= 0 || N <= 0 || N > 1024 || rmax <= 0 || rmax > 128 || n_groups <= 0 || n_groups > MVMC_MAX_VIEWS + 1)
         return MVMC_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 127) != 0) return MVMC_ERR_INVALID;   // TMA needs 16-byte, we ask for 128
+    AlsMaps maps;
+    const int rc = als_build_maps(&maps, (double*)workspace, B, N, rmax);
+    if (rc) return rc;
     const size_t smem = als_smem_bytes(N);
     MVMC_CUDA_OK(cudaFuncSetAttribute(k_als, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MVMC_LAUNCH(k_als, dim3(B), dim3(AL_THREADS), smem, stream, sim, dim_groups, n_groups, f32_first_iter, rand_stream, N,
-                rmax, (double*)workspace, xbin, n_iter, 50.0, 0.1, 1e-4, 1000);
+    MVMC_LAUNCH(k_als, dim3(B), dim3(AL_THREADS), smem, stream, maps, sim, dim_groups, n_groups, f32_first_iter, rand_stream,
+                order, N, rmax, (double*)workspace, xbin, n_iter, 50.0, 0.1, 1e-4, 1000);
     MVMC_CHECK_LAUNCH("k_als");
     return MVMC_OK;
+}
+
+extern "C" int mvmc_match_als(const double* sim, const int* dim_groups, int n_groups, const int* f32_first_iter,
+                              const double* rand_stream, int B, int N, int rmax, void* workspace, uint32_t* xbin,
+                              int* n_iter, void* stream) {
+    return mvmc_match_als_ordered(sim, dim_groups, n_groups, f32_first_iter, rand_stream, nullptr, B, N, rmax, workspace, xbin,
+                                  n_iter, stream);
 }

@@ -13,6 +13,10 @@
 #include <vector>
 
 int mvmc_ensure_skeleton();
+int mvmc_als_order(const int* prev_iter, int B, int* order, void* stream);
+int mvmc_match_als_ordered(const double* sim, const int* dim_groups, int n_groups, const int* f32_first_iter,
+                           const double* rand_stream, const int* order, int B, int N, int rmax, void* workspace, uint32_t* xbin,
+                           int* n_iter, void* stream);
 int mvmc_ik_launch(const double* kps2d, const double* Psel, const int* n_views, const double* x0, const uint8_t* birth,
                    const int* max_nfev, const uint8_t* free_mask, int n_items, int cnt, int S, int s0, int V, int vmax,
                    int* counter, double* x_out, double* joints, int* info, double* cost, void* stream);
@@ -408,7 +412,7 @@ struct mvmc_clips {
     double *dst = nullptr, *sim = nullptr, *rand_stream = nullptr;
     void* als_ws = nullptr;
     uint32_t* xbin = nullptr;
-    int* als_iter = nullptr;
+    int *als_iter = nullptr, *als_order = nullptr;
     int *trk_nsel = nullptr, *trk_sel = nullptr, *new_n = nullptr, *new_nsel = nullptr, *new_sel = nullptr, *n_dup = nullptr,
         *assign_err = nullptr;
     double *w_kps = nullptr, *w_P = nullptr, *w_x0 = nullptr, *w_xout = nullptr, *w_joints = nullptr, *w_cost = nullptr;
@@ -533,6 +537,7 @@ extern "C" int mvmc_clips_create(const mvmc_config* cfg, mvmc_clips** out) {
     }
     TRY(h->alloc(&h->xbin, (size_t)B * N * h->NW));
     TRY(h->alloc(&h->als_iter, (size_t)B));
+    TRY(h->alloc(&h->als_order, (size_t)B));
     TRY(h->alloc(&h->trk_nsel, (size_t)B * Tmax));
     TRY(h->alloc(&h->trk_sel, (size_t)B * Tmax * MVMC_MAX_SEL * 2));
     TRY(h->alloc(&h->new_n, (size_t)B));
@@ -619,8 +624,10 @@ extern "C" int mvmc_clips_step(mvmc_clips* h, const double* kps, const int* n_po
                        Pmax, Tmax, h->dst, h->sim, stream);
     if (rc) return rc;
     MVMC_EV(1);
-    rc = mvmc_match_als(h->sim, h->dim_groups, C + 1, h->f32_flag, h->rand_stream, B, N, h->rmax, h->als_ws, h->xbin,
-                        h->als_iter, stream);
+    rc = mvmc_als_order(h->als_iter, B, h->als_order, stream);   // previous frame's iteration counts: longest solves first
+    if (rc) return rc;
+    rc = mvmc_match_als_ordered(h->sim, h->dim_groups, C + 1, h->f32_flag, h->rand_stream, h->als_order, B, N, h->rmax, h->als_ws,
+                                h->xbin, h->als_iter, stream);
     if (rc) return rc;
     MVMC_EV(2);
     rc = mvmc_assign(h->xbin, h->dim_groups, h->idx_view, h->idx_pose, h->st.n_trk, B, C, N, Tmax, h->cfg.max_new,

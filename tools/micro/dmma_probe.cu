@@ -47,6 +47,28 @@ __global__ void k_dmma16816(int iters, double* sink) {
     if (r == 1.2345) sink[0] = r;
 }
 
+// DMMA and DFMA in the same warp: per iteration 8 DMMA (4096 flops / warp) + NF x 8 DFMA per thread (NF*8*64 flops / warp).
+// If the two instruction classes run on separate pipes the time is max(t_dmma, t_dfma), otherwise the sum.
+template <int NF>
+__global__ void k_mixed(int iters, double* sink) {
+    double c[8][2], f[8];
+    for (int i = 0; i < 8; i++) { c[i][0] = c[i][1] = 0.0; f[i] = threadIdx.x * 1e-3 + i; }
+    double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-6;
+    const double m = 1.0000001, cc = 1e-9;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+#pragma unroll
+            for (int q = 0; q < NF; q++) f[(i + q) & 7] = fma(f[(i + q) & 7], m, cc);
+        }
+    }
+    double r = 0;
+    for (int i = 0; i < 8; i++) r += c[i][0] + c[i][1] + f[i];
+    if (r == 1.2345) sink[0] = r;
+}
+
 template <class F>
 float timeit(F f) {
     cudaEvent_t e0, e1;
@@ -65,6 +87,17 @@ int main() {
     printf("DMMA 8x8x4: %.2f TFLOP/s\n", (double)blocks * (thr / 32) * iters * 8 * (8.0 * 8 * 4 * 2) / (t * 1e-3) / 1e12);
     t = timeit([&] { k_dmma16816<<<blocks, thr>>>(iters, sink); });
     printf("DMMA 16x8x16: %.2f TFLOP/s\n", (double)blocks * (thr / 32) * iters * 4 * (16.0 * 8 * 16 * 2) / (t * 1e-3) / 1e12);
+    {
+        float tm = timeit([&] { k_mixed<4><<<blocks, thr>>>(iters / 4, sink); });
+        double fl = (double)blocks * (thr / 32) * (iters / 4) * (8 * 512.0 + 4 * 8 * 64.0);
+        printf("mixed 8 DMMA + 32 DFMA per warp-iter : %.2f TFLOP/s total (%.3f ms)\n", fl / (tm * 1e-3) / 1e12, tm);
+        tm = timeit([&] { k_mixed<8><<<blocks, thr>>>(iters / 4, sink); });
+        fl = (double)blocks * (thr / 32) * (iters / 4) * (8 * 512.0 + 8 * 8 * 64.0);
+        printf("mixed 8 DMMA + 64 DFMA per warp-iter : %.2f TFLOP/s total (%.3f ms)\n", fl / (tm * 1e-3) / 1e12, tm);
+        tm = timeit([&] { k_mixed<2><<<blocks, thr>>>(iters / 4, sink); });
+        fl = (double)blocks * (thr / 32) * (iters / 4) * (8 * 512.0 + 2 * 8 * 64.0);
+        printf("mixed 8 DMMA + 16 DFMA per warp-iter : %.2f TFLOP/s total (%.3f ms)\n", fl / (tm * 1e-3) / 1e12, tm);
+    }
     printf("err: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
