@@ -214,6 +214,8 @@ def run_ours(args):
         cb.step_device(kps_dev[1 + s], np_dev[1 + s], 1 + s)
     cb.stats(reset=True)
     cb.profile(1)
+    if args.als_phases:
+        check(lib.mvmc_als_phase_profile(1, None), "mvmc_als_phase_profile")
     launches0 = lib.mvmc_launch_count()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -237,6 +239,12 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = lib.mvmc_launch_count() - launches0
+    if args.als_phases and rank == 0:
+        ph = np.zeros(12)
+        check(lib.mvmc_als_phase_profile(0, ptr(ph)), "mvmc_als_phase_profile")
+        names = ["G=AtA", "inv1", "T=AtXt", "B", "H=BtB", "inv2", "T=BtXtt", "A", "X=ABt+admm", "reduce", "mu-pass", "init"]
+        print("k_als phase share of CTA cycles: " + ", ".join(f"{n} {100 * v / ph.sum():.1f}%" for n, v in zip(names, ph)),
+              file=sys.stderr, flush=True)
     stage_ms, n_prof = cb.profile(0)
     st = cb.stats(reset=True)
     value = world * B * K / (ms * 1e-3)
@@ -373,6 +381,7 @@ def main():
     ap.add_argument("--max-tracks", type=int, default=40)
     ap.add_argument("--preroll", type=int, default=4, help="untimed frames before the warm-up (track births happen here)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--als-phases", action="store_true", help="print k_als's per-phase cycle shares to stderr (diagnostic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cores", type=int, default=0)
     args = ap.parse_args()

@@ -430,12 +430,121 @@ __device__ void invert_spd(double* G, int r, int ldg, double* aux) {
     }
 }
 
-// Gg (r x r, ld ldr, global) <- inverse of Gg
-__device__ __noinline__ void invert_normal_matrix(double* Gg, int r, int ldr, double* aux) {
+// ---- blocked Gauss-Jordan inverse on the tensor cores ----
+// The scalar elimination above is a chain of r dependent pivots with a block barrier each (about 1 us per pivot once the
+// FP64 pipe is shared with another CTA's DMMAs: 19 % of an ADMM iteration at r = 64). Here the matrix sits in shared
+// memory (the idle operand ring) and is eliminated 8 columns at a time:
+//     Pinv = inv(G[kb,kb])                        every warp, redundantly, in registers: 8 shuffle pivots, no barrier
+//     R    = Pinv G[kb,:]                         8 x 8 blocks, two DMMA each, spread over the warps     | barrier
+//     G[i,j] -= G[i,kb] R[j],  G[i,kb] = -G[i,kb] Pinv,  G[kb,:] = R, G[kb,kb] = Pinv   (row block i = warp) | barrier
+// 2 barriers per 8 pivots instead of 8, and the rank-8 updates run as DMMA. Same in-place Gauss-Jordan recurrences, block
+// wise; the matrix is padded with an identity to a multiple of 8.
+constexpr int GJB_MAXR = 88;     // (88 x 92 + 8 x 92) doubles = 70.6 KB of the 80 KB ring
+
+// 8 x 8 inverse in registers: lane l holds P[l/4][2(l%4)], P[l/4][2(l%4)+1] (the DMMA accumulator layout)
+__device__ __forceinline__ void inv8_regs(double& e0, double& e1, int lane) {
+    const int ro = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int ks = k & 1, kl = k >> 1;
+        const double diag = __shfl_sync(MVMC_FULL, ks ? e1 : e0, 4 * k + kl);
+        const double rk0 = __shfl_sync(MVMC_FULL, e0, 4 * k + q), rk1 = __shfl_sync(MVMC_FULL, e1, 4 * k + q);
+        const double f = __shfl_sync(MVMC_FULL, ks ? e1 : e0, 4 * ro + kl);
+        const double p = 1.0 / diag;
+        const double r0 = rk0 * p, r1 = rk1 * p;
+        if (ro == k) {
+            e0 = r0;
+            e1 = r1;
+        } else {
+            e0 = e0 - f * r0;
+            e1 = e1 - f * r1;
+        }
+        if (q == kl) {
+            const double v = (ro == k) ? p : -f * p;
+            if (ks) e1 = v;
+            else e0 = v;
+        }
+    }
+}
+
+__device__ void invert_spd_blocked(double* Gg, int r, int ldr, double* sm) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int ro = lane >> 2, q = lane & 3;
+    const int nb = (r + 7) >> 3, np = 8 * nb, ld = np + 4;   // pitch = 4 (mod 8): every fragment pattern is conflict free
+    double* Gs = sm;               // [np][ld]
+    double* R = sm + np * ld;      // [8][ld]
+    for (int e = threadIdx.x; e < np * np; e += AL_THREADS) {
+        const int i = e / np, j = e - i * np;
+        Gs[i * ld + j] = (i < r && j < r) ? Gg[(size_t)i * ldr + j] : (i == j ? 1.0 : 0.0);
+    }
     __syncthreads();
-    if (r <= 32) invert_spd_regs<4, 1>(Gg, r, ldr, aux);
-    else if (r <= 64) invert_spd_regs<8, 2>(Gg, r, ldr, aux);
-    else if (r <= AL_RSMEM) invert_spd_regs<11, 3>(Gg, r, ldr, aux);
+    for (int kb = 0; kb < nb; kb++) {
+        // Pinv, in the accumulator layout
+        double2 pv = *reinterpret_cast<const double2*>(Gs + (8 * kb + ro) * ld + 8 * kb + 2 * q);
+        inv8_regs(pv.x, pv.y, lane);
+        // Pinv as A fragments (row ro, k = 4h + q) and as B fragments (k = 4h + q, column ro)
+        double pa[2], pb[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int sa = 4 * ro + 2 * h + (q >> 1);
+            const double a0 = __shfl_sync(MVMC_FULL, pv.x, sa), a1 = __shfl_sync(MVMC_FULL, pv.y, sa);
+            pa[h] = (q & 1) ? a1 : a0;
+            const int sb = 4 * (4 * h + q) + (ro >> 1);
+            const double b0 = __shfl_sync(MVMC_FULL, pv.x, sb), b1 = __shfl_sync(MVMC_FULL, pv.y, sb);
+            pb[h] = (ro & 1) ? b1 : b0;
+        }
+        // R[j] = Pinv G[kb, j]
+        for (int j = w; j < nb; j += AL_WARPS) {
+            if (j == kb) continue;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int h = 0; h < 2; h++) dmma(c0, c1, pa[h], Gs[(8 * kb + 4 * h + q) * ld + 8 * j + ro]);
+            double2 o;
+            o.x = c0;
+            o.y = c1;
+            *reinterpret_cast<double2*>(R + ro * ld + 8 * j + 2 * q) = o;
+        }
+        __syncthreads();
+        for (int i = w; i < nb; i += AL_WARPS) {
+            if (i == kb) {
+                for (int j = 0; j < nb; j++) {
+                    const double2 v = (j == kb) ? pv : *reinterpret_cast<const double2*>(R + ro * ld + 8 * j + 2 * q);
+                    *reinterpret_cast<double2*>(Gs + (8 * kb + ro) * ld + 8 * j + 2 * q) = v;
+                }
+            } else {
+                double nf[2];   // -G[i,kb] as A fragments
+#pragma unroll
+                for (int h = 0; h < 2; h++) nf[h] = -Gs[(8 * i + ro) * ld + 8 * kb + 4 * h + q];
+                __syncwarp();   // the block G[i,kb] is overwritten below by lanes that hold other elements of it
+                for (int j = 0; j < nb; j++) {
+                    double2* cp = reinterpret_cast<double2*>(Gs + (8 * i + ro) * ld + 8 * j + 2 * q);
+                    double c0 = 0.0, c1 = 0.0;
+                    if (j != kb) {
+                        const double2 c = *cp;
+                        c0 = c.x;
+                        c1 = c.y;
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; h++) dmma(c0, c1, nf[h], j == kb ? pb[h] : R[(4 * h + q) * ld + 8 * j + ro]);
+                    double2 o;
+                    o.x = c0;
+                    o.y = c1;
+                    *cp = o;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < r * r; e += AL_THREADS) {
+        const int i = e / r, j = e - i * r;
+        Gg[(size_t)i * ldr + j] = Gs[i * ld + j];
+    }
+}
+
+// Gg (r x r, ld ldr, global) <- inverse of Gg; `ring` = the (idle) operand ring, used as scratch
+__device__ __noinline__ void invert_normal_matrix(double* Gg, int r, int ldr, double* aux, double* ring) {
+    __syncthreads();
+    if (r <= GJB_MAXR) invert_spd_blocked(Gg, r, ldr, ring);
     else invert_spd(Gg, r, ldr, aux);
     __syncthreads();
 }
@@ -453,6 +562,30 @@ struct AlsLayout {
         ldr = (rmax + AL_PAD - 1) / AL_PAD * AL_PAD;
         zero_span = (size_t)NP * ldn + (size_t)2 * NP * ldr + (size_t)ldr * ldn + (size_t)ldr * ldr;
         per = (size_t)4 * NP * ldn + zero_span;
+    }
+};
+
+// optional per-phase cycle counters (thread 0 of every CTA; enabled by mvmc_als_phase_profile(1)): where an iteration's time goes
+enum { PH_G1 = 0, PH_INV1, PH_T1, PH_B, PH_G2, PH_INV2, PH_T2, PH_A, PH_X, PH_RED, PH_MU, PH_INIT, PH_COUNT };
+__device__ unsigned long long g_als_phase[PH_COUNT];
+__device__ int g_als_phase_on = 0;
+struct PhaseClock {
+    long long t;
+    bool on;
+    __device__ __forceinline__ void start() {
+#ifndef MVMC_EMU
+        on = g_als_phase_on != 0 && threadIdx.x == 0;
+        if (on) t = clock64();
+#endif
+    }
+    __device__ __forceinline__ void lap(int ph) {
+#ifndef MVMC_EMU
+        if (on) {
+            const long long now = clock64();
+            atomicAdd(&g_als_phase[ph], (unsigned long long)(now - t));
+            t = now;
+        }
+#endif
     }
 };
 
@@ -558,6 +691,8 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
     double* Tm = Bm + (size_t)L.NP * ldr;      // [ldr][ldn]
     double* Gg = Tm + (size_t)ldr * ldn;       // [ldr][ldr]
 
+    PhaseClock pc;
+    pc.start();
     const double* S = sim + (size_t)b * N * N;
     const bool f32 = f32_first_iter != nullptr && f32_first_iter[b] != 0;
 
@@ -593,6 +728,7 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
     __syncthreads();
 
     auto op = [&](int which, int I) { return Operand{&maps.m[which], maps.bytes[which], I}; };
+    pc.lap(PH_INIT);
     int it = 0;
     for (it = 0; it < max_iter; it++) {
         const double reg = alpha / mu;
@@ -604,7 +740,9 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
             });
             cta_gemm<KMAJ, KMAJ>(rg, op(MAP_A_KM, r), op(MAP_A_KN, r), n, ep);
         }
-        invert_normal_matrix(Gg, r, ldr, inv_aux);
+        pc.lap(PH_G1);
+        invert_normal_matrix(Gg, r, ldr, inv_aux, rg.stages);
+        pc.lap(PH_INV1);
         // ---- T = A^T Xt ----
         {
             auto ep = store_ep([&](int m, int nn, double v0, double v1) {
@@ -613,6 +751,7 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
             });
             cta_gemm<KMAJ, KMAJ>(rg, op(MAP_A_KM, r), op(MAP_XT_KN, n), n, ep);
         }
+        pc.lap(PH_T1);
         // ---- B = (Ginv T)^T ----
         {
             auto ep = store_ep([&](int m, int nn, double v0, double v1) {
@@ -621,6 +760,7 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
             });
             cta_gemm<IMAJ, KMAJ>(rg, op(MAP_G_IM, r), op(MAP_T_KN, n), r, ep);
         }
+        pc.lap(PH_B);
         // ---- H = B^T B + reg I, inverted ----
         {
             auto ep = store_ep([&](int m, int nn, double v0, double v1) {
@@ -629,7 +769,9 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
             });
             cta_gemm<KMAJ, KMAJ>(rg, op(MAP_B_KM, r), op(MAP_B_KN, r), n, ep);
         }
-        invert_normal_matrix(Gg, r, ldr, inv_aux);
+        pc.lap(PH_G2);
+        invert_normal_matrix(Gg, r, ldr, inv_aux, rg.stages);
+        pc.lap(PH_INV2);
         // ---- T = B^T Xt^T : T[m][i] = sum_j B[j][m] Xt[i][j] ----
         {
             auto ep = store_ep([&](int m, int nn, double v0, double v1) {
@@ -638,6 +780,7 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
             });
             cta_gemm<KMAJ, IMAJ>(rg, op(MAP_B_KM, r), op(MAP_XT_IN, n), n, ep);
         }
+        pc.lap(PH_T2);
         // ---- A = (Hinv T)^T ----
         {
             auto ep = store_ep([&](int m, int nn, double v0, double v1) {
@@ -646,13 +789,16 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
             });
             cta_gemm<IMAJ, KMAJ>(rg, op(MAP_G_IM, r), op(MAP_T_KN, n), r, ep);
         }
+        pc.lap(PH_A);
         // ---- X = A B^T, fused with the Z / Y / next-Xt updates and both residual norms ----
         AdmmEp ep{Xm, Y, Z, Xt, W, s_grp, n, ldn, mu, inv_mu, beta, 0.0, 0.0};
         cta_gemm<IMAJ, IMAJ>(rg, op(MAP_A_IM, n), op(MAP_B_IN, n), r, ep);
+        pc.lap(PH_X);
         const double psum = block_sum(ep.pacc, scratch);
         const double dsum = block_sum(ep.dacc, scratch);
         const double p_res = sqrt(psum) / n;
         const double d_res = mu * sqrt(dsum) / n;
+        pc.lap(PH_RED);
         if (p_res < tol && d_res < tol) {
             it++;
             break;
@@ -669,6 +815,7 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
                     const size_t o = (size_t)i * ldn + j;
                     Xt[o] = Z[o] - (Y[o] - W[o] + beta) * inv_mu;
                 }
+            pc.lap(PH_MU);
         }
     }
     __syncthreads();
@@ -839,7 +986,7 @@ int mvmc_match_als_ordered(const double* sim, const int* dim_groups, int n_group
     if (!sim || !dim_groups || !rand_stream || !workspace || !xbin || !n_iter) return MVMC_ERR_INVALID;
     if (B <= 0 || N <= 0 || N > 1024 || rmax <= 0 || rmax > 128 || n_groups <= 0 || n_groups > MVMC_MAX_VIEWS + 1)
         return MVMC_ERR_INVALID;
-    if ((reinterpret_cast<uintptr_t>(workspace) & 127) != 0) return MVMC_ERR_INVALID;   // TMA needs 16-byte, we ask for 128
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return MVMC_ERR_INVALID;   // tensor maps need a 16-byte aligned base
     AlsMaps maps;
     const int rc = als_build_maps(&maps, (double*)workspace, B, N, rmax);
     if (rc) return rc;
@@ -848,6 +995,26 @@ int mvmc_match_als_ordered(const double* sim, const int* dim_groups, int n_group
     MVMC_LAUNCH(k_als, dim3(B), dim3(AL_THREADS), smem, stream, maps, sim, dim_groups, n_groups, f32_first_iter, rand_stream,
                 order, N, rmax, (double*)workspace, xbin, n_iter, 50.0, 0.1, 1e-4, 1000);
     MVMC_CHECK_LAUNCH("k_als");
+    return MVMC_OK;
+}
+
+// enable != 0: start counting (resets); enable == 0: stop. out (may be null) receives the PH_COUNT cycle sums so far.
+extern "C" int mvmc_als_phase_profile(int enable, double* out) {
+#ifndef MVMC_EMU
+    unsigned long long h[PH_COUNT];
+    MVMC_CUDA_OK(cudaDeviceSynchronize());
+    MVMC_CUDA_OK(cudaMemcpyFromSymbol(h, g_als_phase, sizeof(h)));
+    if (out) for (int q = 0; q < PH_COUNT; q++) out[q] = (double)h[q];
+    const int on = enable ? 1 : 0;
+    if (enable) {
+        memset(h, 0, sizeof(h));
+        MVMC_CUDA_OK(cudaMemcpyToSymbol(g_als_phase, h, sizeof(h)));
+    }
+    MVMC_CUDA_OK(cudaMemcpyToSymbol(g_als_phase_on, &on, sizeof(on)));
+#else
+    if (out) for (int q = 0; q < PH_COUNT; q++) out[q] = 0.0;
+    (void)enable;
+#endif
     return MVMC_OK;
 }
 
