@@ -240,9 +240,9 @@ def run_ours(args):
     ms = float(ms.item())
     launches = lib.mvmc_launch_count() - launches0
     if args.als_phases and rank == 0:
-        ph = np.zeros(12)
+        ph = np.zeros(15)
         check(lib.mvmc_als_phase_profile(0, ptr(ph)), "mvmc_als_phase_profile")
-        names = ["G=AtA", "inv1", "T=AtXt", "B", "H=BtB", "inv2", "T=BtXtt", "A", "X=ABt+admm", "reduce", "mu-pass", "init"]
+        names = ["G=AtA", "inv1", "T=AtXt", "B", "H=BtB", "inv2", "T=BtXtt", "A", "X=ABt", "reduce", "mu-pass", "init", "admm-pass", "admm-wait", "admm-fence"]
         print("k_als phase share of CTA cycles: " + ", ".join(f"{n} {100 * v / ph.sum():.1f}%" for n, v in zip(names, ph)),
               file=sys.stderr, flush=True)
     stage_ms, n_prof = cb.profile(0)

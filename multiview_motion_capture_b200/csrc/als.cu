@@ -90,6 +90,7 @@ inline void emu_tma(double* dst, const TMap* m, const int* crd) {
                 dst[row * 16 + unit * 2 + (x & 1)] = in ? m->base[off] : 0.0;
             }
 }
+__device__ __forceinline__ void bulk_g2s(double* dst, const double* src, unsigned bytes, mbar_t*) { memcpy(dst, src, bytes); }
 __device__ __forceinline__ void tma_load3(double* dst, const TMap* m, int c0, int c1, int c2, mbar_t*) {
     const int crd[4] = {c0, c1, c2, 0};
     emu_tma(dst, m, crd);
@@ -137,6 +138,12 @@ __device__ __forceinline__ void tma_load4(double* dst, const TMap* m, int c0, in
             smem_u32(dst)),
         "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+// contiguous global -> shared bulk copy (16-byte aligned, size a multiple of 16), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(double* dst, const double* src, unsigned bytes, mbar_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 // orders this thread's earlier generic-proxy writes before later async-proxy (TMA) reads of the same data
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -561,12 +568,12 @@ struct AlsLayout {
         ldn = NP;
         ldr = (rmax + AL_PAD - 1) / AL_PAD * AL_PAD;
         zero_span = (size_t)NP * ldn + (size_t)2 * NP * ldr + (size_t)ldr * ldn + (size_t)ldr * ldr;
-        per = (size_t)4 * NP * ldn + zero_span;
+        per = (size_t)5 * NP * ldn + zero_span;
     }
 };
 
 // optional per-phase cycle counters (thread 0 of every CTA; enabled by mvmc_als_phase_profile(1)): where an iteration's time goes
-enum { PH_G1 = 0, PH_INV1, PH_T1, PH_B, PH_G2, PH_INV2, PH_T2, PH_A, PH_X, PH_RED, PH_MU, PH_INIT, PH_COUNT };
+enum { PH_G1 = 0, PH_INV1, PH_T1, PH_B, PH_G2, PH_INV2, PH_T2, PH_A, PH_X, PH_RED, PH_MU, PH_INIT, PH_ADMM, PH_ADMM_WAIT, PH_ADMM_FENCE, PH_COUNT };
 __device__ unsigned long long g_als_phase[PH_COUNT];
 __device__ int g_als_phase_on = 0;
 struct PhaseClock {
@@ -589,56 +596,122 @@ struct PhaseClock {
     }
 };
 
-// epilogue of X = A B^T: Z / Y / next-Xt update and the two residual sums (mv_association.py:286-296)
-struct AdmmEp {
-    struct Buf {
-        double2 x0, y, w;
-    };
-    double *Xm, *Y, *Z, *Xt;
-    const double* W;
-    const int* grp;
-    int n, ldn;
-    double mu, inv_mu, beta;
-    double pacc, dacc;
-    __device__ __forceinline__ void load(Buf& b, int i, int j) const {
-        const size_t o = (size_t)i * ldn + j;
-        b.x0 = *reinterpret_cast<const double2*>(Xm + o);
-        b.y = *reinterpret_cast<const double2*>(Y + o);
-        b.w = *reinterpret_cast<const double2*>(W + o);
-    }
-    __device__ __forceinline__ void one(int gi, int i, int j, double x, double x0, double y, double w, bool live, double& yn,
-                                        double& z, double& xt) {
-        const double dd = x - x0;
-        z = x + y * inv_mu;                       // y / mu (mu is a power of two)
-        if (gi == grp[live ? j : i]) z = 0.0;
-        if (i == j) z = 1.0;
-        if (z < 0.0) z = 0.0;
-        if (z > 1.0) z = 1.0;
-        const double pd = x - z;
-        yn = y + mu * pd;
-        xt = z - (yn - w + beta) * inv_mu;        // next iteration's Xt if mu stays
-        if (live) {
-            dacc += dd * dd;
-            pacc += pd * pd;
-        } else {
-            xt = 0.0;                             // padding column of Xt stays zero (it is read by the next products)
-        }
-    }
-    __device__ __forceinline__ void apply(const Buf& b, int i, int j, double v0, double v1) {
-        const size_t o = (size_t)i * ldn + j;
-        const bool live1 = j + 1 < n;   // the odd column of the last pair may be padding
-        const int gi = grp[i];
-        double2 yn, z, xt, xv;
-        one(gi, i, j, v0, b.x0.x, b.y.x, b.w.x, true, yn.x, z.x, xt.x);
-        one(gi, i, j + 1, v1, b.x0.y, b.y.y, b.w.y, live1, yn.y, z.y, xt.y);
-        xv.x = v0;
-        xv.y = v1;
-        *reinterpret_cast<double2*>(Y + o) = yn;
-        *reinterpret_cast<double2*>(Z + o) = z;
-        *reinterpret_cast<double2*>(Xm + o) = xv;
-        *reinterpret_cast<double2*>(Xt + o) = xt;
-    }
+// The ADMM element-wise update (mv_association.py:286-296) as a streaming pass over row strips: X = A B^T only stores X
+// (two X buffers alternate between "new" and "previous"); this pass then pulls strips of X_new, X_prev, Y, W through the
+// (idle) operand ring with contiguous bulk copies - up to 4 strips (~78 KB) in flight per CTA, none of it held in
+// registers - and writes the new Y and the next Xt with coalesced 16-byte stores (Y alternates between two buffers like
+// X; Z itself is never stored: the rare mu change recomputes it from X and the previous Y, bit for bit). As an epilogue of the product the same
+// update was bound by the few loads a thread can keep in flight next to its 48 accumulator registers.
+constexpr int AL_PASS_NS = 4;
+struct AdmmPass {
+    mbar_t* bar;        // [AL_PASS_NS]
+    unsigned use;       // strips consumed so far (all passes of this CTA): stage and parity of the next one
+    int rs, ns;         // rows per strip, stages (fixed per launch: functions of ldn)
 };
+
+__device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const double* Xn, const double* Xo, const double* Yo, double* Yn,
+                                          const double* W, double* Xt, const int* grp, int n, int ldn, double mu, double inv_mu,
+                                          double beta, double& pacc, double& dacc, PhaseClock& pc) {
+    const int rs = ps.rs, ns = ps.ns;
+    const int stage_doubles = 4 * rs * ldn;
+    const int total = (n + rs - 1) / rs;          // strips
+    const int hpn = (n + 1) >> 1;                 // live column pairs of a row
+    const int spp = rs * hpn;                     // pairs of a (full) strip
+    const int P = n * hpn;                        // pairs of the whole pass
+    fence_proxy_async();   // X_new (and the Y of the previous pass) were written with generic stores
+    __syncthreads();
+    pc.lap(PH_ADMM_FENCE);
+    // Rows are visited last to first (the rows X = A B^T wrote most recently are the ones most likely still in L2):
+    // "logical" row q is row n-1-q; strip s = logical rows [s rs, (s+1) rs) = one contiguous block of rows.
+    auto issue = [&](int s) {
+        const unsigned g = ps.use + (unsigned)s;
+        const int st = g % ns;
+        const int hi = min(n, (s + 1) * rs), nr = hi - s * rs, r0 = n - hi;
+        const unsigned bytes = (unsigned)(nr * ldn) * 8u;
+        double* dst = ring + st * stage_doubles;
+        const size_t o = (size_t)r0 * ldn;
+        mbar_expect_tx(&ps.bar[st], 4u * bytes);
+        bulk_g2s(dst, Xn + o, bytes, &ps.bar[st]);
+        bulk_g2s(dst + rs * ldn, Xo + o, bytes, &ps.bar[st]);
+        bulk_g2s(dst + 2 * rs * ldn, Yo + o, bytes, &ps.bar[st]);
+        bulk_g2s(dst + 3 * rs * ldn, W + o, bytes, &ps.bar[st]);
+    };
+    if (threadIdx.x == 0) {
+        const int pre = min(ns, total);
+        for (int s = 0; s < pre; s++) issue(s);
+    }
+    // The pairs of the pass are one flat index space walked 256 at a time, independent of the strip boundaries (a strip
+    // of two 262-column rows is 262 pairs: strip-synchronous rounds would run half empty). A round waits for the strips
+    // it touches, and the strips it completes are refilled after one barrier.
+    int waited = 0, done = 0;   // strips whose data this thread has waited for / that are fully consumed (uniform)
+    for (int e0 = 0; e0 < P;) {
+        const int e1 = min(min(P, e0 + AL_THREADS), (done + ns) * spp);   // never past the strips in flight
+        const int sb = (e1 - 1) / spp;
+        pc.lap(PH_ADMM);
+        for (; waited <= sb; waited++) {
+            const unsigned g = ps.use + (unsigned)waited;
+            mbar_wait(&ps.bar[g % ns], (g / ns) & 1);
+        }
+        pc.lap(PH_ADMM_WAIT);
+        AL_EMU_SYNC();
+        const int e = e0 + (int)threadIdx.x;
+        if (e < e1) {
+            const int q = e / hpn, j = (e - q * hpn) * 2;   // logical row, first column of the pair
+            const int sq = q / rs;
+            const int i = n - 1 - q;
+            const int hi = min(n, (sq + 1) * rs);
+            const int so = (i - (n - hi)) * ldn + j;
+            const double* sx = ring + ((ps.use + (unsigned)sq) % ns) * stage_doubles;
+            const double2 x = *reinterpret_cast<const double2*>(sx + so), x0 = *reinterpret_cast<const double2*>(sx + rs * ldn + so),
+                          y = *reinterpret_cast<const double2*>(sx + 2 * rs * ldn + so),
+                          w = *reinterpret_cast<const double2*>(sx + 3 * rs * ldn + so);
+            const int gi = grp[i];
+            const bool live1 = j + 1 < n;     // the odd column of the last pair may be padding
+            double2 yn, xt;
+            {
+                const double dd = x.x - x0.x;
+                double zz = x.x + y.x * inv_mu;                 // y / mu (mu is a power of two)
+                if (gi == grp[j]) zz = 0.0;
+                if (i == j) zz = 1.0;
+                if (zz < 0.0) zz = 0.0;
+                if (zz > 1.0) zz = 1.0;
+                const double pd = x.x - zz;
+                yn.x = y.x + mu * pd;
+                xt.x = zz - (yn.x - w.x + beta) * inv_mu;       // next iteration's Xt if mu stays
+                dacc += dd * dd;
+                pacc += pd * pd;
+            }
+            {
+                const double dd = x.y - x0.y;
+                double zz = x.y + y.y * inv_mu;
+                if (gi == grp[live1 ? j + 1 : i]) zz = 0.0;
+                if (i == j + 1) zz = 1.0;
+                if (zz < 0.0) zz = 0.0;
+                if (zz > 1.0) zz = 1.0;
+                const double pd = x.y - zz;
+                yn.y = y.y + mu * pd;
+                xt.y = live1 ? zz - (yn.y - w.y + beta) * inv_mu : 0.0;   // the padding column of Xt stays zero
+                if (live1) {
+                    dacc += dd * dd;
+                    pacc += pd * pd;
+                }
+            }
+            const size_t o = (size_t)i * ldn + j;
+            *reinterpret_cast<double2*>(Yn + o) = yn;
+            *reinterpret_cast<double2*>(Xt + o) = xt;
+        }
+        const int now_done = e1 >= P ? total : e1 / spp;   // strips with every pair below e1
+        if (now_done > done) {
+            __syncthreads();   // everyone is done with those stages
+            if (threadIdx.x == 0)
+                for (int s2 = done; s2 < now_done; s2++)
+                    if (s2 + ns < total) issue(s2 + ns);
+            done = now_done;
+        }
+        e0 = e1;
+    }
+    ps.use += (unsigned)total;
+}
 
 __global__ void __launch_bounds__(AL_THREADS, 2)
     k_als(const AL_GRID_CONSTANT AlsMaps maps, const double* __restrict__ sim, const int* __restrict__ dim_groups, int n_groups,
@@ -670,22 +743,32 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
     rg.empty = rg.full + AL_NS;                                   // [AL_NS]
     rg.gc = 0;
     rg.clip = b;
-    int* s_grp = reinterpret_cast<int*>(rg.empty + AL_NS);        // [N + 1]
+    AdmmPass ps;
+    ps.bar = rg.empty + AL_NS;                                    // [AL_PASS_NS]
+    ps.use = 0;
+    {
+        const int ring_doubles = AL_NS * AL_STAGE, ldn_ = (N + AL_PAD - 1) / AL_PAD * AL_PAD;
+        ps.rs = max(1, ring_doubles / (AL_PASS_NS * 4 * ldn_));
+        ps.ns = max(1, min(AL_PASS_NS, ring_doubles / (4 * ps.rs * ldn_)));
+    }
+    int* s_grp = reinterpret_cast<int*>(ps.bar + AL_PASS_NS);     // [N + 1]
     if (threadIdx.x == 0) {
         for (int s = 0; s < AL_NS; s++) {
             mbar_init(&rg.full[s], 1);
             mbar_init(&rg.empty[s], AL_WARPS);
         }
+        for (int s = 0; s < AL_PASS_NS; s++) mbar_init(&ps.bar[s], 1);
         mbar_fence_init();
     }
 
     const AlsLayout L(N, rmax);
     const int ldn = L.ldn, ldr = L.ldr;
     double* W = ws + (size_t)b * L.per;
-    double* Z = W + (size_t)L.NP * ldn;
-    double* Y = Z + (size_t)L.NP * ldn;
-    double* Xm = Y + (size_t)L.NP * ldn;
-    double* Xt = Xm + (size_t)L.NP * ldn;      // [NP][ldn]   (from here on: zeroed below, padding stays zero)
+    double* Yn = W + (size_t)L.NP * ldn;       // Y being formed        } swap every iteration
+    double* Y = Yn + (size_t)L.NP * ldn;       // Y of the last update  }
+    double* Xm = Y + (size_t)L.NP * ldn;       // X of the previous iteration  } the two buffers swap roles
+    double* Xn = Xm + (size_t)L.NP * ldn;      // X being formed               } every iteration
+    double* Xt = Xn + (size_t)L.NP * ldn;      // [NP][ldn]   (from here on: zeroed below, padding stays zero)
     double* A = Xt + (size_t)L.NP * ldn;       // [NP][ldr]
     double* Bm = A + (size_t)L.NP * ldr;       // [NP][ldr]
     double* Tm = Bm + (size_t)L.NP * ldr;      // [ldr][ldn]
@@ -717,7 +800,6 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
             if (f32) w = (double)(0.5f * ((float)S[(size_t)i * N + j] + (float)S[(size_t)j * N + i]));
             else w = 0.5 * (S[(size_t)i * N + j] + S[(size_t)j * N + i]);
             W[o] = w;
-            Z[o] = w;
             Xm[o] = w;
             Y[o] = 0.0;
             // first Xt (Z = W, Y = 0); the float32 no-track path of the reference keeps float32 through this expression
@@ -790,12 +872,31 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
             cta_gemm<IMAJ, KMAJ>(rg, op(MAP_G_IM, r), op(MAP_T_KN, n), r, ep);
         }
         pc.lap(PH_A);
-        // ---- X = A B^T, fused with the Z / Y / next-Xt updates and both residual norms ----
-        AdmmEp ep{Xm, Y, Z, Xt, W, s_grp, n, ldn, mu, inv_mu, beta, 0.0, 0.0};
-        cta_gemm<IMAJ, IMAJ>(rg, op(MAP_A_IM, n), op(MAP_B_IN, n), r, ep);
+        // ---- X = A B^T ----
+        {
+            auto ep = store_ep([&](int i, int j, double v0, double v1) {
+                double2 xv;
+                xv.x = v0;
+                xv.y = v1;
+                *reinterpret_cast<double2*>(Xn + (size_t)i * ldn + j) = xv;   // (an odd last column lands in the padding)
+            });
+            cta_gemm<IMAJ, IMAJ>(rg, op(MAP_A_IM, n), op(MAP_B_IN, n), r, ep);
+        }
         pc.lap(PH_X);
-        const double psum = block_sum(ep.pacc, scratch);
-        const double dsum = block_sum(ep.dacc, scratch);
+        // ---- Z / Y / next-Xt updates and both residual norms ----
+        double pacc = 0.0, dacc = 0.0;
+        admm_pass(ps, rg.stages, Xn, Xm, Y, Yn, W, Xt, s_grp, n, ldn, mu, inv_mu, beta, pacc, dacc, pc);
+        {
+            double* t = Xm;
+            Xm = Xn;
+            Xn = t;
+            t = Y;
+            Y = Yn;
+            Yn = t;
+        }
+        pc.lap(PH_ADMM);
+        const double psum = block_sum(pacc, scratch);
+        const double dsum = block_sum(dacc, scratch);
         const double p_res = sqrt(psum) / n;
         const double d_res = mu * sqrt(dsum) / n;
         pc.lap(PH_RED);
@@ -807,14 +908,24 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
         if (p_res > 10.0 * d_res) mu_new = 2.0 * mu;
         else if (d_res > 10.0 * p_res) mu_new = mu / 2.0;
         if (mu_new != mu) {
+            // Xt = Z - (Y - W + beta) / mu_new, with Z recomputed exactly as the pass formed it (same operands: the new X, the
+            // Y before the update - now in Yn after the swap - and the old mu)
+            const double inv_old = inv_mu;
             mu = mu_new;
             inv_mu = 1.0 / mu;
             __syncthreads();
-            for (int i = threadIdx.x >> 5; i < n; i += AL_WARPS)
+            for (int i = threadIdx.x >> 5; i < n; i += AL_WARPS) {
+                const int gi = s_grp[i];
                 for (int j = threadIdx.x & 31; j < n; j += 32) {
                     const size_t o = (size_t)i * ldn + j;
-                    Xt[o] = Z[o] - (Y[o] - W[o] + beta) * inv_mu;
+                    double zz = Xm[o] + Yn[o] * inv_old;
+                    if (gi == s_grp[j]) zz = 0.0;
+                    if (i == j) zz = 1.0;
+                    if (zz < 0.0) zz = 0.0;
+                    if (zz > 1.0) zz = 1.0;
+                    Xt[o] = zz - (Y[o] - W[o] + beta) * inv_mu;
                 }
+            }
             pc.lap(PH_MU);
         }
     }
@@ -877,7 +988,7 @@ int mvmc_als_order(const int* prev_iter, int B, int* order, void* stream) {
 }
 
 static size_t als_smem_bytes(int N) {
-    return 1024 + (size_t)(AL_NS * AL_STAGE + 32 + 4 * GJ_LD) * sizeof(double) + 2 * AL_NS * sizeof(mbar_t) +
+    return 1024 + (size_t)(AL_NS * AL_STAGE + 32 + 4 * GJ_LD) * sizeof(double) + (2 * AL_NS + AL_PASS_NS) * sizeof(mbar_t) +
            (size_t)(N + 2) * sizeof(int);
 }
 
@@ -953,7 +1064,7 @@ static int als_make_map(TMap* out, unsigned* bytes, double* base, int rows, int 
 
 static int als_build_maps(AlsMaps* M, double* ws, int B, int N, int rmax) {
     const AlsLayout L(N, rmax);
-    double* Xt = ws + (size_t)4 * L.NP * L.ldn;
+    double* Xt = ws + (size_t)5 * L.NP * L.ldn;
     double* A = Xt + (size_t)L.NP * L.ldn;
     double* Bm = A + (size_t)L.NP * L.ldr;
     double* Tm = Bm + (size_t)L.NP * L.ldr;
