@@ -602,9 +602,11 @@ struct PhaseClock {
 // registers - and writes the new Y and the next Xt with coalesced 16-byte stores (Y alternates between two buffers like
 // X; Z itself is never stored: the rare mu change recomputes it from X and the previous Y, bit for bit). As an epilogue of the product the same
 // update was bound by the few loads a thread can keep in flight next to its 48 accumulator registers.
-constexpr int AL_PASS_NS = 4;
+constexpr int AL_PASS_NS = 4;    // strips in flight
+constexpr int AL_PASS_U = 1;     // pairs per thread per round
 struct AdmmPass {
-    mbar_t* bar;        // [AL_PASS_NS]
+    mbar_t* bar;        // [AL_PASS_NS] bytes landed in a stage
+    unsigned* cnt;      // [AL_PASS_NS] warps that have left a stage (running count)
     unsigned use;       // strips consumed so far (all passes of this CTA): stage and parity of the next one
     int rs, ns;         // rows per strip, stages (fixed per launch: functions of ldn)
 };
@@ -630,11 +632,15 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
         const unsigned bytes = (unsigned)(nr * ldn) * 8u;
         double* dst = ring + st * stage_doubles;
         const size_t o = (size_t)r0 * ldn;
+#ifndef AL_EXP_NOLOAD
         mbar_expect_tx(&ps.bar[st], 4u * bytes);
         bulk_g2s(dst, Xn + o, bytes, &ps.bar[st]);
         bulk_g2s(dst + rs * ldn, Xo + o, bytes, &ps.bar[st]);
         bulk_g2s(dst + 2 * rs * ldn, Yo + o, bytes, &ps.bar[st]);
         bulk_g2s(dst + 3 * rs * ldn, W + o, bytes, &ps.bar[st]);
+#else
+        mbar_arrive(&ps.bar[st]);
+#endif
     };
     if (threadIdx.x == 0) {
         const int pre = min(ns, total);
@@ -642,75 +648,126 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
     }
     // The pairs of the pass are one flat index space walked 256 at a time, independent of the strip boundaries (a strip
     // of two 262-column rows is 262 pairs: strip-synchronous rounds would run half empty). A round waits for the strips
-    // it touches, and the strips it completes are refilled after one barrier.
+    // it touches, and the strips it completes are refilled after one barrier. All indices advance incrementally - the
+    // pass is issue bound, an integer division per pair would cost as much as its arithmetic.
     int waited = 0, done = 0;   // strips whose data this thread has waited for / that are fully consumed (uniform)
+    // A thread handles AL_PASS_U pairs per round, AL_THREADS apart, as independent instruction streams: the FP64 pipe is
+    // shared with the other CTA's DMMAs, so a single dependent chain of ~25 FP64 operations crawls.
+    int q = 0, c = (int)threadIdx.x;            // this thread's first pair: logical row q, pair c of the row
+    int sq = 0, stq = (int)(ps.use % (unsigned)ns);   // strip of row q and its stage
+    while (c >= hpn) {
+        c -= hpn;
+        q++;
+    }
     for (int e0 = 0; e0 < P;) {
-        const int e1 = min(min(P, e0 + AL_THREADS), (done + ns) * spp);   // never past the strips in flight
-        const int sb = (e1 - 1) / spp;
-        pc.lap(PH_ADMM);
-        for (; waited <= sb; waited++) {
+        const int e1 = min(min(P, e0 + AL_PASS_U * AL_THREADS), (done + ns) * spp);   // never past the strips in flight
+        while (waited < total && waited * spp < e1) {
             const unsigned g = ps.use + (unsigned)waited;
             mbar_wait(&ps.bar[g % ns], (g / ns) & 1);
+            waited++;
         }
-        pc.lap(PH_ADMM_WAIT);
         AL_EMU_SYNC();
-        const int e = e0 + (int)threadIdx.x;
-        if (e < e1) {
-            const int q = e / hpn, j = (e - q * hpn) * 2;   // logical row, first column of the pair
-            const int sq = q / rs;
-            const int i = n - 1 - q;
-            const int hi = min(n, (sq + 1) * rs);
-            const int so = (i - (n - hi)) * ldn + j;
-            const double* sx = ring + ((ps.use + (unsigned)sq) % ns) * stage_doubles;
-            const double2 x = *reinterpret_cast<const double2*>(sx + so), x0 = *reinterpret_cast<const double2*>(sx + rs * ldn + so),
-                          y = *reinterpret_cast<const double2*>(sx + 2 * rs * ldn + so),
-                          w = *reinterpret_cast<const double2*>(sx + 3 * rs * ldn + so);
-            const int gi = grp[i];
+        while (q >= (sq + 1) * rs) {
+            sq++;
+            stq = stq + 1 == ns ? 0 : stq + 1;
+        }
+        bool on[AL_PASS_U];
+        int pi[AL_PASS_U], pj[AL_PASS_U];
+        double2 x[AL_PASS_U], x0[AL_PASS_U], y[AL_PASS_U], w[AL_PASS_U];
+        int gi[AL_PASS_U];
+        int2 gj[AL_PASS_U];
+        {
+            int uq = q, uc = c, usq = sq, ust = stq;
+#pragma unroll
+            for (int u = 0; u < AL_PASS_U; u++) {
+                on[u] = e0 + u * AL_THREADS + (int)threadIdx.x < e1;
+                if (on[u]) {
+                    const int j = 2 * uc, i = n - 1 - uq;
+                    const int hi = min(n, (usq + 1) * rs);
+                    const double* sx = ring + ust * stage_doubles + (i - (n - hi)) * ldn + j;
+                    x[u] = *reinterpret_cast<const double2*>(sx);
+                    x0[u] = *reinterpret_cast<const double2*>(sx + rs * ldn);
+                    y[u] = *reinterpret_cast<const double2*>(sx + 2 * rs * ldn);
+                    w[u] = *reinterpret_cast<const double2*>(sx + 3 * rs * ldn);
+                    gi[u] = grp[i];
+                    gj[u] = *reinterpret_cast<const int2*>(grp + j);   // (grp[n] = -1: an odd last column is in no group)
+                    pi[u] = i;
+                    pj[u] = j;
+                }
+                // the next pair of this thread is AL_THREADS further on
+                uc += AL_THREADS;
+                while (uc >= hpn) {
+                    uc -= hpn;
+                    uq++;
+                }
+                while (uq >= (usq + 1) * rs) {
+                    usq++;
+                    ust = ust + 1 == ns ? 0 : ust + 1;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < AL_PASS_U; u++) {
+            if (!on[u]) continue;
+            const int i = pi[u], j = pj[u];
             const bool live1 = j + 1 < n;     // the odd column of the last pair may be padding
             double2 yn, xt;
             {
-                const double dd = x.x - x0.x;
-                double zz = x.x + y.x * inv_mu;                 // y / mu (mu is a power of two)
-                if (gi == grp[j]) zz = 0.0;
+                const double dd = x[u].x - x0[u].x;
+                double zz = x[u].x + y[u].x * inv_mu;           // y / mu (mu is a power of two)
+                if (gi[u] == gj[u].x) zz = 0.0;
                 if (i == j) zz = 1.0;
-                if (zz < 0.0) zz = 0.0;
-                if (zz > 1.0) zz = 1.0;
-                const double pd = x.x - zz;
-                yn.x = y.x + mu * pd;
-                xt.x = zz - (yn.x - w.x + beta) * inv_mu;       // next iteration's Xt if mu stays
+                zz = fmin(fmax(zz, 0.0), 1.0);
+                const double pd = x[u].x - zz;
+                yn.x = y[u].x + mu * pd;
+                xt.x = zz - (yn.x - w[u].x + beta) * inv_mu;    // next iteration's Xt if mu stays
                 dacc += dd * dd;
                 pacc += pd * pd;
             }
             {
-                const double dd = x.y - x0.y;
-                double zz = x.y + y.y * inv_mu;
-                if (gi == grp[live1 ? j + 1 : i]) zz = 0.0;
+                const double dd = x[u].y - x0[u].y;
+                double zz = x[u].y + y[u].y * inv_mu;
+                if (gi[u] == gj[u].y) zz = 0.0;
                 if (i == j + 1) zz = 1.0;
-                if (zz < 0.0) zz = 0.0;
-                if (zz > 1.0) zz = 1.0;
-                const double pd = x.y - zz;
-                yn.y = y.y + mu * pd;
-                xt.y = live1 ? zz - (yn.y - w.y + beta) * inv_mu : 0.0;   // the padding column of Xt stays zero
+                zz = fmin(fmax(zz, 0.0), 1.0);
+                const double pd = x[u].y - zz;
+                yn.y = y[u].y + mu * pd;
+                xt.y = live1 ? zz - (yn.y - w[u].y + beta) * inv_mu : 0.0;   // the padding column of Xt stays zero
                 if (live1) {
                     dacc += dd * dd;
                     pacc += pd * pd;
                 }
             }
             const size_t o = (size_t)i * ldn + j;
+#ifndef AL_EXP_NOSTORE
             *reinterpret_cast<double2*>(Yn + o) = yn;
             *reinterpret_cast<double2*>(Xt + o) = xt;
+#else
+            pacc += yn.x * 1e-30 + yn.y * 1e-30 + xt.x * 1e-30 + xt.y * 1e-30 + (double)o * 1e-300;
+#endif
         }
-        const int now_done = e1 >= P ? total : e1 / spp;   // strips with every pair below e1
-        if (now_done > done) {
-            __syncthreads();   // everyone is done with those stages
-            if (threadIdx.x == 0)
-                for (int s2 = done; s2 < now_done; s2++)
-                    if (s2 + ns < total) issue(s2 + ns);
-            done = now_done;
+        // every thread moves on by the size of the round
+        c += e1 - e0;
+        while (c >= hpn) {
+            c -= hpn;
+            q++;
         }
+        // strips this warp has finished with: the last of the 8 warps out of a strip refills its stage (no block barrier:
+        // the warps drift apart by up to the depth of the ring, and no single thread's copy issue is on everyone's path)
+        __syncwarp();
+        while (done < total && min(P, (done + 1) * spp) <= e1) {
+            if ((threadIdx.x & 31) == 0) {
+                __threadfence_block();
+                const unsigned was = atomicAdd(&ps.cnt[(ps.use + (unsigned)done) % ns], 1u);
+                if ((was & (AL_WARPS - 1)) == AL_WARPS - 1 && done + ns < total) issue(done + ns);
+            }
+            done++;
+        }
+        AL_EMU_SYNC();
         e0 = e1;
     }
     ps.use += (unsigned)total;
+    __syncthreads();   // (the ring is handed back to the products)
 }
 
 __global__ void __launch_bounds__(AL_THREADS, 2)
@@ -751,13 +808,17 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
         ps.rs = max(1, ring_doubles / (AL_PASS_NS * 4 * ldn_));
         ps.ns = max(1, min(AL_PASS_NS, ring_doubles / (4 * ps.rs * ldn_)));
     }
-    int* s_grp = reinterpret_cast<int*>(ps.bar + AL_PASS_NS);     // [N + 1]
+    ps.cnt = reinterpret_cast<unsigned*>(ps.bar + AL_PASS_NS);    // [AL_PASS_NS]
+    int* s_grp = reinterpret_cast<int*>(ps.cnt + AL_PASS_NS + (AL_PASS_NS & 1));   // [N + 1], 8-byte aligned
     if (threadIdx.x == 0) {
         for (int s = 0; s < AL_NS; s++) {
             mbar_init(&rg.full[s], 1);
             mbar_init(&rg.empty[s], AL_WARPS);
         }
-        for (int s = 0; s < AL_PASS_NS; s++) mbar_init(&ps.bar[s], 1);
+        for (int s = 0; s < AL_PASS_NS; s++) {
+            mbar_init(&ps.bar[s], 1);
+            ps.cnt[s] = 0;
+        }
         mbar_fence_init();
     }
 
@@ -988,7 +1049,7 @@ int mvmc_als_order(const int* prev_iter, int B, int* order, void* stream) {
 }
 
 static size_t als_smem_bytes(int N) {
-    return 1024 + (size_t)(AL_NS * AL_STAGE + 32 + 4 * GJ_LD) * sizeof(double) + (2 * AL_NS + AL_PASS_NS) * sizeof(mbar_t) +
+    return 1024 + (size_t)(AL_NS * AL_STAGE + 32 + 4 * GJ_LD) * sizeof(double) + (2 * AL_NS + 2 * AL_PASS_NS) * sizeof(mbar_t) +
            (size_t)(N + 2) * sizeof(int);
 }
 
