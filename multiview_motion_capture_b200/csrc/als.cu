@@ -211,18 +211,34 @@ __device__ __forceinline__ double frag_ld(const double* S, int base, int s) {
     return S[base ^ ((kb >> 1) << 1)];                            // unit ^= kb / 2
 }
 
-// Shape of one product as the ring sees it.
+// Shape of one product as the ring sees it, and a cursor over its chunks (tile-major, N tiles inside M tiles, k-chunks
+// inside a tile) that every thread advances in step with the chunk loop: the position of the chunk to issue next costs
+// three compares instead of two integer divisions.
 struct Tiling {
     int nk, tn, total;   // k-chunks per tile, tiles along N, chunks of the whole product
 };
+struct ChunkCursor {
+    int c, kc, tn, m0, n0;   // chunk index; k-chunk and N tile inside the current tile row; tile origin
+    __device__ __forceinline__ void reset() { c = kc = tn = m0 = n0 = 0; }
+    __device__ __forceinline__ void next(const Tiling& tl) {
+        c++;
+        if (++kc == tl.nk) {
+            kc = 0;
+            n0 += AL_TN;
+            if (++tn == tl.tn) {
+                tn = 0;
+                n0 = 0;
+                m0 += AL_TM;
+            }
+        }
+    }
+};
 
-// Loads chunk c (0-based inside the product) of both operands into its stage. Called by ONE converged warp.
+// Loads the chunk under the cursor of both operands into its stage. Called by ONE converged warp.
 template <bool MK, bool NK>
-__device__ __forceinline__ void ring_issue(const Ring& rg, const Operand& Mop, const Operand& Nop, const Tiling& tl, int c) {
-    const int t = c / tl.nk, kc = c - t * tl.nk;
-    const int tm = t / tl.tn, tnn = t - tm * tl.tn;
-    const int m0 = tm * AL_TM, n0 = tnn * AL_TN, k0 = kc * AL_KC;
-    const unsigned g = rg.gc + (unsigned)c;
+__device__ __forceinline__ void ring_issue(const Ring& rg, const Operand& Mop, const Operand& Nop, const ChunkCursor& cu) {
+    const int k0 = cu.kc * AL_KC;
+    const unsigned g = rg.gc + (unsigned)cu.c;
     const int st = g % AL_NS;
     const unsigned use = g / AL_NS;
     if (use > 0) mbar_wait(&rg.empty[st], (use - 1) & 1);     // all 8 warps have finished with the stage's previous chunk
@@ -230,10 +246,10 @@ __device__ __forceinline__ void ring_issue(const Ring& rg, const Operand& Mop, c
         double* Sm = rg.stages + st * AL_STAGE;
         double* Sn = Sm + AL_STAGE_M;
         mbar_expect_tx(&rg.full[st], Mop.bytes + Nop.bytes);
-        if (MK) tma_load4(Sm, Mop.map, 0, k0, m0 >> 4, rg.clip, &rg.full[st]);
-        else tma_load3(Sm, Mop.map, k0, m0, rg.clip, &rg.full[st]);
-        if (NK) tma_load4(Sn, Nop.map, 0, k0, n0 >> 4, rg.clip, &rg.full[st]);
-        else tma_load3(Sn, Nop.map, k0, n0, rg.clip, &rg.full[st]);
+        if (MK) tma_load4(Sm, Mop.map, 0, k0, cu.m0 >> 4, rg.clip, &rg.full[st]);
+        else tma_load3(Sm, Mop.map, k0, cu.m0, rg.clip, &rg.full[st]);
+        if (NK) tma_load4(Sn, Nop.map, 0, k0, cu.n0 >> 4, rg.clip, &rg.full[st]);
+        else tma_load3(Sn, Nop.map, k0, cu.n0, rg.clip, &rg.full[st]);
     }
     __syncwarp();
 }
@@ -255,9 +271,14 @@ __device__ __forceinline__ void cta_gemm(Ring& rg, const Operand Mop, const Oper
     tl.total = ((M + AL_TM - 1) / AL_TM) * tl.tn * tl.nk;
     fence_proxy_async();
     __syncthreads();
-    if (warp == 0) {
+    ChunkCursor cu;   // the next chunk to issue (uniform across the CTA)
+    cu.reset();
+    {
         const int pre = min(AL_NS, tl.total);
-        for (int c = 0; c < pre; c++) ring_issue<MK, NK>(rg, Mop, Nop, tl, c);
+        for (int c = 0; c < pre; c++) {
+            if (warp == 0) ring_issue<MK, NK>(rg, Mop, Nop, cu);
+            cu.next(tl);
+        }
     }
     FragLane fl;
     fl.kq = (lane & 1) + 4 * ((lane >> 1) & 1);
@@ -313,7 +334,10 @@ __device__ __forceinline__ void cta_gemm(Ring& rg, const Operand Mop, const Oper
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&rg.empty[st]);
                 AL_EMU_SYNC();
-                if (warp == (c & (AL_WARPS - 1)) && c + AL_NS < tl.total) ring_issue<MK, NK>(rg, Mop, Nop, tl, c + AL_NS);
+                if (cu.c < tl.total) {
+                    if (warp == (c & (AL_WARPS - 1))) ring_issue<MK, NK>(rg, Mop, Nop, cu);
+                    cu.next(tl);
+                }
             }
 #pragma unroll
             for (int s = 0; s < 12; s++) {
@@ -603,18 +627,18 @@ struct PhaseClock {
 // X; Z itself is never stored: the rare mu change recomputes it from X and the previous Y, bit for bit). As an epilogue of the product the same
 // update was bound by the few loads a thread can keep in flight next to its 48 accumulator registers.
 constexpr int AL_PASS_NS = 4;    // strips in flight
-constexpr int AL_PASS_U = 1;     // pairs per thread per round
+constexpr int AL_PASS_U = 1;     // pairs per thread per round (2 measured slower: a round then spans half the ring)
 struct AdmmPass {
     mbar_t* bar;        // [AL_PASS_NS] bytes landed in a stage
     unsigned* cnt;      // [AL_PASS_NS] warps that have left a stage (running count)
     unsigned use;       // strips consumed so far (all passes of this CTA): stage and parity of the next one
-    int rs, ns;         // rows per strip, stages (fixed per launch: functions of ldn)
+    int rs, lns;        // rows per strip, log2(stages) (fixed per launch: functions of ldn)
 };
 
 __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const double* Xn, const double* Xo, const double* Yo, double* Yn,
                                           const double* W, double* Xt, const int* grp, int n, int ldn, double mu, double inv_mu,
                                           double beta, double& pacc, double& dacc, PhaseClock& pc) {
-    const int rs = ps.rs, ns = ps.ns;
+    const int rs = ps.rs, lns = ps.lns, ns = 1 << lns;   // the stage count is a power of two: no division in the loop
     const int stage_doubles = 4 * rs * ldn;
     const int total = (n + rs - 1) / rs;          // strips
     const int hpn = (n + 1) >> 1;                 // live column pairs of a row
@@ -627,7 +651,7 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
     // "logical" row q is row n-1-q; strip s = logical rows [s rs, (s+1) rs) = one contiguous block of rows.
     auto issue = [&](int s) {
         const unsigned g = ps.use + (unsigned)s;
-        const int st = g % ns;
+        const int st = g & (ns - 1);
         const int hi = min(n, (s + 1) * rs), nr = hi - s * rs, r0 = n - hi;
         const unsigned bytes = (unsigned)(nr * ldn) * 8u;
         double* dst = ring + st * stage_doubles;
@@ -646,30 +670,32 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
         const int pre = min(ns, total);
         for (int s = 0; s < pre; s++) issue(s);
     }
-    // The pairs of the pass are one flat index space walked 256 at a time, independent of the strip boundaries (a strip
-    // of two 262-column rows is 262 pairs: strip-synchronous rounds would run half empty). A round waits for the strips
-    // it touches, and the strips it completes are refilled after one barrier. All indices advance incrementally - the
-    // pass is issue bound, an integer division per pair would cost as much as its arithmetic.
-    int waited = 0, done = 0;   // strips whose data this thread has waited for / that are fully consumed (uniform)
-    // A thread handles AL_PASS_U pairs per round, AL_THREADS apart, as independent instruction streams: the FP64 pipe is
-    // shared with the other CTA's DMMAs, so a single dependent chain of ~25 FP64 operations crawls.
-    int q = 0, c = (int)threadIdx.x;            // this thread's first pair: logical row q, pair c of the row
-    int sq = 0, stq = (int)(ps.use % (unsigned)ns);   // strip of row q and its stage
+    // The pairs of the pass are one flat index space walked AL_PASS_U x 256 at a time, independent of the strip boundaries
+    // (a strip of two 262-column rows is 262 pairs: strip-synchronous rounds would run half empty). A round waits for the
+    // strips it touches; the last warp out of a strip refills its stage (no block barrier: the warps drift apart by up to
+    // the depth of the ring). Every index advances incrementally and every per-round quantity is a compare or an add: the
+    // loop skeleton (integer divisions by run-time values, in an earlier version) cost more than the arithmetic.
+    int waited = 0, wait_at = 0;        // strips waited for; first pair of strip `waited`
+    int done = 0, done_at = min(P, spp);   // strips this warp has left; end (pair index) of strip `done`
+    int q = 0, c = (int)threadIdx.x;    // this thread's first pair of the round: logical row q, pair c of the row
+    int sq = 0, stq = (int)(ps.use & (unsigned)(ns - 1)), sq_end = rs;   // strip of row q, its stage, its first row beyond
     while (c >= hpn) {
         c -= hpn;
         q++;
     }
     for (int e0 = 0; e0 < P;) {
         const int e1 = min(min(P, e0 + AL_PASS_U * AL_THREADS), (done + ns) * spp);   // never past the strips in flight
-        while (waited < total && waited * spp < e1) {
+        while (waited < total && wait_at < e1) {
             const unsigned g = ps.use + (unsigned)waited;
-            mbar_wait(&ps.bar[g % ns], (g / ns) & 1);
+            mbar_wait(&ps.bar[g & (ns - 1)], (g >> lns) & 1);
             waited++;
+            wait_at += spp;
         }
         AL_EMU_SYNC();
-        while (q >= (sq + 1) * rs) {
+        while (q >= sq_end) {
             sq++;
-            stq = stq + 1 == ns ? 0 : stq + 1;
+            sq_end += rs;
+            stq = (stq + 1) & (ns - 1);
         }
         bool on[AL_PASS_U];
         int pi[AL_PASS_U], pj[AL_PASS_U];
@@ -677,13 +703,13 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
         int gi[AL_PASS_U];
         int2 gj[AL_PASS_U];
         {
-            int uq = q, uc = c, usq = sq, ust = stq;
+            int uq = q, uc = c, usq_end = sq_end, ust = stq;
 #pragma unroll
             for (int u = 0; u < AL_PASS_U; u++) {
                 on[u] = e0 + u * AL_THREADS + (int)threadIdx.x < e1;
                 if (on[u]) {
                     const int j = 2 * uc, i = n - 1 - uq;
-                    const int hi = min(n, (usq + 1) * rs);
+                    const int hi = min(n, usq_end);
                     const double* sx = ring + ust * stage_doubles + (i - (n - hi)) * ldn + j;
                     x[u] = *reinterpret_cast<const double2*>(sx);
                     x0[u] = *reinterpret_cast<const double2*>(sx + rs * ldn);
@@ -694,15 +720,16 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
                     pi[u] = i;
                     pj[u] = j;
                 }
-                // the next pair of this thread is AL_THREADS further on
-                uc += AL_THREADS;
-                while (uc >= hpn) {
-                    uc -= hpn;
-                    uq++;
-                }
-                while (uq >= (usq + 1) * rs) {
-                    usq++;
-                    ust = ust + 1 == ns ? 0 : ust + 1;
+                if (u + 1 < AL_PASS_U) {   // the next pair of this thread is AL_THREADS further on
+                    uc += AL_THREADS;
+                    while (uc >= hpn) {
+                        uc -= hpn;
+                        uq++;
+                    }
+                    while (uq >= usq_end) {
+                        usq_end += rs;
+                        ust = (ust + 1) & (ns - 1);
+                    }
                 }
             }
         }
@@ -739,12 +766,8 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
                 }
             }
             const size_t o = (size_t)i * ldn + j;
-#ifndef AL_EXP_NOSTORE
             *reinterpret_cast<double2*>(Yn + o) = yn;
             *reinterpret_cast<double2*>(Xt + o) = xt;
-#else
-            pacc += yn.x * 1e-30 + yn.y * 1e-30 + xt.x * 1e-30 + xt.y * 1e-30 + (double)o * 1e-300;
-#endif
         }
         // every thread moves on by the size of the round
         c += e1 - e0;
@@ -752,16 +775,16 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
             c -= hpn;
             q++;
         }
-        // strips this warp has finished with: the last of the 8 warps out of a strip refills its stage (no block barrier:
-        // the warps drift apart by up to the depth of the ring, and no single thread's copy issue is on everyone's path)
+        // strips this warp has finished with: the last of the 8 warps out of a strip refills its stage
         __syncwarp();
-        while (done < total && min(P, (done + 1) * spp) <= e1) {
+        while (done < total && done_at <= e1) {
             if ((threadIdx.x & 31) == 0) {
                 __threadfence_block();
-                const unsigned was = atomicAdd(&ps.cnt[(ps.use + (unsigned)done) % ns], 1u);
+                const unsigned was = atomicAdd(&ps.cnt[(ps.use + (unsigned)done) & (unsigned)(ns - 1)], 1u);
                 if ((was & (AL_WARPS - 1)) == AL_WARPS - 1 && done + ns < total) issue(done + ns);
             }
             done++;
+            done_at = min(P, done_at + spp);
         }
         AL_EMU_SYNC();
         e0 = e1;
@@ -806,7 +829,7 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
     {
         const int ring_doubles = AL_NS * AL_STAGE, ldn_ = (N + AL_PAD - 1) / AL_PAD * AL_PAD;
         ps.rs = max(1, ring_doubles / (AL_PASS_NS * 4 * ldn_));
-        ps.ns = max(1, min(AL_PASS_NS, ring_doubles / (4 * ps.rs * ldn_)));
+        ps.lns = ring_doubles / (4 * ps.rs * ldn_) >= 4 ? 2 : 1;   // 4 stages, or 2 when a row is longer than 640
     }
     ps.cnt = reinterpret_cast<unsigned*>(ps.bar + AL_PASS_NS);    // [AL_PASS_NS]
     int* s_grp = reinterpret_cast<int*>(ps.cnt + AL_PASS_NS + (AL_PASS_NS & 1));   // [N + 1], 8-byte aligned

@@ -7,11 +7,15 @@ SRC="$ROOT/multiview_motion_capture_b200/csrc"
 OUT="$HERE/libmvmc_emu.so"
 FLAGS="-O1 -g -fPIC -std=c++17 -DMVMC_EMU -ffp-contract=off -I$ROOT/include -I$HERE -I$SRC -Wno-unused-variable"
 objs=""
+pids=""
 for f in affinity als assign ik pipeline; do
+  rm -f "$HERE/$f.emu.o"
   g++ $FLAGS -x c++ -c "$SRC/$f.cu" -o "$HERE/$f.emu.o" &
+  pids="$pids $!"
   objs="$objs $HERE/$f.emu.o"
 done
 g++ $FLAGS -c "$HERE/emu_main.cpp" -o "$HERE/emu_main.emu.o" &
-wait
+pids="$pids $!"
+for p in $pids; do wait $p; done   # (a bare `wait` would swallow a failed compile and relink the stale object)
 g++ -shared -o "$OUT" $objs "$HERE/emu_main.emu.o"
 echo "built $OUT"

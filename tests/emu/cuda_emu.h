@@ -24,6 +24,7 @@ struct dim3 {
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct alignas(16) double2 { double x, y; };
+struct alignas(8) int2 { int x, y; };
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 typedef int cudaError_t;
@@ -47,7 +48,8 @@ namespace emu {
 struct Fiber {
     ucontext_t ctx;
     char* stack = nullptr;
-    int state = 0;  // 0 runnable, 1 wait-block, 2 wait-warp, 3 done
+    int state = 0;  // 0 runnable, 1 wait-block, 2 wait-warp, 3 done, 4 wait-named-barrier
+    int bar = 0;    // named barrier waited on (state 4)
     uint3_ tid;
     int linear = 0;
 };
@@ -61,6 +63,7 @@ struct BlockCtx {
     std::function<void()> body;
     uint64_t warp_slot[64][32];
     uint64_t warp_slot2[64][32];
+    int bar_expect[16];   // threads a named barrier releases at
 };
 
 extern BlockCtx* g_blk;
@@ -72,6 +75,13 @@ inline Fiber& me() { return g_blk->fibers[g_blk->cur]; }
 inline void yield_to_sched() { Fiber& f = me(); swapcontext(&f.ctx, &g_blk->sched); }
 
 inline void block_sync() { me().state = 1; yield_to_sched(); }
+// bar.sync id, nthreads: released when `nthreads` fibers wait on barrier `id`
+inline void named_sync(int id, int nthreads) {
+    g_blk->bar_expect[id] = nthreads;
+    me().bar = id;
+    me().state = 4;
+    yield_to_sched();
+}
 inline void warp_sync() { me().state = 2; yield_to_sched(); }
 
 void fiber_entry();
@@ -263,6 +273,16 @@ void run_block(BlockCtx& b) {
             if (alive > 0 && waiting == alive) {
                 for (int l = 0; l < 32 && w * 32 + l < n; l++)
                     if (b.fibers[w * 32 + l].state == 2) b.fibers[w * 32 + l].state = 0;
+                released = true;
+            }
+        }
+        for (int id = 0; id < 16; id++) {
+            int w4 = 0;
+            for (int i = 0; i < n; i++)
+                if (b.fibers[i].state == 4 && b.fibers[i].bar == id) w4++;
+            if (w4 > 0 && w4 >= b.bar_expect[id]) {
+                for (int i = 0; i < n; i++)
+                    if (b.fibers[i].state == 4 && b.fibers[i].bar == id) b.fibers[i].state = 0;
                 released = true;
             }
         }
