@@ -626,7 +626,10 @@ struct PhaseClock {
 // registers - and writes the new Y and the next Xt with coalesced 16-byte stores (Y alternates between two buffers like
 // X; Z itself is never stored: the rare mu change recomputes it from X and the previous Y, bit for bit). As an epilogue of the product the same
 // update was bound by the few loads a thread can keep in flight next to its 48 accumulator registers.
-constexpr int AL_PASS_NS = 4;    // strips in flight
+#ifndef AL_PASS_NS_
+#define AL_PASS_NS_ 4
+#endif
+constexpr int AL_PASS_NS = AL_PASS_NS_;    // strips in flight (power of two)
 constexpr int AL_PASS_U = 1;     // pairs per thread per round (2 measured slower: a round then spans half the ring)
 struct AdmmPass {
     mbar_t* bar;        // [AL_PASS_NS] bytes landed in a stage
@@ -656,15 +659,11 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
         const unsigned bytes = (unsigned)(nr * ldn) * 8u;
         double* dst = ring + st * stage_doubles;
         const size_t o = (size_t)r0 * ldn;
-#ifndef AL_EXP_NOLOAD
         mbar_expect_tx(&ps.bar[st], 4u * bytes);
         bulk_g2s(dst, Xn + o, bytes, &ps.bar[st]);
         bulk_g2s(dst + rs * ldn, Xo + o, bytes, &ps.bar[st]);
         bulk_g2s(dst + 2 * rs * ldn, Yo + o, bytes, &ps.bar[st]);
         bulk_g2s(dst + 3 * rs * ldn, W + o, bytes, &ps.bar[st]);
-#else
-        mbar_arrive(&ps.bar[st]);
-#endif
     };
     if (threadIdx.x == 0) {
         const int pre = min(ns, total);
@@ -829,7 +828,8 @@ __global__ void __launch_bounds__(AL_THREADS, 2)
     {
         const int ring_doubles = AL_NS * AL_STAGE, ldn_ = (N + AL_PAD - 1) / AL_PAD * AL_PAD;
         ps.rs = max(1, ring_doubles / (AL_PASS_NS * 4 * ldn_));
-        ps.lns = ring_doubles / (4 * ps.rs * ldn_) >= 4 ? 2 : 1;   // 4 stages, or 2 when a row is longer than 640
+        const int fit = min(AL_PASS_NS, ring_doubles / (4 * ps.rs * ldn_));   // stages that fit: rounded down to a power of two
+        ps.lns = fit >= 8 ? 3 : (fit >= 4 ? 2 : 1);
     }
     ps.cnt = reinterpret_cast<unsigned*>(ps.bar + AL_PASS_NS);    // [AL_PASS_NS]
     int* s_grp = reinterpret_cast<int*>(ps.cnt + AL_PASS_NS + (AL_PASS_NS & 1));   // [N + 1], 8-byte aligned
