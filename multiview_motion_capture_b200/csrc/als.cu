@@ -191,25 +191,73 @@ struct Ring {
 // The four DMMA steps of a 16-chunk take the k-sets {0,1,4,5}, {2,3,6,7}, {8,9,12,13}, {10,11,14,15} (lane%4 -> the
 // set's element): any partition works as long as both operands use it, and with this one the 32 lanes of a fragment load
 // hit every 8-byte bank pair exactly twice in BOTH swizzled layouts (the minimum for 256 bytes).
-struct FragLane {
-    int kq;       // (q & 1) + 4 (q >> 1), q = lane % 4: this lane's k inside the step's set
-    int p;        // lane / 4: this lane's i inside a fragment
+//
+// Fragment loads are `ld.shared.f64 [register + immediate]`: everything that depends on the lane is folded into a handful
+// of per-thread byte offsets (FragTab), re-based once per chunk on the stage's shared-memory address; the fragment index
+// and the step only contribute compile-time immediates. (Indexing the stage through a generic pointer cost an IMAD, an
+// IMAD.WIDE and a generic LD per fragment, issued right in front of the DMMA that needs it.)
+//
+// With q = lane % 4, p = lane / 4, kq = (q & 1) + 4 (q >> 1), step s, kb = 8 (s >> 1) + 2 (s & 1), k = kb + kq (disjoint bits):
+//   k-major stage [TI/16][16 k][16 i] (bytes): element (k, i), i = I0 + p, I0 a multiple of 8, h = (I0 >> 3) & 1:
+//       (I0 >> 4) 2048 + kb 128 + KT[h][s & 1],   KT[h][par] = kq 128 + (p & 1) 8 + ((((4 h + (p >> 1)) ^ kq) << 4) ^ (par << 5))
+//   i-major stage [TI][16 k] (bytes):
+//       I0 128 + IT[s],                            IT[s] = p 128 + (kq & 1) 8 + ((((kq >> 1) ^ p) ^ (kb >> 1)) << 4)
+#ifdef MVMC_EMU
+typedef const unsigned char* saddr_t;
+__device__ __forceinline__ saddr_t saddr_of(const double* p) { return reinterpret_cast<saddr_t>(p); }
+__device__ __forceinline__ double lds64(saddr_t a) { return *reinterpret_cast<const double*>(a); }
+#else
+typedef unsigned saddr_t;
+__device__ __forceinline__ saddr_t saddr_of(const double* p) { return smem_u32(p); }
+__device__ __forceinline__ double lds64(saddr_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+#endif
+struct FragTab {
+    int kt[2][2];   // k-major lane offsets by (h, step parity)
+    int it[4];      // i-major lane offsets by step
+    __device__ __forceinline__ void init(int lane) {
+        const int q = lane & 3, p = lane >> 2, kq = (q & 1) + 4 * (q >> 1);
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int par = 0; par < 2; par++)
+                kt[h][par] = kq * 128 + (p & 1) * 8 + ((((4 * h + (p >> 1)) ^ kq) << 4) ^ (par << 5));
+#pragma unroll
+        for (int s4 = 0; s4 < 4; s4++) {
+            const int kb = 8 * (s4 >> 1) + 2 * (s4 & 1);
+            it[s4] = p * 128 + (kq & 1) * 8 + ((((kq >> 1) ^ p) ^ (kb >> 1)) << 4);
+        }
+    }
 };
-// k-major stage [TI/16][16][16]: element (k, i) at (i>>4)*256 + k*16 + ((((i&15)>>1) ^ (k&7)) << 1) + (i&1)
-// i-major stage [TI][16]:        element (k, i) at i*16 + (((k>>1) ^ (i&7)) << 1) + (k&1)
-template <bool kmajor>
-__device__ __forceinline__ int frag_base(const FragLane& fl, int i8) {
-    const int i = i8 + fl.p;
-    if (kmajor) return (i >> 4) * 256 + fl.kq * 16 + (((((i & 15) >> 1) ^ fl.kq)) << 1) + (i & 1);
-    return i * 16 + ((((fl.kq >> 1) ^ fl.p)) << 1) + (fl.kq & 1);
-}
-// offset of step s relative to frag_base: k = kb + kq with kb = 8 (s >> 1) + 2 (s & 1); the bits of kb and kq are disjoint
-template <bool kmajor>
-__device__ __forceinline__ double frag_ld(const double* S, int base, int s) {
-    const int kb = 8 * (s >> 1) + 2 * (s & 1);
-    if (kmajor) return S[(base ^ ((kb & 7) << 1)) + kb * 16];     // unit ^= kb % 8, row += kb
-    return S[base ^ ((kb >> 1) << 1)];                            // unit ^= kb / 2
-}
+// An operand's fragment addressing for one warp: `nreg` lane/warp dependent byte offsets (re-based per chunk) and, per
+// (fragment f, step s), which of them to use plus a compile-time immediate. I0 of fragment f = w0 + 8 f.
+template <bool kmajor, int NF>
+struct FragAddr {
+    // k-major: reg[f][par] (the 16-column block and the half h of fragment f are folded in: they depend on the warp for
+    // the N operand); i-major: reg[0][s] shared by all fragments, fragment f adds the immediate f * 1024.
+    int reg[kmajor ? NF : 1][kmajor ? 2 : 4];
+    __device__ __forceinline__ void init(const FragTab& t, int w0 /*first column of the warp inside the tile*/) {
+        if (kmajor) {
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                const int I0 = w0 + 8 * f;
+#pragma unroll
+                for (int par = 0; par < 2; par++) reg[f][par] = (I0 >> 4) * 2048 + (((I0 >> 3) & 1) ? t.kt[1][par] : t.kt[0][par]);
+            }
+        } else {
+#pragma unroll
+            for (int s4 = 0; s4 < 4; s4++) reg[0][s4] = w0 * 128 + t.it[s4];
+        }
+    }
+    // shared-memory address of fragment f, step s4, in the stage operand region starting at `base`
+    __device__ __forceinline__ saddr_t at(saddr_t base, int f, int s4) const {
+        if (kmajor) return base + reg[f][s4 & 1] + (8 * (s4 >> 1) + 2 * (s4 & 1)) * 128;
+        return base + reg[0][s4] + f * 1024;
+    }
+};
 
 // Shape of one product as the ring sees it, and a cursor over its chunks (tile-major, N tiles inside M tiles, k-chunks
 // inside a tile) that every thread advances in step with the chunk loop: the position of the chunk to issue next costs
@@ -280,14 +328,13 @@ __device__ __forceinline__ void cta_gemm(Ring& rg, const Operand Mop, const Oper
             cu.next(tl);
         }
     }
-    FragLane fl;
-    fl.kq = (lane & 1) + 4 * ((lane >> 1) & 1);
-    fl.p = lane >> 2;
-    int fa[4], fb[3];   // fragment bases of this thread inside a stage (the same for every tile)
-#pragma unroll
-    for (int a = 0; a < 4; a++) fa[a] = frag_base<MK>(fl, 32 * wm + 8 * a);
-#pragma unroll
-    for (int b = 0; b < 3; b++) fb[b] = frag_base<NK>(fl, 24 * wn + 8 * b);
+    FragTab ftab;
+    ftab.init(lane);
+    FragAddr<MK, 4> fm;   // M operand: rows 32 wm + 8 a
+    FragAddr<NK, 3> fn;   // N operand: columns 24 wn + 8 b
+    fm.init(ftab, 32 * wm);
+    fn.init(ftab, 24 * wn);
+    const saddr_t ring0 = saddr_of(rg.stages);
     int c = 0;
     for (int m0 = 0; m0 < M; m0 += AL_TM) {
         const int mw0 = m0 + 32 * wm;
@@ -313,22 +360,28 @@ __device__ __forceinline__ void cta_gemm(Ring& rg, const Operand Mop, const Oper
                 mbar_wait(&rg.full[st], (g / AL_NS) & 1);
                 AL_EMU_SYNC();
                 if (nt > 0) {
-                    const double* Sm = rg.stages + st * AL_STAGE;
-                    const double* Sn = Sm + AL_STAGE_M;
+                    // every fragment of the warp tile, live or not (dead ones multiply zero padding or stale finite data into
+                    // accumulators that are never stored): no branch and no predicate inside the DMMA sequence. The loads of
+                    // step s+1 are issued before the DMMAs of step s.
+                    const saddr_t Sm = ring0 + st * (AL_STAGE * 8);
+                    const saddr_t Sn = Sm + AL_STAGE_M * 8;
+                    double af[2][4], bf[2][3];
+#pragma unroll
+                    for (int b = 0; b < 3; b++) bf[0][b] = lds64(fn.at(Sn, b, 0));
+#pragma unroll
+                    for (int a = 0; a < 4; a++) af[0][a] = lds64(fm.at(Sm, a, 0));
 #pragma unroll
                     for (int s = 0; s < 4; s++) {
-                        double bf[3];
+                        if (s + 1 < 4) {
 #pragma unroll
-                        for (int b = 0; b < 3; b++) bf[b] = b < nt ? frag_ld<NK>(Sn, fb[b], s) : 0.0;
+                            for (int b = 0; b < 3; b++) bf[(s + 1) & 1][b] = lds64(fn.at(Sn, b, s + 1));
 #pragma unroll
-                        for (int a = 0; a < 4; a++) {
-                            if (a < mt) {
-                                const double av = frag_ld<MK>(Sm, fa[a], s);
-#pragma unroll
-                                for (int b = 0; b < 3; b++)
-                                    if (b < nt) dmma(acc[a][b][0], acc[a][b][1], av, bf[b]);
-                            }
+                            for (int a = 0; a < 4; a++) af[(s + 1) & 1][a] = lds64(fm.at(Sm, a, s + 1));
                         }
+#pragma unroll
+                        for (int a = 0; a < 4; a++)
+#pragma unroll
+                            for (int b = 0; b < 3; b++) dmma(acc[a][b][0], acc[a][b][1], af[s & 1][a], bf[s & 1][b]);
                     }
                 }
                 __syncwarp();
