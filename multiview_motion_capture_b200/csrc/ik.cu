@@ -194,7 +194,7 @@ __device__ __forceinline__ void project3(const double* Pv, double X, double Y, d
 }
 
 // ---- reprojection residual of the BASIC_18 pose (inverse_kinematics.py:202-277) ----
-// rows: (view v, observed joint q, {u, v}) -> (v*16 + q)*2 + {0,1};  a chunk = 8 joints of one view (16 rows)
+// rows: (view v, observed joint q, {u, v}) -> (v*16 + q)*2 + {0,1};  a chunk = 4 joints of one view (8 rows)
 struct IkRes {
     const double* obs;   // [V][16][3] gathered at c_ik_obs_idx (shared)
     const double* P;     // [V][12] (shared)
@@ -202,9 +202,9 @@ struct IkRes {
     double* Rloc;        // [18][9] local rotations of the pose being differentiated / evaluated (shared)
     int V;
     __device__ int m() const { return V * MVMC_N_IKJ * 2; }
-    __device__ int n_chunks() const { return 2 * V; }
-    __device__ int chunk_rows(int) const { return 16; }
-    __device__ int chunk_row0(int c) const { return 16 * c; }
+    __device__ int n_chunks() const { return 4 * V; }
+    __device__ int chunk_rows(int) const { return 8; }
+    __device__ int chunk_row0(int c) const { return 8 * c; }
 
     __device__ __noinline__ void eval(const double* x, double* f) {
         const int lane = threadIdx.x & 31;
@@ -241,7 +241,7 @@ struct IkRes {
     }
     __device__ __noinline__ void fd_chunk(TrfWarp& s, int ncol, int ch, const double* f) {
         const int lane = threadIdx.x & 31;
-        const int v = ch >> 1, q0 = (ch & 1) * 8;
+        const int v = ch >> 2, q0 = (ch & 3) * 4;
         const double* S = s.A;
         double Pv[12];
 #pragma unroll
@@ -249,7 +249,7 @@ struct IkRes {
         for (int c = lane; c < ncol; c += 32) {
             const double rdx = 1.0 / s.dx[c];
 #pragma unroll
-            for (int qq = 0; qq < 8; qq++) {
+            for (int qq = 0; qq < 4; qq++) {
                 const int q = q0 + qq;
                 const double* o = obs + (v * MVMC_N_IKJ + q) * 3;
                 double pu, pv, pw;
@@ -266,16 +266,17 @@ struct IkRes {
 };
 
 // ---- triangulation refine residual (mv_math_util.py:190-202): rows (view v, point k) -> v*K + k ----
-// a chunk = half of the points of one view
+// a chunk = a third of the points of one view (K <= 18: at most 6 rows)
 struct TriRes {
     const double* obs;  // [V][K][3] (shared)
     const double* P;    // [V][12]
     int V, K;
-    __device__ int half() const { return (K + 1) / 2; }
+    __device__ int third() const { return (K + 2) / 3; }
+    __device__ int part0(int t) const { return min(K, t * third()); }           // first point of part t (t = 0..3)
     __device__ int m() const { return V * K; }
-    __device__ int n_chunks() const { return 2 * V; }
-    __device__ int chunk_rows(int c) const { return (c & 1) ? K - half() : half(); }
-    __device__ int chunk_row0(int c) const { return (c >> 1) * K + (c & 1) * half(); }
+    __device__ int n_chunks() const { return 3 * V; }
+    __device__ int chunk_rows(int c) const { return part0(c % 3 + 1) - part0(c % 3); }
+    __device__ int chunk_row0(int c) const { return (c / 3) * K + part0(c % 3); }
     __device__ double one(const double* Pv, const double* o, double X, double Y, double Z) const {
         double pu, pv, pw;
         project3(Pv, X, Y, Z, pu, pv, pw);
@@ -294,10 +295,10 @@ struct TriRes {
     __device__ void fd_prepare(TrfWarp&, int) {}
     __device__ void fd_chunk(TrfWarp& s, int ncol, int ch, const double* f) {
         const int lane = threadIdx.x & 31;
-        const int v = ch >> 1, k0 = (ch & 1) * half(), k1 = k0 + chunk_rows(ch);
+        const int v = ch / 3, k0 = part0(ch % 3), k1 = k0 + chunk_rows(ch);
         for (int c = lane; c < ncol; c += 32) {
             const int prm = s.act[c], k = prm / 3, comp = prm % 3;
-            for (int r = 0; r < k1 - k0; r++) s.Jc[r * WS_LDJ + c] = 0.0;   // (the other half-view's entry is stale)
+            for (int r = 0; r < k1 - k0; r++) s.Jc[r * WS_LDJ + c] = 0.0;   // (the other parts' entries are stale)
             if (k < k0 || k >= k1) continue;   // a point only moves its own residual rows
             double X[3] = {s.x[3 * k], s.x[3 * k + 1], s.x[3 * k + 2]};
             X[comp] = s.w[c];
@@ -396,17 +397,24 @@ __device__ __forceinline__ void mid_spine(const double* k, double* o) {
 }
 
 // ---- per-warp shared memory of the solver kernels ----
+// (the staging copy of the 18-point observations and the triangulated points exist only in the kernels that give birth)
+template <int VMAX, bool BIRTH>
+struct IkBirthSh {
+    double obs18[VMAX * 18 * 3];
+    double p3[18 * 4];
+};
 template <int VMAX>
-struct alignas(16) IkWarpSh {
+struct IkBirthSh<VMAX, false> {};
+template <int VMAX, bool BIRTH = true>
+struct alignas(16) IkWarpSh : IkBirthSh<VMAX, BIRTH> {
     TrfWarp t;
     double f[32 * VMAX], fn[32 * VMAX];
     double obs16[VMAX * MVMC_N_IKJ * 3];
-    double obs18[VMAX * 18 * 3];
     double P[VMAX * 12];
     double posb[MVMC_N_IKJ * 3];
     double Rloc[MVMC_N_B18 * 9];
-    double p3[18 * 4];
 };
+static_assert(5 * (sizeof(IkWarpSh<8, false>) + 1024) <= 228 * 1024, "five update-solver CTAs must fit the 228 KB of an SM");
 
 // Triangulate K (<= 18) joints from nv views (+ optional refine_nfev-evaluation TRF refine); result in sh.p3 [K][4].
 template <int VMAX>
@@ -463,8 +471,9 @@ __global__ void __launch_bounds__(32)
                const double* __restrict__ x0, const uint8_t* __restrict__ birth, const int* __restrict__ max_nfev,
                const uint8_t* __restrict__ free_mask, int n_items, int cnt, int S, int s0, int V, int* __restrict__ counter,
                double* __restrict__ x_out, double* __restrict__ joints, int* __restrict__ info, double* __restrict__ cost_out) {
-    MVMC_DYN_SMEM(IkWarpSh<VMAX>, shp);
-    IkWarpSh<VMAX>& sh = *shp;
+    typedef IkWarpSh<VMAX, WITH_BIRTH> Sh;
+    MVMC_DYN_SMEM(Sh, shp);
+    Sh& sh = *shp;
     const int lane = threadIdx.x & 31;
     for (;;) {
         int item = 0;
@@ -487,32 +496,59 @@ __global__ void __launch_bounds__(32)
         const int nfev_cap = max_nfev[mI];
         __syncwarp();
         // stage observations (+ mid spine) and projection matrices
-        for (int e = lane; e < nv * MVMC_N_COCO * 3; e += 32) {
-            const int v = e / (MVMC_N_COCO * 3), q = e % (MVMC_N_COCO * 3);
-            sh.obs18[v * 54 + q] = kps2d[((size_t)mI * V + v) * (MVMC_N_COCO * 3) + q];
-        }
         for (int e = lane; e < nv * 12; e += 32) sh.P[e] = Psel[(size_t)mI * V * 12 + e];
-        __syncwarp();
-        if (lane < nv) mid_spine(sh.obs18 + lane * 54, sh.obs18 + lane * 54 + 51);
-        __syncwarp();
-        for (int e = lane; e < nv * MVMC_N_IKJ * 3; e += 32) {
-            const int v = e / (MVMC_N_IKJ * 3), q = (e / 3) % MVMC_N_IKJ, c = e % 3;
-            sh.obs16[e] = sh.obs18[v * 54 + c_ik_obs_idx[q] * 3 + c];
+        if constexpr (WITH_BIRTH) {
+            for (int e = lane; e < nv * MVMC_N_COCO * 3; e += 32) {
+                const int v = e / (MVMC_N_COCO * 3), q = e % (MVMC_N_COCO * 3);
+                sh.obs18[v * 54 + q] = kps2d[((size_t)mI * V + v) * (MVMC_N_COCO * 3) + q];
+            }
+            __syncwarp();
+            if (lane < nv) mid_spine(sh.obs18 + lane * 54, sh.obs18 + lane * 54 + 51);
+            __syncwarp();
+            for (int e = lane; e < nv * MVMC_N_IKJ * 3; e += 32) {
+                const int v = e / (MVMC_N_IKJ * 3), q = (e / 3) % MVMC_N_IKJ, c = e % 3;
+                sh.obs16[e] = sh.obs18[v * 54 + c_ik_obs_idx[q] * 3 + c];
+            }
+        } else {
+            // straight from global memory into the 16-joint layout; the mid spine (index 17) with mid_spine()'s arithmetic
+            for (int e = lane; e < nv * MVMC_N_IKJ * 3; e += 32) {
+                const int v = e / (MVMC_N_IKJ * 3), q = (e / 3) % MVMC_N_IKJ, c = e % 3;
+                const double* k = kps2d + ((size_t)mI * V + v) * (MVMC_N_COCO * 3);
+                const int src = c_ik_obs_idx[q];
+                double val;
+                if (src < MVMC_N_COCO) {
+                    val = k[src * 3 + c];
+                } else {
+                    const double ls = k[3 * kCocoLShoulder + c], rs = k[3 * kCocoRShoulder + c], lh = k[3 * kCocoLHip + c],
+                                 rh = k[3 * kCocoRHip + c];
+                    if (c < 2) {
+                        val = 0.5 * (0.5 * (ls + rs) + 0.5 * (lh + rh));
+                    } else {
+                        double sc = ls * rs;
+                        sc *= lh * rh;
+                        val = sc;
+                    }
+                }
+                sh.obs16[e] = val;
+            }
         }
         __syncwarp();
         bool born = false;
-        if constexpr (WITH_BIRTH) born = is_birth;
-        if (born) {
-            // triangulate 18 joints (min score 0.01), refine with a 2-nfev TRF, inverse_kinematics.py:389-396
-            if constexpr (WITH_BIRTH) warp_triangulate(sh, sh.obs18, nv, 18, 0.01, 2);
-            if (lane == 0) {
-                double root[3];
-                for (int c = 0; c < 3; c++) root[c] = 0.5 * (sh.p3[kCocoLHip * 4 + c] + sh.p3[kCocoRHip * 4 + c]);
-                for (int c = 0; c < 3; c++) sh.t.x[c] = root[c];
-                for (int e = 3; e < 57; e++) sh.t.x[e] = 0.0;
-                for (int e = 0; e < 11; e++) sh.t.x[57 + e] = c_skel.ref_side_lens[e];
+        if constexpr (WITH_BIRTH) {
+            born = is_birth;
+            if (born) {
+                // triangulate 18 joints (min score 0.01), refine with a 2-nfev TRF, inverse_kinematics.py:389-396
+                warp_triangulate(sh, sh.obs18, nv, 18, 0.01, 2);
+                if (lane == 0) {
+                    double root[3];
+                    for (int c = 0; c < 3; c++) root[c] = 0.5 * (sh.p3[kCocoLHip * 4 + c] + sh.p3[kCocoRHip * 4 + c]);
+                    for (int c = 0; c < 3; c++) sh.t.x[c] = root[c];
+                    for (int e = 3; e < 57; e++) sh.t.x[e] = 0.0;
+                    for (int e = 0; e < 11; e++) sh.t.x[57 + e] = c_skel.ref_side_lens[e];
+                }
             }
-        } else {
+        }
+        if (!born) {
             for (int e = lane; e < MVMC_N_PARAM; e += 32) sh.t.x[e] = x0[(size_t)mI * MVMC_N_PARAM + e];
         }
         __syncwarp();
@@ -681,7 +717,7 @@ static int ensure_skeleton() {
 }
 
 // persistent grid: 148 SMs x 4 resident one-warp CTAs
-constexpr int IK_MAX_GRID = 148 * 4;
+constexpr int IK_MAX_GRID = 148 * 5;   // persistent one-warp CTAs: five update solvers per SM
 static int ik_grid(int M) { return M < IK_MAX_GRID ? M : IK_MAX_GRID; }
 
 extern "C" size_t mvmc_ik_workspace_bytes(int M, int V) {
@@ -699,8 +735,8 @@ int mvmc_ik_launch(const double* kps2d, const double* Psel, const int* n_views, 
     MVMC_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
     if (vmax <= 8 && birth == nullptr) {
         auto kern = k_ik_solve<8, false>;
-        MVMC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IkWarpSh<8>)));
-        MVMC_LAUNCH(kern, dim3(ik_grid(n_items)), dim3(32), sizeof(IkWarpSh<8>), stream, kps2d, Psel, n_views, x0, birth,
+        MVMC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IkWarpSh<8, false>)));
+        MVMC_LAUNCH(kern, dim3(ik_grid(n_items)), dim3(32), sizeof(IkWarpSh<8, false>), stream, kps2d, Psel, n_views, x0, birth,
                     max_nfev, free_mask, n_items, cnt, S, s0, V, counter, x_out, joints, info, cost);
     } else {
         auto kern = k_ik_solve<MVMC_MAX_SEL, true>;

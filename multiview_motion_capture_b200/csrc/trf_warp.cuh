@@ -23,7 +23,7 @@ constexpr int WS_NC = 56;    // live Jacobian columns per solve (multiple of 8; 
 constexpr int WS_NT = WS_NC / 8;
 constexpr int WS_LDA = 57;   // row stride of A (odd: conflict-free column walks with 64-bit accesses)
 constexpr int WS_LDJ = 58;   // row stride of the J chunk (16-byte aligned rows, odd multiple of 16 B: conflict-free LDS.128)
-constexpr int WS_CH = 16;    // rows of J per chunk
+constexpr int WS_CH = 8;     // rows of J per chunk (16 measured the same speed; 8 lets a fifth solver CTA fit on an SM)
 constexpr double kSqrtEps = 1.4901161193847656e-08;   // sqrt(2^-52)
 constexpr double kEps = 2.220446049250313e-16;
 constexpr double kDblMax = 1.79769313486231570e308;
@@ -68,7 +68,7 @@ __device__ __forceinline__ void lane_tile(int lane, int& ti, int& tj) {
 // ---- Jacobian, g = J^T f, A = J^T J, then A = Q T Q^T ---------------------------------------------------------------
 // Res interface (all members are called by the whole warp):
 //   int  m() const;                      residual rows
-//   int  n_chunks() const;               J is produced chunk by chunk (a chunk = half a camera view, <= WS_CH rows)
+//   int  n_chunks() const;               J is produced chunk by chunk (<= WS_CH rows each)
 //   int  chunk_rows(int c) const;        rows of chunk c;  row index of its first row = chunk_row0(c)
 //   void eval(const double* x, double* f);                 all residuals at x (x, f in shared memory)
 //   void fd_prepare(TrfWarp& s, int ncol);                 per column: perturb, evaluate the model, park the state in s.A
