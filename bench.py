@@ -335,7 +335,13 @@ def run_ours(args):
         "hbm": {"achieved": alg_bytes / (ms / K * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (ms / K * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                 "algorithmic_bytes_per_step": alg_bytes,
-                "note": "whole step; the path is FP64-compute bound (about 25 kFLOP per algorithmic byte), not HBM bound"},
+                "note": "whole step, ALGORITHMIC bytes (inputs + results): about 25 kFLOP per algorithmic byte, so the roofline "
+                        "that binds is the FP64 tensor pipe; the kernel's real DRAM traffic is in kernel_dram"},
+        "kernel_dram": None if traffic is None else {
+            "achieved": traffic["dram_bytes_per_clip_frame"] * B / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": traffic["dram_bytes_per_clip_frame"] * B / (dom_ms * 1e-3) / 1e9 / hbm_peak,
+            "note": "DRAM bytes of the dominant kernel per clip-frame from the committed ncu capture x clips of this run / its "
+                    "event-timed duration: the second bound of k_als (its n x n iterates stream through HBM every iteration)"},
         "stage_ms_per_step": {k: v / n_prof for k, v in stage_ms.items()},
         "ik": {"achieved": st["ik_flops"] / K / (ik_ms * 1e-3) / 1e12 if ik_ms > 0 else None, "peak": fp64_dfma_tflops,
                "unit": "TFLOP/s", "note": "k_ik_solve, SURVEY.md 8d flop formula on the run's own (nfev, njev) counts"},
