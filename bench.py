@@ -186,7 +186,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     from multiview_motion_capture_b200 import _lib
-    from multiview_motion_capture_b200.clips import ClipBatch
+    from multiview_motion_capture_b200.clips import ClipBatch, ClipStreams
     from multiview_motion_capture_b200._lib import STEP_OUT_DTYPE, check, ptr
     lib = _lib.get_lib()
 
@@ -195,8 +195,10 @@ def run_ours(args):
     t_gen = time.time()
     kps, n_pose, Kc, RT, _ = make_inputs(B, n_frames, seed=1000 + 7919 * rank, distinct=args.distinct)
     t_gen = time.time() - t_gen
-    cb = ClipBatch(B, N_VIEWS, N_PEOPLE, max_tracks=args.max_tracks, max_new=N_PEOPLE, device=dev)
-    cb.set_calib(Kc, RT)
+    # the batch runs as `groups` groups of clips on their own streams (ClipStreams): one group's IK / affinity / copies fill
+    # the SMs another group's ALS launch leaves idle while it drains
+    cs = ClipStreams(B, N_VIEWS, N_PEOPLE, groups=args.groups, max_tracks=args.max_tracks, max_new=N_PEOPLE, device=dev)
+    cs.set_calib(Kc, RT)
     kps_pin = torch.from_numpy(kps).pin_memory()
     np_pin = torch.from_numpy(n_pose).pin_memory()
     kps_dev = kps_pin.to(dev, non_blocking=True)
@@ -210,19 +212,20 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     # ---------------- device-resident timing ----------------
+    cs.fork()
     for s in range(W):
-        cb.step_device(kps_dev[1 + s], np_dev[1 + s], 1 + s)
-    cb.stats(reset=True)
-    cb.profile(1)
-    if args.als_phases:
-        check(lib.mvmc_als_phase_profile(1, None), "mvmc_als_phase_profile")
+        cs.step_device(kps_dev[1 + s], np_dev[1 + s], 1 + s)
+    cs.join()
+    cs.stats(reset=True)
     launches0 = lib.mvmc_launch_count()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
+    cs.fork()
     for s in range(K):
-        cb.step_device(kps_dev[1 + W + s], np_dev[1 + W + s], 1 + W + s)
+        cs.step_device(kps_dev[1 + W + s], np_dev[1 + W + s], 1 + W + s)
+    cs.join()
     summary = None
     if world > 1:
         # the only collective of the path: gather per-rank result summaries (north_star: NCCL only to gather)
@@ -239,6 +242,24 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = lib.mvmc_launch_count() - launches0
+    st_run = cs.stats(reset=True)
+    value = world * B * K / (ms * 1e-3)
+
+    # ---------------- the kernels timed alone (roofline): ONE launch of all B clips per stage, nothing overlapped ----------------
+    # (in the throughput run above kernels of different groups share the SMs, so per-kernel event times there say nothing
+    #  about a kernel; this is the same kernel on the same clips, two steps after the same warm-up)
+    cb = ClipBatch(B, N_VIEWS, N_PEOPLE, max_tracks=args.max_tracks, max_new=N_PEOPLE, device=dev)
+    cb.set_calib(Kc, RT)
+    for s in range(W):
+        cb.step_device(kps_dev[1 + s], np_dev[1 + s], 1 + s)
+    cb.stats(reset=True)
+    cb.profile(1)
+    if args.als_phases:
+        check(lib.mvmc_als_phase_profile(1, None), "mvmc_als_phase_profile")
+    KP = min(K, 2)
+    for s in range(KP):
+        cb.step_device(kps_dev[1 + W + s], np_dev[1 + W + s], 1 + W + s)
+    torch.cuda.synchronize(dev)
     if args.als_phases and rank == 0:
         ph = np.zeros(15)
         check(lib.mvmc_als_phase_profile(0, ptr(ph)), "mvmc_als_phase_profile")
@@ -247,7 +268,9 @@ def run_ours(args):
               file=sys.stderr, flush=True)
     stage_ms, n_prof = cb.profile(0)
     st = cb.stats(reset=True)
-    value = world * B * K / (ms * 1e-3)
+    single_bytes = cb.device_bytes
+    cb.close()
+    del cb
 
     # ---------------- FP64 peak probes (CUDA-core DFMA and tensor-core DMMA), timed in this run ----------------
     sink = torch.zeros(8, dtype=torch.float64, device=dev)
@@ -269,12 +292,11 @@ def run_ours(args):
     # ---------------- end-to-end through the host-buffer C-ABI call ----------------
     e2e = None
     if not args.no_e2e:
-        cb.reset()
+        cs.reset()
         out_pin = torch.empty(B * STEP_OUT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
 
-        def host_step(fi):
-            check(lib.mvmc_clips_step_host(cb._h, ptr(kps_pin[fi]), ptr(np_pin[fi]), fi, ptr(out_pin), stream.cuda_stream),
-                  "mvmc_clips_step_host")
+        def host_step(fi):   # every group: H2D of its slice, the step, D2H of its records (mvmc_clips_step_host_async), then sync
+            cs.step_host(kps_pin[fi], np_pin[fi], fi, out_pin)
         for s in range(W):
             host_step(1 + s)
         barrier()
@@ -310,7 +332,7 @@ def run_ours(args):
     ik_ms = stage_ms["ik"] / n_prof
     dom = "k_als" if als_ms >= ik_ms else "k_ik_solve"
     dom_ms = max(als_ms, ik_ms)
-    dom_flops = (st["als_flops"] if dom == "k_als" else st["ik_flops"]) / K
+    dom_flops = (st["als_flops"] if dom == "k_als" else st["ik_flops"]) / KP
     # k_als runs on the FP64 tensor cores (DMMA), k_ik_solve on the FP64 CUDA cores: each against its own probed peak
     peak_tf = fp64_dmma_tflops if dom == "k_als" else fp64_dfma_tflops
     # algorithmic bytes per launch: inputs (BODY_25 detections as float64 COCO) + outputs (params + joints + assignments)
@@ -343,7 +365,9 @@ def run_ours(args):
             "note": "DRAM bytes of the dominant kernel per clip-frame from the committed ncu capture x clips of this run / its "
                     "event-timed duration: the second bound of k_als (its n x n iterates stream through HBM every iteration)"},
         "stage_ms_per_step": {k: v / n_prof for k, v in stage_ms.items()},
-        "ik": {"achieved": st["ik_flops"] / K / (ik_ms * 1e-3) / 1e12 if ik_ms > 0 else None, "peak": fp64_dfma_tflops,
+        "timed": f"each kernel alone: one launch of all {B} clips per stage, {KP} steps after the same warm-up (the throughput run "
+                 f"overlaps {args.groups} clip groups on streams)",
+        "ik": {"achieved": st["ik_flops"] / KP / (ik_ms * 1e-3) / 1e12 if ik_ms > 0 else None, "peak": fp64_dfma_tflops,
                "unit": "TFLOP/s", "note": "k_ik_solve, SURVEY.md 8d flop formula on the run's own (nfev, njev) counts"},
     }
 
@@ -364,10 +388,11 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "clips_per_gpu": B, "distinct_clips": min(args.distinct, B), "n_views": N_VIEWS,
                    "n_people": N_PEOPLE, "max_tracks": args.max_tracks, "preroll_frames": args.preroll,
+                   "clip_groups_on_streams": args.groups,
                    "l2": "each step reads a new frame for every clip and sweeps the per-clip ALS workspaces "
-                         f"({cb.device_bytes / 2**20:.0f} MiB on device, far larger than the 126 MB L2)",
-                   "als_iters_per_clip_frame": st["als_iters"] / max(st["clip_frames"], 1),
-                   "ik_solves_per_clip_frame": st["ik_solves"] / max(st["clip_frames"], 1) / 2,
+                         f"({cs.device_bytes / 2**20:.0f} MiB on device, far larger than the 126 MB L2)",
+                   "als_iters_per_clip_frame": st_run["als_iters"] / max(st_run["clip_frames"], 1),
+                   "ik_solves_per_clip_frame": st_run["ik_solves"] / max(st_run["clip_frames"], 1) / 2,
                    "input_gen_s": t_gen},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
@@ -386,6 +411,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=148, help="distinct synthetic clips generated per rank (tiled to --clips)")
     ap.add_argument("--max-tracks", type=int, default=40)
     ap.add_argument("--preroll", type=int, default=4, help="untimed frames before the warm-up (track births happen here)")
+    ap.add_argument("--groups", type=int, default=3, help="clip groups stepped concurrently on their own CUDA streams")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--als-phases", action="store_true", help="print k_als's per-phase cycle shares to stderr (diagnostic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -207,6 +207,11 @@ const mvmc_step_out* mvmc_clips_last_out(const mvmc_clips* h);
  * synchronises the stream. out_host may be NULL (then only `n_alive`-sized summaries stay on device). */
 int mvmc_clips_step_host(mvmc_clips* h, const double* kps_host, const int* n_pose_host, int frame_idx,
                          mvmc_step_out* out_host, void* stream);
+/* The same without the final synchronisation (pinned host buffers; the caller synchronises `stream` before it reads
+ * out_host or reuses the input buffers): several handles on several streams then overlap each other's copies and kernels
+ * (the host side's ClipStreams steps groups of clips that way). */
+int mvmc_clips_step_host_async(mvmc_clips* h, const double* kps_host, const int* n_pose_host, int frame_idx,
+                               mvmc_step_out* out_host, void* stream);
 
 /* Teacher forcing / checkpoint-resume: overwrite the alive-track table of every clip.
  * n_trk [B]; ids, state, hits, tsu, length [B,Tmax]; param [B,Tmax,68]; joints [B,Tmax,18,3];

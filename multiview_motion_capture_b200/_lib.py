@@ -60,6 +60,7 @@ _SIGNATURES = {
     "mvmc_sizeof_step_out": (c_size_t, []),
     "mvmc_clips_last_out": (c_void_p, [c_void_p]),
     "mvmc_clips_step_host": (c_int, [c_void_p, _P, _P, c_int, _P, _P]),
+    "mvmc_clips_step_host_async": (c_int, [c_void_p, _P, _P, c_int, _P, _P]),
     "mvmc_clips_set_tracks_host": (c_int, [c_void_p] + [_P] * 9 + [_P]),
     "mvmc_clips_read_matrices_host": (c_int, [c_void_p, c_int, _P, _P, _P, _P, _P, _P]),
     "mvmc_clips_stats_host": (c_int, [c_void_p, _P, c_int, _P]),

@@ -157,3 +157,109 @@ class ClipBatch:
         k = n.value
         return (dst.reshape(-1)[:k * k].reshape(k, k).copy(), sim.reshape(-1)[:k * k].reshape(k, k).copy(),
                 xb.reshape(-1)[:k * k].reshape(k, k).astype(bool), dg)
+
+
+
+class ClipStreams:
+    """The same batch of clips as G groups, each a ClipBatch on its own CUDA stream.
+
+    Clips share nothing, so groups can run concurrently: while one group's ALS launch drains (its last CTAs leave SMs
+    idle) another group's IK / affinity kernels and host<->device copies fill the machine. Measured on a B200 at 8x32:
+    +4 % with two groups, +5 % with three (tools/groups_probe.py). Results are those of ClipBatch, clip for clip."""
+
+    def __init__(self, n_clips, n_views, max_poses, groups=3, device=None, **kw):
+        groups = max(1, min(int(groups), n_clips))
+        self.B, self.C, self.Pmax = n_clips, n_views, max_poses
+        sizes = [n_clips // groups + (1 if g < n_clips % groups else 0) for g in range(groups)]
+        self.bounds = [0]
+        for sz in sizes:
+            self.bounds.append(self.bounds[-1] + sz)
+        self.batches = [ClipBatch(sz, n_views, max_poses, device=device, **kw) for sz in sizes]
+        self.device = self.batches[0].device
+        self.lib = self.batches[0].lib
+        self.streams = [torch.cuda.Stream(self.device) for _ in sizes] if self.device.type == "cuda" else [None] * groups
+        self.Tmax = self.batches[0].Tmax
+
+    def _each(self):
+        for g, cb in enumerate(self.batches):
+            yield cb, self.bounds[g], self.bounds[g + 1], self.streams[g]
+
+    @property
+    def device_bytes(self):
+        return sum(cb.device_bytes for cb in self.batches)
+
+    def close(self):
+        for cb in self.batches:
+            cb.close()
+
+    def set_calib(self, K, Rt):
+        K = np.asarray(K, dtype=np.float64).reshape(self.B, self.C, 3, 3)
+        Rt = np.asarray(Rt, dtype=np.float64).reshape(self.B, self.C, 3, 4)
+        for cb, lo, hi, _ in self._each():
+            cb.set_calib(K[lo:hi], Rt[lo:hi])
+
+    def reset(self):
+        for cb in self.batches:
+            cb.reset()
+        self.sync()
+
+    def fork(self):
+        """Group streams wait for the work queued so far on the current stream."""
+        if self.device.type == "cuda":
+            cur = torch.cuda.current_stream(self.device)
+            for st in self.streams:
+                st.wait_stream(cur)
+
+    def join(self):
+        """The current stream waits for every group."""
+        if self.device.type == "cuda":
+            cur = torch.cuda.current_stream(self.device)
+            for st in self.streams:
+                cur.wait_stream(st)
+
+    def sync(self):
+        if self.device.type == "cuda":
+            for st in self.streams:
+                st.synchronize()
+
+    def step_device(self, kps, n_pose, frame_idx):
+        """kps [B,C,Pmax,17,3] f64, n_pose [B,C] i32 on the device; asynchronous (bracket a run with fork() / join())."""
+        for cb, lo, hi, st in self._each():
+            if st is None:
+                cb.step_device(kps[lo:hi], n_pose[lo:hi], frame_idx)
+            else:
+                with torch.cuda.stream(st):
+                    cb.step_device(kps[lo:hi], n_pose[lo:hi], frame_idx)
+
+    def step_host(self, kps_pinned, n_pose_pinned, frame_idx, out_pinned):
+        """Pinned host tensors kps [B,...] f64, n_pose [B,C] i32, out uint8 [B * sizeof(mvmc_step_out)]: every group copies
+        its slice in, steps, copies its records out - all asynchronous on the group's stream; returns after all did."""
+        rec = STEP_OUT_DTYPE.itemsize
+        for cb, lo, hi, st in self._each():
+            check(self.lib.mvmc_clips_step_host_async(cb._h, ptr(kps_pinned[lo:hi]), ptr(n_pose_pinned[lo:hi]), int(frame_idx),
+                                                      ptr(out_pinned[lo * rec:hi * rec]),
+                                                      st.cuda_stream if st is not None else None), "mvmc_clips_step_host_async")
+        self.sync()
+
+    def set_tracks(self, n_trk, ids, state, hits, tsu, length, param, joints, next_id):
+        B, T = self.B, self.Tmax
+        r = lambda x, dt, shape: np.asarray(x, dtype=dt).reshape(shape)
+        n_trk, next_id = r(n_trk, np.int32, (B,)), r(next_id, np.int32, (B,))
+        ids, state, hits, tsu, length = (r(x, np.int32, (B, T)) for x in (ids, state, hits, tsu, length))
+        param, joints = r(param, np.float64, (B, T, 68)), r(joints, np.float64, (B, T, 54))
+        for cb, lo, hi, st in self._each():
+            args = (n_trk[lo:hi], ids[lo:hi], state[lo:hi], hits[lo:hi], tsu[lo:hi], length[lo:hi], param[lo:hi], joints[lo:hi],
+                    next_id[lo:hi])
+            if st is None:
+                cb.set_tracks(*args)
+            else:
+                with torch.cuda.stream(st):
+                    cb.set_tracks(*args)
+        self.sync()
+
+    def stats(self, reset=False):
+        tot = None
+        for cb in self.batches:
+            s = cb.stats(reset)
+            tot = s if tot is None else {k: tot[k] + v for k, v in s.items()}
+        return tot

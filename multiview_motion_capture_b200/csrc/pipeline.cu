@@ -708,8 +708,8 @@ extern "C" size_t mvmc_sizeof_step_out(void) { return sizeof(mvmc_step_out); }
 
 extern "C" const mvmc_step_out* mvmc_clips_last_out(const mvmc_clips* h) { return h ? h->out : nullptr; }
 
-extern "C" int mvmc_clips_step_host(mvmc_clips* h, const double* kps_host, const int* n_pose_host, int frame_idx,
-                                    mvmc_step_out* out_host, void* stream) {
+extern "C" int mvmc_clips_step_host_async(mvmc_clips* h, const double* kps_host, const int* n_pose_host, int frame_idx,
+                                          mvmc_step_out* out_host, void* stream) {
     if (!h || !kps_host || !n_pose_host) return MVMC_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t nk = (size_t)h->B * h->C * h->Pmax * MVMC_N_COCO * 3;
@@ -719,7 +719,14 @@ extern "C" int mvmc_clips_step_host(mvmc_clips* h, const double* kps_host, const
     if (rc) return rc;
     if (out_host)
         MVMC_CUDA_OK(cudaMemcpyAsync(out_host, h->out, (size_t)h->B * sizeof(mvmc_step_out), cudaMemcpyDeviceToHost, s));
-    MVMC_CUDA_OK(cudaStreamSynchronize(s));
+    return MVMC_OK;
+}
+
+extern "C" int mvmc_clips_step_host(mvmc_clips* h, const double* kps_host, const int* n_pose_host, int frame_idx,
+                                    mvmc_step_out* out_host, void* stream) {
+    const int rc = mvmc_clips_step_host_async(h, kps_host, n_pose_host, frame_idx, out_host, stream);
+    if (rc) return rc;
+    MVMC_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
     return MVMC_OK;
 }
 

@@ -62,3 +62,37 @@ def run_golden_clip(dev, name, Pmax, Tmax, forced, B=1, max_new=8, frames=None):
     return st
 
 
+
+
+def check_clip_streams_equal_clip_batch(dev, name="synth_c4p3", Pmax=4, Tmax=8, max_new=4, frames=(2, 6), B=3, groups=2):
+    """ClipStreams (groups of clips on their own streams, mvmc_clips_step_host_async) returns, clip for clip, the records
+    ClipBatch returns: B clips with different inputs (the golden clip with its camera views rotated), the track table of
+    every frame taken from the golden run (tracking frames: the matcher converges in tens of iterations)."""
+    import torch
+    from multiview_motion_capture_b200._lib import STEP_OUT_DTYPE
+    from multiview_motion_capture_b200.clips import ClipBatch, ClipStreams
+    inp, g = golden(name)
+    kps = o.body25_to_coco(inp["kps25"])
+    C = kps.shape[1]
+    rot = [np.roll(np.arange(C), b) for b in range(B)]           # clip b sees the cameras in a rotated order
+    K = np.stack([inp["K"][r] for r in rot])
+    RT = np.stack([inp["RT"][r] for r in rot])
+    cb = ClipBatch(B, C, Pmax, max_tracks=Tmax, max_new=max_new, device=dev)
+    cs = ClipStreams(B, C, Pmax, groups=groups, max_tracks=Tmax, max_new=max_new, device=dev)
+    cb.set_calib(K, RT)
+    cs.set_calib(K, RT)
+    tab = GoldenTable(g)
+    pin = (lambda t: t.pin_memory()) if str(dev).startswith("cuda") else (lambda t: t)
+    out = pin(torch.empty(B * STEP_OUT_DTYPE.itemsize, dtype=torch.uint8))
+    for f in frames:
+        kf = np.stack([pad_poses(kps[f][r], Pmax) for r in rot])
+        nf = np.stack([inp["n_pose"][f][r] for r in rot]).astype(np.int32)
+        cb.set_tracks(**tab.packed(f, B, Tmax))
+        cs.set_tracks(**tab.packed(f, B, Tmax))
+        ref = cb.step(kf, nf, f).copy()
+        cs.step_host(pin(torch.from_numpy(np.ascontiguousarray(kf))), pin(torch.from_numpy(np.ascontiguousarray(nf))), f, out)
+        got = out.numpy().view(STEP_OUT_DTYPE)
+        assert got.tobytes() == ref.tobytes(), (name, f)
+        assert len({ref[b].tobytes() for b in range(B)}) > 1, "the clips of this test must differ"
+    cb.close()
+    cs.close()

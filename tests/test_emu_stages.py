@@ -61,3 +61,9 @@ def test_pipeline_teacher_forced_two_frames(emu):
     assert st["xbin"] == st["alive"] == st["upd"] == st["iters"] == st["frames"] == 2
     assert st["replicas"] == 2
     assert np.median(st["dj"]) < 2e-2
+
+
+def test_clip_streams_equal_clip_batch(emu):
+    """The grouped host-side runner (ClipStreams) returns the records of ClipBatch, clip for clip."""
+    from pipeline_checks import check_clip_streams_equal_clip_batch
+    check_clip_streams_equal_clip_batch(DEV, B=2, frames=(2,))

@@ -124,3 +124,10 @@ def test_full_size_properties_8x32(cuda):
                        for t in upd]
                 assert np.median(err) < 0.15, (f, b, np.median(err))
     cb.close()
+
+
+@pytest.mark.gpu
+def test_clip_streams_equal_clip_batch(cuda):
+    """Groups of clips on their own CUDA streams (ClipStreams, mvmc_clips_step_host_async): byte-identical records."""
+    from pipeline_checks import check_clip_streams_equal_clip_batch
+    check_clip_streams_equal_clip_batch(DEV, name="synth_c8p6", Pmax=8, Tmax=16, max_new=8, frames=(2, 3, 4), B=5, groups=3)
