@@ -1,1 +1,1 @@
-timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -12
+timeout 900 python -m pytest tests/test_gpu_configs.py -x -q -m gpu 2>&1 | tail -30
