@@ -261,9 +261,9 @@ def run_ours(args):
         cb.step_device(kps_dev[1 + W + s], np_dev[1 + W + s], 1 + W + s)
     torch.cuda.synchronize(dev)
     if args.als_phases and rank == 0:
-        ph = np.zeros(15)
+        ph = np.zeros(20)
         check(lib.mvmc_als_phase_profile(0, ptr(ph)), "mvmc_als_phase_profile")
-        names = ["G=AtA", "inv1", "T=AtXt", "B", "H=BtB", "inv2", "T=BtXtt", "A", "X=ABt", "reduce", "mu-pass", "init", "admm-pass", "admm-wait", "admm-fence"]
+        names = ["G=AtA", "inv1", "T=AtXt", "B", "H=BtB", "inv2", "T=BtXtt", "A", "X=ABt", "reduce", "mu-pass", "init", "admm-pass", "admm-wait", "admm-fence", "gj-load", "gj-inv8", "gj-panel", "gj-update", "gj-store"]
         print("k_als phase share of CTA cycles: " + ", ".join(f"{n} {100 * v / ph.sum():.1f}%" for n, v in zip(names, ph)),
               file=sys.stderr, flush=True)
     stage_ms, n_prof = cb.profile(0)

@@ -242,10 +242,10 @@ int mvmc_fp64_probe(int blocks, int iters, double* sink, void* stream);
 int mvmc_fp64_tensor_probe(int blocks, int iters, double* sink, void* stream);
 
 /* Diagnostics of mvmc_match_als: per-phase SM-cycle sums of thread 0 of every CTA since the counters were enabled
- * (enable != 0 resets and starts, 0 stops; out may be NULL, else 15 doubles: G = A^T A, its inverse, T = A^T Xt, B,
- * H = B^T B, its inverse, T = B^T Xt^T, A, X = A B^T, residual reduction, mu-change pass, init, ADMM update pass: arithmetic, waiting for its strips, its opening fence).
+ * (enable != 0 resets and starts, 0 stops; out may be NULL, else 20 doubles: G = A^T A, its inverse, T = A^T Xt, B,
+ * H = B^T B, its inverse, T = B^T Xt^T, A, X = A B^T, residual reduction, mu-change pass, init, ADMM update pass: arithmetic, waiting for its strips, its opening fence; then, inside the two inverses: load, 8 x 8 pivot-block inverses, row panels, updates, store).
  * Synchronises the device. */
-#define MVMC_ALS_N_PHASES 15
+#define MVMC_ALS_N_PHASES 20
 int mvmc_als_phase_profile(int enable, double* out);
 
 /* number of kernel launches enqueued by this library since load (for bench.py's gpu_launches) */

@@ -514,6 +514,30 @@ __device__ void invert_spd(double* G, int r, int ldg, double* aux) {
     }
 }
 
+// optional per-phase cycle counters (thread 0 of every CTA; enabled by mvmc_als_phase_profile(1)): where an iteration's time goes
+enum { PH_G1 = 0, PH_INV1, PH_T1, PH_B, PH_G2, PH_INV2, PH_T2, PH_A, PH_X, PH_RED, PH_MU, PH_INIT, PH_ADMM, PH_ADMM_WAIT, PH_ADMM_FENCE, PH_GJ_LOAD, PH_GJ_INV8, PH_GJ_PANEL, PH_GJ_UPD, PH_GJ_STORE, PH_COUNT };
+__device__ unsigned long long g_als_phase[PH_COUNT];
+__device__ int g_als_phase_on = 0;
+struct PhaseClock {
+    long long t;
+    bool on;
+    __device__ __forceinline__ void start() {
+#ifndef MVMC_EMU
+        on = g_als_phase_on != 0 && threadIdx.x == 0;
+        if (on) t = clock64();
+#endif
+    }
+    __device__ __forceinline__ void lap(int ph) {
+#ifndef MVMC_EMU
+        if (on) {
+            const long long now = clock64();
+            atomicAdd(&g_als_phase[ph], (unsigned long long)(now - t));
+            t = now;
+        }
+#endif
+    }
+};
+
 // ---- blocked Gauss-Jordan inverse on the tensor cores ----
 // The scalar elimination above is a chain of r dependent pivots with a block barrier each (about 1 us per pivot once the
 // FP64 pipe is shared with another CTA's DMMAs: 19 % of an ADMM iteration at r = 64). Here the matrix sits in shared
@@ -562,20 +586,39 @@ __device__ __forceinline__ void inv8_regs(double& e0, double& e1, int lane) {
 }
 
 __device__ void invert_spd_blocked(double* Gg, int r, int ldr, double* sm) {
+    PhaseClock gc;
+    gc.start();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int ro = lane >> 2, q = lane & 3;
     const int nb = (r + 7) >> 3, np = 8 * nb, ld = np + 4;   // pitch = 4 (mod 8): every fragment pattern is conflict free
     double* Gs = sm;               // [np][ld]
     double* R = sm + np * ld;      // [8][ld]
-    for (int e = threadIdx.x; e < np * np; e += AL_THREADS) {
-        const int i = e / np, j = e - i * np;
-        Gs[i * ld + j] = (i < r && j < r) ? Gg[(size_t)i * ldr + j] : (i == j ? 1.0 : 0.0);
+    {
+        // thread (w, lane) brings elements (w + 8a, lane + 32b): all the global loads first (they are independent; in a
+        // load-store loop each one waited for the previous store), then the stores
+        double v[(GJB_MAXR + 7) / 8][(GJB_MAXR + 31) / 32];
+#pragma unroll
+        for (int a = 0; a < (GJB_MAXR + 7) / 8; a++)
+#pragma unroll
+            for (int b = 0; b < (GJB_MAXR + 31) / 32; b++) {
+                const int i = w + 8 * a, j = lane + 32 * b;
+                v[a][b] = (i < r && j < r) ? Gg[(size_t)i * ldr + j] : (i == j ? 1.0 : 0.0);
+            }
+#pragma unroll
+        for (int a = 0; a < (GJB_MAXR + 7) / 8; a++)
+#pragma unroll
+            for (int b = 0; b < (GJB_MAXR + 31) / 32; b++) {
+                const int i = w + 8 * a, j = lane + 32 * b;
+                if (i < np && j < np) Gs[i * ld + j] = v[a][b];
+            }
     }
     __syncthreads();
+    gc.lap(PH_GJ_LOAD);
     for (int kb = 0; kb < nb; kb++) {
         // Pinv, in the accumulator layout
         double2 pv = *reinterpret_cast<const double2*>(Gs + (8 * kb + ro) * ld + 8 * kb + 2 * q);
         inv8_regs(pv.x, pv.y, lane);
+        gc.lap(PH_GJ_INV8);
         // Pinv as A fragments (row ro, k = 4h + q) and as B fragments (k = 4h + q, column ro)
         double pa[2], pb[2];
 #pragma unroll
@@ -599,6 +642,7 @@ __device__ void invert_spd_blocked(double* Gg, int r, int ldr, double* sm) {
             *reinterpret_cast<double2*>(R + ro * ld + 8 * j + 2 * q) = o;
         }
         __syncthreads();
+        gc.lap(PH_GJ_PANEL);
         for (int i = w; i < nb; i += AL_WARPS) {
             if (i == kb) {
                 for (int j = 0; j < nb; j++) {
@@ -628,11 +672,16 @@ __device__ void invert_spd_blocked(double* Gg, int r, int ldr, double* sm) {
             }
         }
         __syncthreads();
+        gc.lap(PH_GJ_UPD);
     }
-    for (int e = threadIdx.x; e < r * r; e += AL_THREADS) {
-        const int i = e / r, j = e - i * r;
-        Gg[(size_t)i * ldr + j] = Gs[i * ld + j];
-    }
+#pragma unroll
+    for (int a = 0; a < (GJB_MAXR + 7) / 8; a++)
+#pragma unroll
+        for (int b = 0; b < (GJB_MAXR + 31) / 32; b++) {
+            const int i = w + 8 * a, j = lane + 32 * b;
+            if (i < r && j < r) Gg[(size_t)i * ldr + j] = Gs[i * ld + j];
+        }
+    gc.lap(PH_GJ_STORE);
 }
 
 // Gg (r x r, ld ldr, global) <- inverse of Gg; `ring` = the (idle) operand ring, used as scratch
@@ -656,30 +705,6 @@ struct AlsLayout {
         ldr = (rmax + AL_PAD - 1) / AL_PAD * AL_PAD;
         zero_span = (size_t)NP * ldn + (size_t)2 * NP * ldr + (size_t)ldr * ldn + (size_t)ldr * ldr;
         per = (size_t)5 * NP * ldn + zero_span;
-    }
-};
-
-// optional per-phase cycle counters (thread 0 of every CTA; enabled by mvmc_als_phase_profile(1)): where an iteration's time goes
-enum { PH_G1 = 0, PH_INV1, PH_T1, PH_B, PH_G2, PH_INV2, PH_T2, PH_A, PH_X, PH_RED, PH_MU, PH_INIT, PH_ADMM, PH_ADMM_WAIT, PH_ADMM_FENCE, PH_COUNT };
-__device__ unsigned long long g_als_phase[PH_COUNT];
-__device__ int g_als_phase_on = 0;
-struct PhaseClock {
-    long long t;
-    bool on;
-    __device__ __forceinline__ void start() {
-#ifndef MVMC_EMU
-        on = g_als_phase_on != 0 && threadIdx.x == 0;
-        if (on) t = clock64();
-#endif
-    }
-    __device__ __forceinline__ void lap(int ph) {
-#ifndef MVMC_EMU
-        if (on) {
-            const long long now = clock64();
-            atomicAdd(&g_als_phase[ph], (unsigned long long)(now - t));
-            t = now;
-        }
-#endif
     }
 };
 
