@@ -31,11 +31,14 @@
 
 namespace mvmc {
 
-constexpr int AL_THREADS = 256;           // 8 warps: 2 along M x 4 along N, warp tile 32 x 24
+#ifndef AL_THREADS_
+#define AL_THREADS_ 256
+#endif
+constexpr int AL_THREADS = AL_THREADS_;   // 8 warps: 2 along M x 4 along N, warp tile 32 x 24 (4 warps: 2 x 2, four CTAs per SM)
 constexpr int AL_WARPS = AL_THREADS / 32;
 constexpr int AL_KC = 16;                 // k-chunk (one 128-byte swizzle row of doubles)
 constexpr int AL_TM = 64;                 // CTA tile rows
-constexpr int AL_TN = 96;                 // CTA tile columns (4 warp columns x 24)
+constexpr int AL_TN = 24 * (AL_WARPS / 2); // CTA tile columns (warp columns x 24)
 constexpr int AL_STAGE_M = AL_TM * AL_KC; // doubles: 8 KB
 constexpr int AL_STAGE_N = AL_TN * AL_KC; // 12 KB
 constexpr int AL_STAGE = AL_STAGE_M + AL_STAGE_N;
@@ -413,82 +416,9 @@ struct StoreEp {
 template <class F>
 __device__ __forceinline__ StoreEp<F> store_ep(F f) { return StoreEp<F>{f}; }
 
-// Inverse of the SPD r x r matrix Gg (global, leading dimension ldr) by Gauss-Jordan without pivoting, REGISTER resident:
-// thread (warp w, lane l) owns the elements (i = w + 8a, j = l + 32b), a < NA, b < NB, for the whole elimination, so a
-// pivot step is: the owners of row k / column k publish them (double-buffered in `aux`, [2][2][96]), ONE barrier, then
-// every thread does NA*NB fused multiply-adds on its own registers - no shared-memory read-modify-write, no index
-// arithmetic; the pivot row / column themselves are patched afterwards under (nearly) uniform branches.
 constexpr int GJ_LD = 96;
-template <int NA, int NB>
-__device__ void invert_spd_regs(double* Gg, int r, int ldr, double* aux) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double g[NA][NB];
-#pragma unroll
-    for (int a = 0; a < NA; a++)
-#pragma unroll
-        for (int b = 0; b < NB; b++) {
-            const int i = w + 8 * a, j = lane + 32 * b;
-            g[a][b] = (i < r && j < r) ? Gg[(size_t)i * ldr + j] : 0.0;
-        }
-    for (int k = 0; k < r; k++) {
-        double* rk = aux + (k & 1) * 2 * GJ_LD;   // pivot row (raw)
-        double* ck = rk + GJ_LD;                  // pivot column (raw)
-        const int ka = k >> 3, kb = k >> 5;
-        if (w == (k & 7)) {                       // this warp owns row k
-#pragma unroll
-            for (int a = 0; a < NA; a++)
-                if (a == ka) {
-#pragma unroll
-                    for (int b = 0; b < NB; b++) rk[lane + 32 * b] = g[a][b];
-                }
-        }
-        if (lane == (k & 31)) {                   // this lane owns column k (in every warp)
-#pragma unroll
-            for (int b = 0; b < NB; b++)
-                if (b == kb) {
-#pragma unroll
-                    for (int a = 0; a < NA; a++) ck[w + 8 * a] = g[a][b];
-                }
-        }
-        __syncthreads();
-        const double p = 1.0 / rk[k];
-        double rkp[NB], f[NA];
-#pragma unroll
-        for (int b = 0; b < NB; b++) rkp[b] = rk[lane + 32 * b] * p;
-#pragma unroll
-        for (int a = 0; a < NA; a++) f[a] = ck[w + 8 * a];
-#pragma unroll
-        for (int a = 0; a < NA; a++)
-#pragma unroll
-            for (int b = 0; b < NB; b++) g[a][b] = g[a][b] - f[a] * rkp[b];
-        if (w == (k & 7)) {                       // row k becomes the scaled pivot row
-#pragma unroll
-            for (int a = 0; a < NA; a++)
-                if (a == ka) {
-#pragma unroll
-                    for (int b = 0; b < NB; b++) g[a][b] = rkp[b];
-                }
-        }
-        if (lane == (k & 31)) {                   // column k becomes -f p, the pivot itself p
-#pragma unroll
-            for (int b = 0; b < NB; b++)
-                if (b == kb) {
-#pragma unroll
-                    for (int a = 0; a < NA; a++) g[a][b] = (w + 8 * a == k) ? p : -f[a] * p;
-                }
-        }
-        // (the next pivot publishes into the other half of aux; the barrier after it orders the reuse of this half)
-    }
-#pragma unroll
-    for (int a = 0; a < NA; a++)
-#pragma unroll
-        for (int b = 0; b < NB; b++) {
-            const int i = w + 8 * a, j = lane + 32 * b;
-            if (i < r && j < r) Gg[(size_t)i * ldr + j] = g[a][b];
-        }
-}
 
-// Fallback for r > 88: in place in global memory, thread t owns columns t % 32 + 32q of rows t / 32 + nw p.
+// Fallback for r > GJB_MAXR: in place in global memory, thread t owns columns t % 32 + 32q of rows t / 32 + nw p.
 __device__ void invert_spd(double* G, int r, int ldg, double* aux) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     double* rk = aux;        // pivot row * (1 / pivot)
@@ -547,7 +477,8 @@ struct PhaseClock {
 //     G[i,j] -= G[i,kb] R[j],  G[i,kb] = -G[i,kb] Pinv,  G[kb,:] = R, G[kb,kb] = Pinv   (row block i = warp) | barrier
 // 2 barriers per 8 pivots instead of 8, and the rank-8 updates run as DMMA. Same in-place Gauss-Jordan recurrences, block
 // wise; the matrix is padded with an identity to a multiple of 8.
-constexpr int GJB_MAXR = 88;     // (88 x 92 + 8 x 92) doubles = 70.6 KB of the 80 KB ring
+constexpr int GJB_MAXR = AL_NS * AL_STAGE >= 96 * 92 ? 88 : 64;     // (88 x 92 + 8 x 92) doubles = 70.6 KB of the 80 KB ring; 64 x 68 + 8 x 68 = 39.2 KB
+static_assert((GJB_MAXR + 8) * (GJB_MAXR + 4) <= AL_NS * AL_STAGE, "the blocked inverse works in the operand ring");
 
 // 8 x 8 inverse in registers: lane l holds P[l/4][2(l%4)], P[l/4][2(l%4)+1] (the DMMA accumulator layout).
 // Division-free Gauss-Jordan: instead of scaling the pivot row by 1/d, every other row is multiplied by the pivot,
@@ -596,19 +527,19 @@ __device__ void invert_spd_blocked(double* Gg, int r, int ldr, double* sm) {
     {
         // thread (w, lane) brings elements (w + 8a, lane + 32b): all the global loads first (they are independent; in a
         // load-store loop each one waited for the previous store), then the stores
-        double v[(GJB_MAXR + 7) / 8][(GJB_MAXR + 31) / 32];
+        double v[(GJB_MAXR + AL_WARPS - 1) / AL_WARPS][(GJB_MAXR + 31) / 32];
 #pragma unroll
-        for (int a = 0; a < (GJB_MAXR + 7) / 8; a++)
+        for (int a = 0; a < (GJB_MAXR + AL_WARPS - 1) / AL_WARPS; a++)
 #pragma unroll
             for (int b = 0; b < (GJB_MAXR + 31) / 32; b++) {
-                const int i = w + 8 * a, j = lane + 32 * b;
+                const int i = w + AL_WARPS * a, j = lane + 32 * b;
                 v[a][b] = (i < r && j < r) ? Gg[(size_t)i * ldr + j] : (i == j ? 1.0 : 0.0);
             }
 #pragma unroll
-        for (int a = 0; a < (GJB_MAXR + 7) / 8; a++)
+        for (int a = 0; a < (GJB_MAXR + AL_WARPS - 1) / AL_WARPS; a++)
 #pragma unroll
             for (int b = 0; b < (GJB_MAXR + 31) / 32; b++) {
-                const int i = w + 8 * a, j = lane + 32 * b;
+                const int i = w + AL_WARPS * a, j = lane + 32 * b;
                 if (i < np && j < np) Gs[i * ld + j] = v[a][b];
             }
     }
@@ -675,10 +606,10 @@ __device__ void invert_spd_blocked(double* Gg, int r, int ldr, double* sm) {
         gc.lap(PH_GJ_UPD);
     }
 #pragma unroll
-    for (int a = 0; a < (GJB_MAXR + 7) / 8; a++)
+    for (int a = 0; a < (GJB_MAXR + AL_WARPS - 1) / AL_WARPS; a++)
 #pragma unroll
         for (int b = 0; b < (GJB_MAXR + 31) / 32; b++) {
-            const int i = w + 8 * a, j = lane + 32 * b;
+            const int i = w + AL_WARPS * a, j = lane + 32 * b;
             if (i < r && j < r) Gg[(size_t)i * ldr + j] = Gs[i * ld + j];
         }
     gc.lap(PH_GJ_STORE);
@@ -880,7 +811,7 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
     __syncthreads();   // (the ring is handed back to the products)
 }
 
-__global__ void __launch_bounds__(AL_THREADS, 2)
+__global__ void __launch_bounds__(AL_THREADS, 512 / AL_THREADS)
     k_als(const AL_GRID_CONSTANT AlsMaps maps, const double* __restrict__ sim, const int* __restrict__ dim_groups, int n_groups,
           const int* __restrict__ f32_first_iter, const double* __restrict__ rand_stream, const int* __restrict__ order,
           int N, int rmax, double* __restrict__ ws, uint32_t* __restrict__ xbin, int* __restrict__ n_iter_out, double alpha,

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from helpers import EMU_LIB, ROOT, golden, pad_poses
+from helpers import EMU_LIB, ROOT, GoldenTable, golden, pad_poses
 
 from multiview_motion_capture_b200 import sharding
 
@@ -25,28 +25,29 @@ def test_shard_clips_partition():
 
 
 def _inputs(n_clips):
-    """n_clips clips = the c4p3 synthetic golden scene with the frames rotated by clip index (so clips differ)."""
+    """n_clips clips = the c4p3 synthetic golden scene at a frame that depends on the clip index (so clips differ)."""
     import mvmc_oracle as o
-    inp, _ = golden("synth_c4p3")
+    inp, g = golden("synth_c4p3")
     kps = o.body25_to_coco(inp["kps25"])
     frames = [2 + (c % 3) for c in range(n_clips)]
-    return inp, kps, frames
+    return inp, g, kps, frames
 
 
 def _track(clip_ids):
-    """One tracked frame (births at frame f, update at f+1) for the given global clip ids; returns their records."""
+    """One tracking frame for the given global clip ids (the track table of the frame taken from the golden run: the
+    emulator then needs tens, not a thousand, matcher iterations per clip); returns their records."""
     from multiview_motion_capture_b200 import _lib
     from multiview_motion_capture_b200.clips import ClipBatch
     _lib.use_library(EMU_LIB)
-    inp, kps, frames = _inputs(max(clip_ids) + 1)
+    inp, g, kps, frames = _inputs(max(clip_ids) + 1)
     B = len(clip_ids)
     cb = ClipBatch(B, 4, 4, max_tracks=8, max_new=4, device="cpu")
     cb.set_calib(np.repeat(inp["K"][None], B, 0), np.repeat(inp["RT"][None], B, 0))
-    rec = None
-    for step in range(2):
-        k = np.stack([pad_poses(kps[frames[c] + step], 4) for c in clip_ids])
-        n = np.stack([inp["n_pose"][frames[c] + step] for c in clip_ids])
-        rec = cb.step(k, n, step + 1).copy()
+    packs = [GoldenTable(g).packed(frames[c], 1, 8) for c in clip_ids]
+    cb.set_tracks(**{k: np.concatenate([p[k] for p in packs]) for k in packs[0]})
+    k = np.stack([pad_poses(kps[frames[c]], 4) for c in clip_ids])
+    n = np.stack([inp["n_pose"][frames[c]] for c in clip_ids])
+    rec = cb.step(k, n, 1).copy()
     cb.close()
     return rec
 
