@@ -421,6 +421,11 @@ struct mvmc_clips {
     void* ik_ws = nullptr;
     mvmc_step_out* out = nullptr;
     double* stats = nullptr;  // [MVMC_N_STATS] device counters
+    // side stream for the birth solves (a handful per step, each ~10x an update: alone they are a ~5 ms latency tail)
+#ifndef MVMC_EMU
+    cudaStream_t birth_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+#endif
     // optional per-stage event timing
     int profiling = 0;
     int ev_step = 0;
@@ -460,6 +465,9 @@ extern "C" void mvmc_clips_destroy(mvmc_clips* h) {
     if (!h) return;
 #ifndef MVMC_EMU
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->birth_stream) cudaStreamDestroy(h->birth_stream);
 #endif
     for (void* p : h->allocs) cudaFree(p);
     delete h;
@@ -580,6 +588,18 @@ extern "C" int mvmc_clips_create(const mvmc_config* cfg, mvmc_clips** out) {
             return rc;
         }
     }
+#ifndef MVMC_EMU
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&h->birth_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            int rc = mvmc_set_cuda_error(e, "birth stream");
+            mvmc_clips_destroy(h);
+            return rc;
+        }
+    }
+#endif
     *out = h;
     return MVMC_OK;
 }
@@ -638,14 +658,25 @@ extern "C" int mvmc_clips_step(mvmc_clips* h, const double* kps, const int* n_po
                 h->w_x0, h->w_birth, h->w_nfev);
     MVMC_CHECK_LAUNCH("k_gather");
     MVMC_EV(3);
-    // track updates use one pose per view (<= C observations); births of no-track frames may group more (<= MVMC_MAX_SEL)
+    // track updates use one pose per view (<= C observations); births of no-track frames may group more (<= MVMC_MAX_SEL).
+    // The two launches touch disjoint work slots; the births run on a side stream next to the updates.
+    void* bstream = stream;
+#ifndef MVMC_EMU
+    MVMC_CUDA_OK(cudaEventRecord(h->ev_fork, (cudaStream_t)stream));
+    MVMC_CUDA_OK(cudaStreamWaitEvent(h->birth_stream, h->ev_fork, 0));
+    bstream = h->birth_stream;
+#endif
+    rc = mvmc_ik_launch(h->w_kps, h->w_P, h->w_nv, h->w_x0, h->w_birth, h->w_nfev, nullptr, B * h->cfg.max_new, h->cfg.max_new,
+                        h->S, Tmax, MVMC_MAX_SEL, MVMC_MAX_SEL, (int*)h->ik_ws + 16, h->w_xout, h->w_joints, h->w_info,
+                        h->w_cost, bstream);
+    if (rc) return rc;
     rc = mvmc_ik_launch(h->w_kps, h->w_P, h->w_nv, h->w_x0, nullptr, h->w_nfev, nullptr, B * Tmax, Tmax, h->S, 0,
                         MVMC_MAX_SEL, C, (int*)h->ik_ws, h->w_xout, h->w_joints, h->w_info, h->w_cost, stream);
     if (rc) return rc;
-    rc = mvmc_ik_launch(h->w_kps, h->w_P, h->w_nv, h->w_x0, h->w_birth, h->w_nfev, nullptr, B * h->cfg.max_new, h->cfg.max_new,
-                        h->S, Tmax, MVMC_MAX_SEL, MVMC_MAX_SEL, (int*)h->ik_ws + 16, h->w_xout, h->w_joints, h->w_info,
-                        h->w_cost, stream);
-    if (rc) return rc;
+#ifndef MVMC_EMU
+    MVMC_CUDA_OK(cudaEventRecord(h->ev_join, h->birth_stream));
+    MVMC_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_join, 0));
+#endif
     MVMC_EV(4);
     MVMC_LAUNCH(k_commit, dim3(B), dim3(128), 0, stream, h->st, h->trk_nsel, h->trk_sel, h->new_n, h->new_nsel, h->new_sel,
                 h->n_dup, h->assign_err, h->dim_groups, h->als_iter, h->w_xout, h->w_joints, h->w_info, h->w_cost, C, Tmax,
