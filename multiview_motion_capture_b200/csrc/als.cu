@@ -646,21 +646,24 @@ struct AlsLayout {
 // X; Z itself is never stored: the rare mu change recomputes it from X and the previous Y, bit for bit). As an epilogue of the product the same
 // update was bound by the few loads a thread can keep in flight next to its 48 accumulator registers.
 #ifndef AL_PASS_NS_
-#define AL_PASS_NS_ 4
+#define AL_PASS_NS_ 8
 #endif
-constexpr int AL_PASS_NS = AL_PASS_NS_;    // strips in flight (power of two)
-constexpr int AL_PASS_U = 1;     // pairs per thread per round (2 measured slower: a round then spans half the ring)
+constexpr int AL_PASS_NS = AL_PASS_NS_;    // most strips in flight (what fits the ring decides)
+#ifndef AL_PASS_U_
+#define AL_PASS_U_ 1
+#endif
+constexpr int AL_PASS_U = AL_PASS_U_;     // pairs per thread per round (2 measured slower: a round then spans half the ring)
 struct AdmmPass {
     mbar_t* bar;        // [AL_PASS_NS] bytes landed in a stage
     unsigned* cnt;      // [AL_PASS_NS] warps that have left a stage (running count)
-    unsigned use;       // strips consumed so far (all passes of this CTA): stage and parity of the next one
-    int rs, lns;        // rows per strip, log2(stages) (fixed per launch: functions of ldn)
+    int rs, ns;         // rows per strip, stages (fixed per launch: functions of ldn)
+    int st0, par0;      // stage and phase parity of the next pass's first strip
 };
 
 __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const double* Xn, const double* Xo, const double* Yo, double* Yn,
                                           const double* W, double* Xt, const int* grp, int n, int ldn, double mu, double inv_mu,
                                           double beta, double& pacc, double& dacc, PhaseClock& pc) {
-    const int rs = ps.rs, lns = ps.lns, ns = 1 << lns;   // the stage count is a power of two: no division in the loop
+    const int rs = ps.rs, ns = ps.ns;   // (stage indices advance by compare-and-wrap: no division in the loop)
     const int stage_doubles = 4 * rs * ldn;
     const int total = (n + rs - 1) / rs;          // strips
     const int hpn = (n + 1) >> 1;                 // live column pairs of a row
@@ -671,9 +674,7 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
     pc.lap(PH_ADMM_FENCE);
     // Rows are visited last to first (the rows X = A B^T wrote most recently are the ones most likely still in L2):
     // "logical" row q is row n-1-q; strip s = logical rows [s rs, (s+1) rs) = one contiguous block of rows.
-    auto issue = [&](int s) {
-        const unsigned g = ps.use + (unsigned)s;
-        const int st = g & (ns - 1);
+    auto issue = [&](int s, int st) {   // strip s into stage st
         const int hi = min(n, (s + 1) * rs), nr = hi - s * rs, r0 = n - hi;
         const unsigned bytes = (unsigned)(nr * ldn) * 8u;
         double* dst = ring + st * stage_doubles;
@@ -686,17 +687,21 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
     };
     if (threadIdx.x == 0) {
         const int pre = min(ns, total);
-        for (int s = 0; s < pre; s++) issue(s);
+        int st = ps.st0;
+        for (int s = 0; s < pre; s++) {
+            issue(s, st);
+            st = st + 1 == ns ? 0 : st + 1;
+        }
     }
     // The pairs of the pass are one flat index space walked AL_PASS_U x 256 at a time, independent of the strip boundaries
     // (a strip of two 262-column rows is 262 pairs: strip-synchronous rounds would run half empty). A round waits for the
     // strips it touches; the last warp out of a strip refills its stage (no block barrier: the warps drift apart by up to
     // the depth of the ring). Every index advances incrementally and every per-round quantity is a compare or an add: the
     // loop skeleton (integer divisions by run-time values, in an earlier version) cost more than the arithmetic.
-    int waited = 0, wait_at = 0;        // strips waited for; first pair of strip `waited`
-    int done = 0, done_at = min(P, spp);   // strips this warp has left; end (pair index) of strip `done`
+    int waited = 0, wait_at = 0, wst = ps.st0, wpar = ps.par0;   // strips waited for; first pair, stage, parity of strip `waited`
+    int done = 0, done_at = min(P, spp), dst = ps.st0;           // strips this warp has left; end (pair index) and stage of strip `done`
     int q = 0, c = (int)threadIdx.x;    // this thread's first pair of the round: logical row q, pair c of the row
-    int sq = 0, stq = (int)(ps.use & (unsigned)(ns - 1)), sq_end = rs;   // strip of row q, its stage, its first row beyond
+    int sq = 0, stq = ps.st0, sq_end = rs;   // strip of row q, its stage, its first row beyond
     while (c >= hpn) {
         c -= hpn;
         q++;
@@ -704,16 +709,19 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
     for (int e0 = 0; e0 < P;) {
         const int e1 = min(min(P, e0 + AL_PASS_U * AL_THREADS), (done + ns) * spp);   // never past the strips in flight
         while (waited < total && wait_at < e1) {
-            const unsigned g = ps.use + (unsigned)waited;
-            mbar_wait(&ps.bar[g & (ns - 1)], (g >> lns) & 1);
+            mbar_wait(&ps.bar[wst], (unsigned)wpar);
             waited++;
             wait_at += spp;
+            if (++wst == ns) {
+                wst = 0;
+                wpar ^= 1;
+            }
         }
         AL_EMU_SYNC();
         while (q >= sq_end) {
             sq++;
             sq_end += rs;
-            stq = (stq + 1) & (ns - 1);
+            stq = stq + 1 == ns ? 0 : stq + 1;
         }
         bool on[AL_PASS_U];
         int pi[AL_PASS_U], pj[AL_PASS_U];
@@ -746,7 +754,7 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
                     }
                     while (uq >= usq_end) {
                         usq_end += rs;
-                        ust = (ust + 1) & (ns - 1);
+                        ust = ust + 1 == ns ? 0 : ust + 1;
                     }
                 }
             }
@@ -798,16 +806,21 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
         while (done < total && done_at <= e1) {
             if ((threadIdx.x & 31) == 0) {
                 __threadfence_block();
-                const unsigned was = atomicAdd(&ps.cnt[(ps.use + (unsigned)done) & (unsigned)(ns - 1)], 1u);
-                if ((was & (AL_WARPS - 1)) == AL_WARPS - 1 && done + ns < total) issue(done + ns);
+                const unsigned was = atomicAdd(&ps.cnt[dst], 1u);
+                if ((was & (AL_WARPS - 1)) == AL_WARPS - 1 && done + ns < total) issue(done + ns, dst);   // refill the stage just left
             }
             done++;
             done_at = min(P, done_at + spp);
+            dst = dst + 1 == ns ? 0 : dst + 1;
         }
         AL_EMU_SYNC();
         e0 = e1;
     }
-    ps.use += (unsigned)total;
+    {   // where the next pass starts in the ring (one division per pass)
+        const int adv = ps.st0 + total;
+        ps.par0 ^= (adv / ns) & 1;
+        ps.st0 = adv % ns;
+    }
     __syncthreads();   // (the ring is handed back to the products)
 }
 
@@ -843,12 +856,15 @@ __global__ void __launch_bounds__(AL_THREADS, 512 / AL_THREADS)
     rg.clip = b;
     AdmmPass ps;
     ps.bar = rg.empty + AL_NS;                                    // [AL_PASS_NS]
-    ps.use = 0;
+    ps.st0 = 0;
+    ps.par0 = 0;
     {
         const int ring_doubles = AL_NS * AL_STAGE, ldn_ = (N + AL_PAD - 1) / AL_PAD * AL_PAD;
-        ps.rs = max(1, ring_doubles / (AL_PASS_NS * 4 * ldn_));
-        const int fit = min(AL_PASS_NS, ring_doubles / (4 * ps.rs * ldn_));   // stages that fit: rounded down to a power of two
-        ps.lns = fit >= 8 ? 3 : (fit >= 4 ? 2 : 1);
+#ifndef AL_PASS_TARGET_
+#define AL_PASS_TARGET_ 4
+#endif
+        ps.rs = max(1, ring_doubles / (AL_PASS_TARGET_ * 4 * ldn_));   // strips of about a quarter of the ring (4 matrices per strip)
+        ps.ns = max(1, min(AL_PASS_NS, ring_doubles / (4 * ps.rs * ldn_)));   // stages that fit
     }
     ps.cnt = reinterpret_cast<unsigned*>(ps.bar + AL_PASS_NS);    // [AL_PASS_NS]
     int* s_grp = reinterpret_cast<int*>(ps.cnt + AL_PASS_NS + (AL_PASS_NS & 1));   // [N + 1], 8-byte aligned
