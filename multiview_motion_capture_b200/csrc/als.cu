@@ -43,7 +43,6 @@ constexpr int AL_STAGE_M = AL_TM * AL_KC; // doubles: 8 KB
 constexpr int AL_STAGE_N = AL_TN * AL_KC; // 12 KB
 constexpr int AL_STAGE = AL_STAGE_M + AL_STAGE_N;
 constexpr int AL_NS = 4;                  // stages of the operand ring
-constexpr int AL_RSMEM = 88;              // largest r whose normal matrix is inverted in registers (11 rows x 8 warps)
 constexpr int AL_PAD = 16;                // every matrix dimension of the workspace is padded (with zeros) to this
 
 // ---- tensor maps, mbarriers, TMA loads (emulated synchronously under the CPU emulator) ----
@@ -1073,10 +1072,8 @@ __global__ void __launch_bounds__(AL_THREADS, AL_CTAS_)
 // One CTA; counting sort over 0..1023 iterations. The order only affects scheduling, never a result.
 __global__ void __launch_bounds__(1024) k_als_order(const int* __restrict__ prev_iter, int B, int* __restrict__ order) {
     __shared__ int cnt[1024];
-    __shared__ int carry;
     const int t = threadIdx.x;
     cnt[t] = 0;
-    if (t == 0) carry = 0;
     __syncthreads();
     for (int b = t; b < B; b += 1024) atomicAdd(&cnt[1023 - min(max(prev_iter[b], 0), 1023)], 1);
     __syncthreads();
