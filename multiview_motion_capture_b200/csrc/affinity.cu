@@ -266,22 +266,39 @@ __global__ void __launch_bounds__(AFF_TILE* AFF_TILE)
     const int i0 = blockIdx.y * AFF_TILE, j0 = blockIdx.x * AFF_TILE;
     if (i0 >= n || j0 >= n) return;
     __shared__ double s_item[2 * AFF_TILE][AFF_ITEM];
-    __shared__ int s_view[2 * AFF_TILE];
+    __shared__ int s_view[2 * AFF_TILE], s_pose[2 * AFF_TILE];
     const int tid = threadIdx.y * AFF_TILE + threadIdx.x;
     const int T = min(n_trk[b], Tmax);
-    // stage: items 0..15 = rows i0.., 16..31 = cols j0..
-    for (int it = 0; it < 2 * AFF_TILE; it++) {
-        const int g = (it < AFF_TILE) ? i0 + it : j0 + it - AFF_TILE;
-        if (g >= n) {
-            if (tid == 0) s_view[it] = -2;
-            continue;
+    // stage: items 0..15 = rows i0.., 16..31 = cols j0.. - every thread brings a few elements of several items and all of
+    // its loads are issued before the first store (item by item, the 32 global-load latencies used to run back to back)
+    if (tid < 2 * AFF_TILE) {
+        const int g = (tid < AFF_TILE) ? i0 + tid : j0 + tid - AFF_TILE;
+        s_view[tid] = g < n ? idx_view[(size_t)b * N + g] : -2;
+        s_pose[tid] = g < n ? idx_pose[(size_t)b * N + g] : 0;
+    }
+    __syncthreads();
+    {
+        constexpr int PER = (2 * AFF_TILE * AFF_ITEM + AFF_TILE * AFF_TILE - 1) / (AFF_TILE * AFF_TILE);
+        double val[PER];
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int e = tid + q * AFF_TILE * AFF_TILE, it = e / AFF_ITEM, k = e - it * AFF_ITEM;
+            val[q] = 0.0;
+            if (it < 2 * AFF_TILE) {
+                const int v = s_view[it], p = s_pose[it];
+                const int len = (v < 0) ? MVMC_N_B18 * 3 : MVMC_N_COCO * 3;
+                if (v != -2 && k < len) {
+                    const double* src = (v < 0) ? trk_joints + ((size_t)b * Tmax + p) * (MVMC_N_B18 * 3)
+                                                : kps + ((size_t)(b * C + v) * Pmax + p) * (MVMC_N_COCO * 3);
+                    val[q] = src[k];
+                }
+            }
         }
-        const int v = idx_view[(size_t)b * N + g], p = idx_pose[(size_t)b * N + g];
-        if (tid == 0) s_view[it] = v;
-        const double* src = (v < 0) ? trk_joints + ((size_t)b * Tmax + p) * (MVMC_N_B18 * 3)
-                                    : kps + ((size_t)(b * C + v) * Pmax + p) * (MVMC_N_COCO * 3);
-        const int len = (v < 0) ? MVMC_N_B18 * 3 : MVMC_N_COCO * 3;
-        if (tid < len) s_item[it][tid] = src[tid];
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int e = tid + q * AFF_TILE * AFF_TILE, it = e / AFF_ITEM, k = e - it * AFF_ITEM;
+            if (it < 2 * AFF_TILE) s_item[it][k] = val[q];
+        }
     }
     __syncthreads();
     const int i = i0 + threadIdx.y, j = j0 + threadIdx.x;
