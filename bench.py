@@ -336,7 +336,7 @@ def run_ours(args):
     # k_als runs on the FP64 tensor cores (DMMA), k_ik_solve on the FP64 CUDA cores: each against its own probed peak
     peak_tf = fp64_dmma_tflops if dom == "k_als" else fp64_dfma_tflops
     # algorithmic bytes per launch: inputs (BODY_25 detections as float64 COCO) + outputs (params + joints + assignments)
-    bytes_per_clip_frame = N_VIEWS * N_PEOPLE * 17 * 3 * 8 + N_PEOPLE * (68 + 54) * 8 + 288 * 4
+    bytes_per_clip_frame = N_VIEWS * N_PEOPLE * 17 * 3 * 8 + N_PEOPLE * (68 + 54) * 8 + (N_VIEWS + 1) * N_PEOPLE * 4
     alg_bytes = B * bytes_per_clip_frame
     achieved_tf = dom_flops / (dom_ms * 1e-3) / 1e12
     traffic = None
@@ -416,7 +416,15 @@ def main():
     ap.add_argument("--als-phases", action="store_true", help="print k_als's per-phase cycle shares to stderr (diagnostic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cores", type=int, default=0)
+    ap.add_argument("--views", type=int, default=0, help="other scene shapes (not the headline metric): cameras ...")
+    ap.add_argument("--people", type=int, default=0, help="... and people per scene, e.g. --views 5 --people 4 (Shelf shaped)")
     args = ap.parse_args()
+    if args.views or args.people:
+        global N_VIEWS, N_PEOPLE, WORKLOAD
+        N_VIEWS, N_PEOPLE = args.views or N_VIEWS, args.people or N_PEOPLE
+        WORKLOAD = (f"synthetic {N_VIEWS} cams x {N_PEOPLE} people BODY_25 clips (NOT the headline shape), association + "
+                    f"triangulation + IK, one frame per clip per step")
+        args.max_tracks = min(args.max_tracks, max(8, N_PEOPLE + N_PEOPLE // 4))
     if args.impl == "reference":
         run_reference(args)
     else:
