@@ -208,12 +208,18 @@ struct Ring {
 typedef const unsigned char* saddr_t;
 __device__ __forceinline__ saddr_t saddr_of(const double* p) { return reinterpret_cast<saddr_t>(p); }
 __device__ __forceinline__ double lds64(saddr_t a) { return *reinterpret_cast<const double*>(a); }
+__device__ __forceinline__ double2 lds128(saddr_t a) { return *reinterpret_cast<const double2*>(a); }
 #else
 typedef unsigned saddr_t;
 __device__ __forceinline__ saddr_t saddr_of(const double* p) { return smem_u32(p); }
 __device__ __forceinline__ double lds64(saddr_t a) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds128(saddr_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
     return v;
 }
 #endif
@@ -648,10 +654,7 @@ struct AlsLayout {
 #define AL_PASS_NS_ 8
 #endif
 constexpr int AL_PASS_NS = AL_PASS_NS_;    // most strips in flight (what fits the ring decides)
-#ifndef AL_PASS_U_
-#define AL_PASS_U_ 1
-#endif
-constexpr int AL_PASS_U = AL_PASS_U_;     // pairs per thread per round (2 measured slower: a round then spans half the ring)
+constexpr int AL_PASS_U = 1;     // pairs per thread per round (2 measured slower: a round then spans half the ring)
 struct AdmmPass {
     mbar_t* bar;        // [AL_PASS_NS] bytes landed in a stage
     unsigned* cnt;      // [AL_PASS_NS] warps that have left a stage (running count)
@@ -663,6 +666,7 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
                                           const double* W, double* Xt, const int* grp, int n, int ldn, double mu, double inv_mu,
                                           double beta, double& pacc, double& dacc, PhaseClock& pc) {
     const int rs = ps.rs, ns = ps.ns;   // (stage indices advance by compare-and-wrap: no division in the loop)
+    const saddr_t ring_s = saddr_of(ring);
     const int stage_doubles = 4 * rs * ldn;
     const int total = (n + rs - 1) / rs;          // strips
     const int hpn = (n + 1) >> 1;                 // live column pairs of a row
@@ -722,77 +726,47 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
             sq_end += rs;
             stq = stq + 1 == ns ? 0 : stq + 1;
         }
-        bool on[AL_PASS_U];
-        int pi[AL_PASS_U], pj[AL_PASS_U];
-        double2 x[AL_PASS_U], x0[AL_PASS_U], y[AL_PASS_U], w[AL_PASS_U];
-        int gi[AL_PASS_U];
-        int2 gj[AL_PASS_U];
-        {
-            int uq = q, uc = c, usq_end = sq_end, ust = stq;
-#pragma unroll
-            for (int u = 0; u < AL_PASS_U; u++) {
-                on[u] = e0 + u * AL_THREADS + (int)threadIdx.x < e1;
-                if (on[u]) {
-                    const int j = 2 * uc, i = n - 1 - uq;
-                    const int hi = min(n, usq_end);
-                    const double* sx = ring + ust * stage_doubles + (i - (n - hi)) * ldn + j;
-                    x[u] = *reinterpret_cast<const double2*>(sx);
-                    x0[u] = *reinterpret_cast<const double2*>(sx + rs * ldn);
-                    y[u] = *reinterpret_cast<const double2*>(sx + 2 * rs * ldn);
-                    w[u] = *reinterpret_cast<const double2*>(sx + 3 * rs * ldn);
-                    gi[u] = grp[i];
-                    gj[u] = *reinterpret_cast<const int2*>(grp + j);   // (grp[n] = -1: an odd last column is in no group)
-                    pi[u] = i;
-                    pj[u] = j;
-                }
-                if (u + 1 < AL_PASS_U) {   // the next pair of this thread is AL_THREADS further on
-                    uc += AL_THREADS;
-                    while (uc >= hpn) {
-                        uc -= hpn;
-                        uq++;
-                    }
-                    while (uq >= usq_end) {
-                        usq_end += rs;
-                        ust = ust + 1 == ns ? 0 : ust + 1;
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < AL_PASS_U; u++) {
-            if (!on[u]) continue;
-            const int i = pi[u], j = pj[u];
+        if (e0 + (int)threadIdx.x < e1) {
+            // one pair per thread and round; shared-memory loads through 32-bit shared addresses and one 32-bit byte
+            // offset for the two stores (the generic-pointer version spent a third of the round on 64-bit address arithmetic)
+            const int j = 2 * c, i = n - 1 - q;
+            const int hi = min(n, sq_end);
+            const saddr_t sx = ring_s + (unsigned)((stq * stage_doubles + (i - (n - hi)) * ldn + j) * 8);
+            const unsigned mat = (unsigned)(rs * ldn * 8);
+            const double2 x = lds128(sx), x0 = lds128(sx + mat), y = lds128(sx + 2 * mat), w = lds128(sx + 3 * mat);
+            const int gi = grp[i];
+            const int2 gj = *reinterpret_cast<const int2*>(grp + j);   // (grp[n] = -1: an odd last column is in no group)
             const bool live1 = j + 1 < n;     // the odd column of the last pair may be padding
             double2 yn, xt;
             {
-                const double dd = x[u].x - x0[u].x;
-                double zz = x[u].x + y[u].x * inv_mu;           // y / mu (mu is a power of two)
-                if (gi[u] == gj[u].x) zz = 0.0;
+                const double dd = x.x - x0.x;
+                double zz = x.x + y.x * inv_mu;                 // y / mu (mu is a power of two)
+                if (gi == gj.x) zz = 0.0;
                 if (i == j) zz = 1.0;
                 zz = fmin(fmax(zz, 0.0), 1.0);
-                const double pd = x[u].x - zz;
-                yn.x = y[u].x + mu * pd;
-                xt.x = zz - (yn.x - w[u].x + beta) * inv_mu;    // next iteration's Xt if mu stays
+                const double pd = x.x - zz;
+                yn.x = y.x + mu * pd;
+                xt.x = zz - (yn.x - w.x + beta) * inv_mu;       // next iteration's Xt if mu stays
                 dacc += dd * dd;
                 pacc += pd * pd;
             }
             {
-                const double dd = x[u].y - x0[u].y;
-                double zz = x[u].y + y[u].y * inv_mu;
-                if (gi[u] == gj[u].y) zz = 0.0;
+                const double dd = x.y - x0.y;
+                double zz = x.y + y.y * inv_mu;
+                if (gi == gj.y) zz = 0.0;
                 if (i == j + 1) zz = 1.0;
                 zz = fmin(fmax(zz, 0.0), 1.0);
-                const double pd = x[u].y - zz;
-                yn.y = y[u].y + mu * pd;
-                xt.y = live1 ? zz - (yn.y - w[u].y + beta) * inv_mu : 0.0;   // the padding column of Xt stays zero
+                const double pd = x.y - zz;
+                yn.y = y.y + mu * pd;
+                xt.y = live1 ? zz - (yn.y - w.y + beta) * inv_mu : 0.0;   // the padding column of Xt stays zero
                 if (live1) {
                     dacc += dd * dd;
                     pacc += pd * pd;
                 }
             }
-            const size_t o = (size_t)i * ldn + j;
-            *reinterpret_cast<double2*>(Yn + o) = yn;
-            *reinterpret_cast<double2*>(Xt + o) = xt;
+            const unsigned ob = (unsigned)(i * ldn + j) * 8u;
+            *reinterpret_cast<double2*>(reinterpret_cast<char*>(Yn) + ob) = yn;
+            *reinterpret_cast<double2*>(reinterpret_cast<char*>(Xt) + ob) = xt;
         }
         // every thread moves on by the size of the round
         c += e1 - e0;
