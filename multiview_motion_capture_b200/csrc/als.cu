@@ -209,6 +209,7 @@ typedef const unsigned char* saddr_t;
 __device__ __forceinline__ saddr_t saddr_of(const double* p) { return reinterpret_cast<saddr_t>(p); }
 __device__ __forceinline__ double lds64(saddr_t a) { return *reinterpret_cast<const double*>(a); }
 __device__ __forceinline__ double2 lds128(saddr_t a) { return *reinterpret_cast<const double2*>(a); }
+__device__ __forceinline__ void sts128(saddr_t a, double2 v) { *reinterpret_cast<double2*>(const_cast<unsigned char*>(a)) = v; }
 #else
 typedef unsigned saddr_t;
 __device__ __forceinline__ saddr_t saddr_of(const double* p) { return smem_u32(p); }
@@ -221,6 +222,9 @@ __device__ __forceinline__ double2 lds128(saddr_t a) {
     double2 v;
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
     return v;
+}
+__device__ __forceinline__ void sts128(saddr_t a, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
 }
 #endif
 struct FragTab {
@@ -529,6 +533,7 @@ __device__ void invert_spd_blocked(double* Gg, int r, int ldr, double* sm) {
     const int nb = (r + 7) >> 3, np = 8 * nb, ld = np + 4;   // pitch = 4 (mod 8): every fragment pattern is conflict free
     double* Gs = sm;               // [np][ld]
     double* R = sm + np * ld;      // [8][ld]
+    const saddr_t Gs_s = saddr_of(Gs), R_s = saddr_of(R);
     {
         // thread (w, lane) brings elements (w + 8a, lane + 32b): all the global loads first (they are independent; in a
         // load-store loop each one waited for the previous store), then the stores
@@ -552,7 +557,7 @@ __device__ void invert_spd_blocked(double* Gg, int r, int ldr, double* sm) {
     gc.lap(PH_GJ_LOAD);
     for (int kb = 0; kb < nb; kb++) {
         // Pinv, in the accumulator layout
-        double2 pv = *reinterpret_cast<const double2*>(Gs + (8 * kb + ro) * ld + 8 * kb + 2 * q);
+        double2 pv = lds128(Gs_s + (unsigned)(((8 * kb + ro) * ld + 8 * kb + 2 * q) * 8));
         inv8_regs(pv.x, pv.y, lane);
         gc.lap(PH_GJ_INV8);
         // Pinv as A fragments (row ro, k = 4h + q) and as B fragments (k = 4h + q, column ro)
@@ -566,44 +571,50 @@ __device__ void invert_spd_blocked(double* Gg, int r, int ldr, double* sm) {
             const double b0 = __shfl_sync(MVMC_FULL, pv.x, sb), b1 = __shfl_sync(MVMC_FULL, pv.y, sb);
             pb[h] = (ro & 1) ? b1 : b0;
         }
-        // R[j] = Pinv G[kb, j]
+        // R[j] = Pinv G[kb, j]   (shared-space addresses, 64 bytes per 8-column block)
         for (int j = w; j < nb; j += AL_WARPS) {
             if (j == kb) continue;
             double c0 = 0.0, c1 = 0.0;
+            const saddr_t gb = Gs_s + (unsigned)(((8 * kb + q) * ld + 8 * j + ro) * 8);
 #pragma unroll
-            for (int h = 0; h < 2; h++) dmma(c0, c1, pa[h], Gs[(8 * kb + 4 * h + q) * ld + 8 * j + ro]);
+            for (int h = 0; h < 2; h++) dmma(c0, c1, pa[h], lds64(gb + (unsigned)(h * 4 * ld * 8)));
             double2 o;
             o.x = c0;
             o.y = c1;
-            *reinterpret_cast<double2*>(R + ro * ld + 8 * j + 2 * q) = o;
+            sts128(R_s + (unsigned)((ro * ld + 8 * j + 2 * q) * 8), o);
         }
         __syncthreads();
         gc.lap(PH_GJ_PANEL);
         for (int i = w; i < nb; i += AL_WARPS) {
             if (i == kb) {
                 for (int j = 0; j < nb; j++) {
-                    const double2 v = (j == kb) ? pv : *reinterpret_cast<const double2*>(R + ro * ld + 8 * j + 2 * q);
-                    *reinterpret_cast<double2*>(Gs + (8 * kb + ro) * ld + 8 * j + 2 * q) = v;
+                    const double2 v = (j == kb) ? pv : lds128(R_s + (unsigned)((ro * ld + 8 * j + 2 * q) * 8));
+                    sts128(Gs_s + (unsigned)(((8 * kb + ro) * ld + 8 * j + 2 * q) * 8), v);
                 }
             } else {
                 double nf[2];   // -G[i,kb] as A fragments
 #pragma unroll
-                for (int h = 0; h < 2; h++) nf[h] = -Gs[(8 * i + ro) * ld + 8 * kb + 4 * h + q];
+                for (int h = 0; h < 2; h++) nf[h] = -lds64(Gs_s + (unsigned)(((8 * i + ro) * ld + 8 * kb + 4 * h + q) * 8));
                 __syncwarp();   // the block G[i,kb] is overwritten below by lanes that hold other elements of it
-                for (int j = 0; j < nb; j++) {
-                    double2* cp = reinterpret_cast<double2*>(Gs + (8 * i + ro) * ld + 8 * j + 2 * q);
+                saddr_t cp = Gs_s + (unsigned)(((8 * i + ro) * ld + 2 * q) * 8);       // my two elements of block (i, 0)
+                saddr_t rp = R_s + (unsigned)((q * ld + ro) * 8);                       // R fragment element of block 0, h = 0
+                const unsigned rh = (unsigned)(4 * ld * 8);
+                for (int j = 0; j < nb; j++, cp += 64, rp += 64) {
                     double c0 = 0.0, c1 = 0.0;
+                    double b0 = pb[0], b1 = pb[1];
                     if (j != kb) {
-                        const double2 c = *cp;
+                        const double2 c = lds128(cp);
                         c0 = c.x;
                         c1 = c.y;
+                        b0 = lds64(rp);
+                        b1 = lds64(rp + rh);
                     }
-#pragma unroll
-                    for (int h = 0; h < 2; h++) dmma(c0, c1, nf[h], j == kb ? pb[h] : R[(4 * h + q) * ld + 8 * j + ro]);
+                    dmma(c0, c1, nf[0], b0);
+                    dmma(c0, c1, nf[1], b1);
                     double2 o;
                     o.x = c0;
                     o.y = c1;
-                    *cp = o;
+                    sts128(cp, o);
                 }
             }
         }
@@ -743,7 +754,8 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
                 double zz = x.x + y.x * inv_mu;                 // y / mu (mu is a power of two)
                 if (gi == gj.x) zz = 0.0;
                 if (i == j) zz = 1.0;
-                zz = fmin(fmax(zz, 0.0), 1.0);
+                zz = zz < 0.0 ? 0.0 : zz;
+                zz = zz > 1.0 ? 1.0 : zz;
                 const double pd = x.x - zz;
                 yn.x = y.x + mu * pd;
                 xt.x = zz - (yn.x - w.x + beta) * inv_mu;       // next iteration's Xt if mu stays
@@ -755,7 +767,8 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
                 double zz = x.y + y.y * inv_mu;
                 if (gi == gj.y) zz = 0.0;
                 if (i == j + 1) zz = 1.0;
-                zz = fmin(fmax(zz, 0.0), 1.0);
+                zz = zz < 0.0 ? 0.0 : zz;
+                zz = zz > 1.0 ? 1.0 : zz;
                 const double pd = x.y - zz;
                 yn.y = y.y + mu * pd;
                 xt.y = live1 ? zz - (yn.y - w.y + beta) * inv_mu : 0.0;   // the padding column of Xt stays zero
