@@ -820,7 +820,13 @@ __global__ void __launch_bounds__(AL_THREADS, AL_CTAS_)
           double beta, double tol, int max_iter) {
     MVMC_DYN_SMEM(unsigned char, smem_raw);
     // the swizzle pattern is a function of the shared-memory address: stages start on a 1024-byte boundary
+#ifdef MVMC_EMU
     double* smem = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+#else
+    // (an offset added to the __shared__ array, not integer arithmetic on a generic pointer: the compiler then knows that
+    //  everything derived from it is shared memory - 32-bit addresses, LDS / STS instead of generic loads and stores)
+    double* smem = reinterpret_cast<double*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+#endif
     const int b = order ? order[blockIdx.x] : blockIdx.x;
     const int* dg = dim_groups + b * (n_groups + 1);
     const int n = dg[n_groups];
