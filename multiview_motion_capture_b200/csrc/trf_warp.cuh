@@ -189,10 +189,12 @@ __device__ __noinline__ void warp_tridiagonalise(TrfWarp& s, int n) {
         double w0 = 0.0, w1 = 0.0;
         if (r0 < n) {
             const double* row = s.A + r0 * WS_LDA;
+#pragma unroll 4
             for (int c = k + 1; c < n; c++) w0 = fma(row[c], s.u[c], w0);
         }
         if (r1 < n) {
             const double* row = s.A + r1 * WS_LDA;
+#pragma unroll 4
             for (int c = k + 1; c < n; c++) w1 = fma(row[c], s.u[c], w1);
         }
         w0 *= tau;
@@ -207,10 +209,12 @@ __device__ __noinline__ void warp_tridiagonalise(TrfWarp& s, int n) {
         // A22 -= v w^T + w v^T
         if (r0 < n) {
             double* row = s.A + r0 * WS_LDA;
+#pragma unroll 4
             for (int c = k + 1; c < n; c++) row[c] = row[c] - v0 * s.w[c] - w0 * s.u[c];
         }
         if (r1 < n) {
             double* row = s.A + r1 * WS_LDA;
+#pragma unroll 4
             for (int c = k + 1; c < n; c++) row[c] = row[c] - v1 * s.w[c] - w1 * s.u[c];
         }
         __syncwarp();
