@@ -111,6 +111,8 @@ __constant__ unsigned char c_fk_psel[MVMC_N_B18] = {0, 1, 0, 0, 1, 0, 0, 1, 0, 2
 
 // Rloc[j][9] <- local rotation of joint j at pose x, non-leaf joints only (lane j computes joint j)
 __device__ __noinline__ void local_rots(const double* x, double* Rloc) {
+    MVMC_ASSUME_SHARED(x);
+    MVMC_ASSUME_SHARED(Rloc);
     const int j = threadIdx.x & 31;
     if (j < MVMC_N_B18 && !c_skel.leaf[j]) {
         double m[9];
@@ -126,6 +128,8 @@ __device__ __noinline__ void local_rots(const double* x, double* Rloc) {
 // whole kernel. `Rloc` must hold local_rots(x).
 __device__ __noinline__ void fk_store(const double* x, const double* Rloc, int prm, double xp, double* out, int stride,
                                       bool ik_slots, bool on) {
+    MVMC_ASSUME_SHARED(x);
+    MVMC_ASSUME_SHARED(Rloc);
     auto getx = [&](int i) { return i == prm ? xp : x[i]; };
     // the one local rotation this call overrides (computed by every lane to stay convergent; unused when jo < 0)
     const int jo = (prm >= 3 && prm < 57) ? (prm - 3) / 3 : -1;
@@ -207,6 +211,12 @@ struct IkRes {
     __device__ int chunk_row0(int c) const { return 8 * c; }
 
     __device__ __noinline__ void eval(const double* x, double* f) {
+        MVMC_ASSUME_SHARED(x);
+        MVMC_ASSUME_SHARED(f);
+        MVMC_ASSUME_SHARED(obs);
+        MVMC_ASSUME_SHARED(P);
+        MVMC_ASSUME_SHARED(posb);
+        MVMC_ASSUME_SHARED(Rloc);
         const int lane = threadIdx.x & 31;
         double* pb = posb;
         // the chain is evaluated redundantly by every lane (uniform control flow); lane 0 parks the positions
@@ -240,6 +250,10 @@ struct IkRes {
         }
     }
     __device__ __noinline__ void fd_chunk(TrfWarp& s, int ncol, int ch, const double* f) {
+        MVMC_ASSUME_SHARED(&s);
+        MVMC_ASSUME_SHARED(f);
+        MVMC_ASSUME_SHARED(obs);
+        MVMC_ASSUME_SHARED(P);
         const int lane = threadIdx.x & 31;
         const int v = ch >> 2, q0 = (ch & 3) * 4;
         const double* S = s.A;

@@ -28,6 +28,13 @@ constexpr double kSqrtEps = 1.4901161193847656e-08;   // sqrt(2^-52)
 constexpr double kEps = 2.220446049250313e-16;
 constexpr double kDblMax = 1.79769313486231570e308;
 
+// pointers that cross a __noinline__ call lose their address space; the solver's workspaces are always shared memory
+#ifdef MVMC_EMU
+#define MVMC_ASSUME_SHARED(p) ((void)0)
+#else
+#define MVMC_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#endif
+
 #ifdef MVMC_EMU
 #define DMUL(a, b) ((a) * (b))
 #define DSUB(a, b) ((a) - (b))
@@ -75,6 +82,8 @@ __device__ __forceinline__ void lane_tile(int lane, int& ti, int& tj) {
 //   void fd_chunk(TrfWarp& s, int ncol, int c, const double* f);   fill s.Jc[r][col] = (r'(x + h e_col) - f) / dx for chunk c
 template <class Res>
 __device__ __noinline__ void trf_jacobian(TrfWarp& s, Res& res, int ncol, const double* f) {
+    MVMC_ASSUME_SHARED(&s);
+    MVMC_ASSUME_SHARED(f);
     const int lane = threadIdx.x & 31;
     for (int e = lane; e < WS_CH * WS_LDJ; e += 32) s.Jc[e] = 0.0;
     // SciPy's 2-point rule: h = sqrt(eps) * sign(x) * max(1, |x|) with sign(0) = +1, dx = (x + h) - x
@@ -151,6 +160,7 @@ __device__ __noinline__ void trf_jacobian(TrfWarp& s, Res& res, int ncol, const 
 // A (n x n, symmetric, full storage) -> tridiagonal T = Q^T A Q: d[0..n), e[0..n-1); reflector k is stored in
 // A[k+2.., k] (v[k+1] = 1 implicit) with s.tau[k]. LAPACK dsytd2 (lower) arithmetic, one warp.
 __device__ __noinline__ void warp_tridiagonalise(TrfWarp& s, int n) {
+    MVMC_ASSUME_SHARED(&s);
     const int lane = threadIdx.x & 31;
     for (int k = 0; k + 1 < n; k++) {
         const int r0 = k + 1 + lane, r1 = r0 + 32;
@@ -228,6 +238,8 @@ __device__ __noinline__ void warp_tridiagonalise(TrfWarp& s, int n) {
 
 // y <- H_k y for k = 0..n-3 (forward = true: y <- Q^T y) or k = n-3..0 (y <- Q y). y in shared memory.
 __device__ __noinline__ void warp_apply_q(const TrfWarp& s, int n, double* y, bool transpose) {
+    MVMC_ASSUME_SHARED(&s);
+    MVMC_ASSUME_SHARED(y);
     const int lane = threadIdx.x & 31;
     for (int q = 0; q + 2 < n; q++) {
         const int k = transpose ? q : n - 3 - q;
@@ -346,6 +358,7 @@ __device__ __forceinline__ void pcr_resolve(const PcrFactors& F, double& r0, dou
 // Out: s.pt (step in the Q basis, already rescaled), returns alpha; sc[1] = ||p||, sc[2] = predicted reduction.
 // Every lane computes the same scalars (butterfly reductions), so the control flow is warp uniform.
 __device__ __noinline__ double trf_subproblem(TrfWarp& s, int n, double delta, double alpha, bool full_rank) {
+    MVMC_ASSUME_SHARED(&s);
     const int lane = threadIdx.x & 31;
     const int i0 = lane, i1 = lane + 32;
     const double g0 = i0 < n ? s.gt[i0] : 0.0, g1 = i1 < n ? s.gt[i1] : 0.0;
