@@ -249,7 +249,7 @@ struct IkRes {
             fk_store(s.x, Rloc, prm, xp, S + c, WS_NC, true, on);
         }
     }
-    __device__ __noinline__ void fd_chunk(TrfWarp& s, int ncol, int ch, const double* f) {
+    __device__ __forceinline__ void fd_chunk(TrfWarp& s, int ncol, int ch, const double* f) {
         MVMC_ASSUME_SHARED(&s);
         MVMC_ASSUME_SHARED(f);
         MVMC_ASSUME_SHARED(obs);
