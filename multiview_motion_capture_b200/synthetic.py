@@ -31,6 +31,28 @@ GOLDEN_SCENES = {
     "c8p12": dict(n_views=8, n_people=12, n_frames=3, seed=13, max_poses=12),
 }
 
+# tracked (steady-state) goldens at the BASELINE shapes: the reference's tracker is warm-started from the ground truth
+# of frame first-1 (oracle/make_golden.py warm), then runs frames first..last. `shelf` = the five Shelf cameras.
+WARM_SCENES = {
+    "c8p32": dict(kw=dict(n_views=8, n_people=32, n_frames=9, seed=1000, clip_idx=100000), first=3, last=8),
+    "c8p16": dict(kw=dict(n_views=8, n_people=16, n_frames=11, seed=1000, clip_idx=200000), first=3, last=10),
+    "c8p12": dict(kw=dict(n_views=8, n_people=12, n_frames=10, seed=13, max_poses=12), first=3, last=9),
+    "c5p4": dict(kw=dict(n_views=5, n_people=4, n_frames=14, seed=1000, clip_idx=300000), first=3, last=13, shelf=True),
+}
+
+
+def make_warm_scene(name, shelf_calib=None):
+    spec = WARM_SCENES[name]
+    kw = dict(spec["kw"])
+    if spec.get("shelf"):
+        if shelf_calib is None:
+            import os
+            g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                                     "shelf_inputs.npz"))
+            shelf_calib = (g["K"], g["RT"], g["img_wh"][0])
+        kw["shelf_calib"] = shelf_calib
+    return make_clip(**kw)
+
 
 def body25_to_coco(kps25):
     """OpenPose BODY_25 -> COCO-17 joint gather (reference: src/pose_def.py:262-270)."""

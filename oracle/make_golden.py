@@ -168,7 +168,36 @@ def calibs_from_packed(ref, packed):
     return calibs
 
 
-def run_reference(packed, first_frame, last_frame, verbose=True):
+def warm_start_tracks(ref, rec, tracker, packed, f0):
+    """Seed the reference's tracker with one Confirmed tracklet per person whose last PoseShapeParam is the generator's
+    ground truth at frame f0 (the steady state bench.py measures; a crowded scene's own frame 1 is the reference's
+    non-converging no-track case). The tracklets are real MvTracklet instances built without running __init__'s birth
+    solve; everything the reference then computes on them (predict, association, update, lifecycle) is its own code."""
+    mc, ik = ref.mc, ref.ik
+    skel = tracker.skeleton
+    init = dict(ids=[], param=[], joints=[])
+    n_people = packed["gt_root"].shape[1]
+    for pi in range(n_people):
+        prm = ik.PoseShapeParam(packed["gt_root"][f0, pi].copy(), packed["gt_euler"][f0, pi].copy(),
+                                skel.ref_side_bone_lens.copy() * packed["gt_scale"][pi])
+        locs, _ = ik.foward_kinematics(skel, prm)
+        pose = ref.pose_def.Pose(ref.pose_def.KpsFormat.BASIC_18, keypoints=locs, keypoints_score=np.ones((len(locs), 1)),
+                                 box=None)
+        t = object.__new__(mc.MvTracklet)
+        t.frame_idxs, t.cam_poses_2d, t.cam_projs, t.cam_calibs = [f0], [[]], [[]], [[]]
+        t.skel = skel
+        t.poses = [(f0, prm, pose)]
+        t.time_since_update, t.hits, t.state, t.max_age, t.n_inits = 0, 3, mc.TrackState.Confirmed, 0, 3
+        t.golden_id = rec.next_track_id
+        rec.next_track_id += 1
+        tracker.tracklets.append(t)
+        init["ids"].append(t.golden_id)
+        init["param"].append(np.concatenate([prm.root, prm.euler_angles.reshape(-1), prm.bone_lens]))
+        init["joints"].append(np.array(locs))
+    return init
+
+
+def run_reference(packed, first_frame, last_frame, verbose=True, warm=False):
     """Drive the reference tracker over frames [first_frame, last_frame] and record goldens."""
     ref = ref_shim.load()
     rec = Recorder(ref)
@@ -176,6 +205,12 @@ def run_reference(packed, first_frame, last_frame, verbose=True):
     calibs = calibs_from_packed(ref, packed)
     tracker = mc.MvTracker(ref.ik.load_skeleton())
     gold = {}
+    if warm:
+        init = warm_start_tracks(ref, rec, tracker, packed, first_frame - 1)
+        gold["init_ids"] = np.array(init["ids"], dtype=np.int32)
+        gold["init_param"] = np.array(init["param"])
+        gold["init_joints"] = np.array(init["joints"])
+        gold["init_state"] = np.array([[mc.TrackState.Confirmed.value, 3, 0, 1]] * len(init["ids"]), dtype=np.int32)
     times = []
     import contextlib
     import io
@@ -287,11 +322,29 @@ def _pose_ids(tlet, d_frames):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["shelf", "synth"])
+    ap.add_argument("what", choices=["shelf", "synth", "warm"])
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--scene", default=None, help="warm: one scene of synthetic.WARM_SCENES (default all)")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
+    if args.what == "warm":
+        # tracked (steady-state) frames at the BASELINE shapes: the reference's tracker is seeded from the generator's
+        # ground truth at frame `first - 1` (warm_start_tracks) and then runs frames first..last itself
+        sys.path.insert(0, ROOT)
+        from multiview_motion_capture_b200 import synthetic
+        for name, spec in synthetic.WARM_SCENES.items():
+            if args.scene and name != args.scene:
+                continue
+            packed = synthetic.make_warm_scene(name)
+            first, last = spec["first"], spec["last"]
+            slim = {k: (v[:last + 1] if k in ("kps25", "n_pose", "gt_person", "gt_joints", "gt_root", "gt_euler") else v)
+                    for k, v in packed.items()}
+            np.savez_compressed(os.path.join(GOLD, f"warm_{name}_inputs.npz"), **slim)
+            gold, _ = run_reference(packed, first, last, warm=True)
+            np.savez_compressed(os.path.join(GOLD, f"warm_{name}_ref.npz"), **gold)
+            print("wrote warm", name, "total s:", gold["frame_times_s"].sum())
+        return
     if args.what == "shelf":
         packed = pack_shelf_inputs()
         np.savez_compressed(os.path.join(GOLD, "shelf_inputs.npz"), **packed)

@@ -10,8 +10,26 @@ EMU_LIB = os.path.join(ROOT, "tests", "emu", "libmvmc_emu.so")
 _cache = {}
 
 
+WARM = [("warm_c5p4", 4, 8), ("warm_c8p12", 12, 16), ("warm_c8p16", 16, 24), ("warm_c8p32", 32, 40)]   # (name, Pmax, Tmax)
+
+
+def oracle_tracker_from_golden(name):
+    """An oracle.Tracker for a golden scene; a warm golden's tracker is seeded with the same tracks the reference's was."""
+    import mvmc_oracle as o
+    inp, g = golden(name)
+    trk = o.Tracker(o.projections(inp["K"], inp["RT"]), inp["K"], inp["RT"])
+    if "init_ids" in g.files:
+        f0 = int(g["first_frame"]) - 1
+        for i, tid in enumerate(g["init_ids"].tolist()):
+            prm = o.PoseParam.unpack(g["init_param"][i].copy())
+            trk.tracks.append(o.Track(tid, [f0], [prm], [g["init_joints"][i].copy()], [[]], state=o.CONFIRMED, hits=3))
+        trk.next_id = len(trk.tracks)
+    return trk
+
+
 def golden(name):
-    """(inputs, reference outputs) of a golden scene: 'shelf', 'synth_c4p3', 'synth_c8p6', 'synth_c8p12'."""
+    """(inputs, reference outputs) of a golden scene: 'shelf', 'synth_c4p3', 'synth_c8p6', 'synth_c8p12', and the
+    warm-started 'warm_c5p4', 'warm_c8p12', 'warm_c8p16', 'warm_c8p32' (tracked frames at the BASELINE shapes)."""
     if name not in _cache:
         _cache[name] = (np.load(os.path.join(GOLD, f"{name}_inputs.npz")), np.load(os.path.join(GOLD, f"{name}_ref.npz")))
     return _cache[name]
@@ -30,6 +48,13 @@ class GoldenTable:
         self.g = ref
         self.table = {}
         self.frame = int(ref["first_frame"]) - 1
+        self.init_ids = []
+        if "init_ids" in ref.files:   # warm-started golden (oracle/make_golden.py warm): the tracker was seeded with these
+            self.init_ids = ref["init_ids"].tolist()
+            for i, tid in enumerate(self.init_ids):
+                st = ref["init_state"][i]
+                self.table[tid] = dict(param=ref["init_param"][i].copy(), joints=ref["init_joints"][i].copy(),
+                                       state=int(st[0]), hits=int(st[1]), tsu=int(st[2]), len=int(st[3]))
 
     def advance(self, f):
         """Fold the reference's outputs of frame f into the table."""
@@ -81,7 +106,8 @@ class GoldenTable:
             a["param"][:, i] = e["param"]
             a["joints"][:, i] = e["joints"].reshape(-1)
         # ids are handed out in creation order, so the next id is one past every id ever seen
-        seen = [int(x) for q in range(int(self.g["first_frame"]), f) for x in self.g[fkey(q) + "alive_after"].tolist()]
+        seen = list(self.init_ids) + [int(x) for q in range(int(self.g["first_frame"]), f)
+                                      for x in self.g[fkey(q) + "alive_after"].tolist()]
         a["next_id"] = np.full(B, (max(seen) + 1) if seen else 0, np.int32)
         return a
 

@@ -96,3 +96,85 @@ def check_clip_streams_equal_clip_batch(dev, name="synth_c4p3", Pmax=4, Tmax=8, 
         assert len({ref[b].tobytes() for b in range(B)}) > 1, "the clips of this test must differ"
     cb.close()
     cs.close()
+
+
+def _oracle_table(trk, Tmax):
+    """The oracle tracker's alive-track table packed for ClipBatch.set_tracks (one clip)."""
+    a = dict(n_trk=np.array([len(trk.tracks)], np.int32), ids=np.zeros((1, Tmax), np.int32), state=np.zeros((1, Tmax), np.int32),
+             hits=np.zeros((1, Tmax), np.int32), tsu=np.zeros((1, Tmax), np.int32), length=np.zeros((1, Tmax), np.int32),
+             param=np.zeros((1, Tmax, 68)), joints=np.zeros((1, Tmax, 54)), next_id=np.array([trk.next_id], np.int32))
+    assert len(trk.tracks) <= Tmax
+    for i, t in enumerate(trk.tracks):
+        a["ids"][0, i], a["state"][0, i], a["hits"][0, i] = t.track_id, t.state, t.hits
+        a["tsu"][0, i], a["length"][0, i] = t.time_since_update, len(t)
+        a["param"][0, i] = t.params[-1].pack()
+        a["joints"][0, i] = t.joints[-1].reshape(-1)
+    return a
+
+
+def run_side_by_side_with_oracle(dev, n_views, n_people, n_clips, n_frames, seed, Tmax, first_frame=3, shelf=False):
+    """bench.py's workload, checked: `n_clips` distinct synthetic clips of the benchmarked shape, the oracle's tracker
+    seeded from the generator's ground truth exactly as bench.py's CPU arm is (`_cpu_worker`), then `n_frames` tracked
+    frames with the CUDA pipeline teacher-forced from the oracle's table before every frame. Asserts per clip-frame:
+    kept poses / index layout identical, dst <= 1e-7 px, sim <= 1e-9, X_bin and the ALS stopping iteration bit-exact,
+    matched (view, pose) sets, births, deaths, track ids and lifecycle counters identical. Returns the IK differences."""
+    from multiview_motion_capture_b200 import synthetic as S
+    from multiview_motion_capture_b200.clips import ClipBatch
+    from helpers import golden
+    st = dict(frames=0, dst=0.0, sim=0.0, dj=[], dparam=[], dcost=[], n=[], iters=[], nfev_same=0, solves=0)
+    shelf_calib = None
+    if shelf:
+        gi, _ = golden("shelf")
+        shelf_calib = (gi["K"], gi["RT"], gi["img_wh"][0])
+    for ci in range(n_clips):
+        c = S.make_clip(n_views, n_people, first_frame + n_frames, seed=seed, clip_idx=ci, shelf_calib=shelf_calib)
+        C = len(c["K"])
+        kps = S.body25_to_coco(c["kps25"])
+        trk = o.Tracker(o.projections(c["K"], c["RT"]), c["K"], c["RT"])
+        f0 = first_frame - 1
+        for pi in range(n_people):
+            prm = o.PoseParam(c["gt_root"][f0, pi].copy(), c["gt_euler"][f0, pi].copy(), trk.skel.side_bone_lens * c["gt_scale"][pi])
+            joints, _ = o.forward_kinematics(trk.skel, prm.root, prm.euler, prm.bone_lens)
+            trk.tracks.append(o.Track(pi, [f0], [prm], [joints], [[]], state=o.CONFIRMED, hits=3))
+        trk.next_id = n_people
+        cb = ClipBatch(1, C, n_people, max_tracks=Tmax, max_new=n_people, device=dev)
+        cb.set_calib(c["K"][None], c["RT"][None])
+        for f in range(first_frame, first_frame + n_frames):
+            cb.set_tracks(**_oracle_table(trk, Tmax))
+            before = [(t.track_id, t.params[-1]) for t in trk.tracks]
+            a = trk.step(f, kps[f], c["n_pose"][f])
+            rec = cb.step(kps[f][None], c["n_pose"][f][None], f)[0].copy()
+            dst, sim, xb, dg = cb.read_matrices(0)
+            tag = (n_views, n_people, ci, f)
+            assert dst.shape == a.dst.shape, tag
+            st["dst"] = max(st["dst"], float(np.abs(dst - a.dst).max()))
+            st["sim"] = max(st["sim"], float(np.abs(sim - a.sim).max()))
+            assert np.abs(dst - a.dst).max() <= 1e-7 and np.abs(sim - a.sim).max() <= 1e-9, tag
+            assert np.array_equal(xb, a.x_bin), tag + ("X_bin",)
+            assert int(rec["als_iters"]) == a.n_iter, tag + ("ALS iterations", int(rec["als_iters"]), a.n_iter)
+            n_alive = int(rec["n_alive"])
+            tr = rec["tracks"][:n_alive]
+            assert tr["track_id"].tolist() == [t.track_id for t in trk.tracks], tag + ("track ids",)
+            state = np.stack([tr["state"], tr["hits"], tr["time_since_update"], tr["length"]], 1).reshape(-1, 4)
+            assert np.array_equal(state, np.array([[t.state, t.hits, t.time_since_update, len(t)] for t in trk.tracks]).reshape(-1, 4)), tag
+            assert sorted(rec["died_ids"][:rec["n_died"]].tolist()) == sorted(t.track_id for t in trk.dead if t.frame_idxs[-1] < f
+                                                                               and t.track_id in [b[0] for b in before]), tag
+            assert int(rec["n_dup_view"]) == a.n_dup_view, tag
+            upd_o = [t for t in trk.tracks if t.frame_idxs[-1] == f]
+            upd = tr[tr["updated"] > 0]
+            assert upd["track_id"].tolist() == [t.track_id for t in upd_o], tag
+            log = [e for e in trk.solve_log if e[0] in ("ik1", "ik2")]
+            for u, (t, ot) in enumerate(zip(upd, upd_o)):
+                sel = [tuple(x) for x in t["sel"][:t["n_sel"]].tolist()]
+                assert sel == [tuple(x) for x in ot.views[-1]], tag + ("matched (view, pose)", u)
+                st["dj"].append(float(np.abs(t["joints"].reshape(18, 3) - ot.joints[-1]).max()))
+                st["dparam"].append(float(np.abs(t["param"] - ot.params[-1].pack()).max()))
+                r1, r2 = log[2 * u][2], log[2 * u + 1][2]
+                st["solves"] += 2
+                st["nfev_same"] += int(t["nfev"][0] == r1.nfev) + int(t["nfev"][1] == r2.nfev)
+                st["dcost"].append(float(abs(t["cost"][1] - r2.cost) / max(r2.cost, 1e-300)))
+            st["frames"] += 1
+            st["n"].append(int(dg[-1]))
+            st["iters"].append(a.n_iter)
+        cb.close()
+    return st

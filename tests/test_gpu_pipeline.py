@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import mvmc_oracle as o
-from helpers import GoldenTable, fkey, golden, golden_matches, pad_poses
+from helpers import WARM, GoldenTable, fkey, golden, golden_matches, pad_poses
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -34,6 +34,40 @@ def test_synthetic_teacher_forced(cuda, name, Pmax, Tmax):
     ok = st["frames"] - sum(1 for _, same in st["unstable_frames"] if not same)
     print(name, "unstable no-track frames (frame, X_bin identical):", st["unstable_frames"])
     assert st["xbin"] >= ok and st["alive"] >= ok and st["upd"] >= ok
+
+
+@pytest.mark.parametrize("name,Pmax,Tmax", WARM)
+def test_warm_goldens_teacher_forced(cuda, name, Pmax, Tmax):
+    """Tracked frames at the BASELINE shapes (8 x 32: 6 frames, 8 x 16: 8, 8 x 12: 7, Shelf-shaped 5 x 4: 11) recorded from
+    the REAL reference warm-started from ground truth (oracle/make_golden.py warm): X_bin, the ALS stopping iteration,
+    matched (view, pose) sets, track ids and lifecycle counters identical on every frame; IK inside the envelope."""
+    st = _run(name, Pmax, Tmax, forced=True, max_new=Pmax)
+    dj = np.array(st["dj"])
+    print(f"PARITY {name} vs reference, teacher-forced: frames {st['frames']} X_bin {st['xbin']} ALS-iterations {st['iters']} "
+          f"track-ids {st['alive']} updated-sets {st['upd']}; IK joints median {np.median(dj)*1e3:.2f} mm p90 "
+          f"{np.percentile(dj, 90)*1e3:.2f} mm max {dj.max()*1e3:.2f} mm over {len(dj)} solves")
+    assert st["unstable_frames"] == []
+    assert st["xbin"] == st["iters"] == st["alive"] == st["upd"] == st["frames"]
+    assert np.median(dj) <= 7e-3
+
+
+@pytest.mark.parametrize("views,people,clips,frames,Tmax,shelf", [(8, 32, 3, 5, 40, False), (8, 16, 3, 6, 24, False),
+                                                                 (5, 4, 4, 12, 8, True)])
+def test_benchmarked_shapes_side_by_side_with_oracle(cuda, views, people, clips, frames, Tmax, shelf):
+    """bench.py's own workload with the oracle beside it: distinct clips seeded like bench.py's CPU arm,
+    teacher-forced every frame; everything discrete bit-exact (asserted inside), IK reported against the envelope."""
+    from pipeline_checks import run_side_by_side_with_oracle
+    st = run_side_by_side_with_oracle(DEV, views, people, clips, frames, seed=1000, Tmax=Tmax, shelf=shelf)
+    dj, dp = np.array(st["dj"]), np.array(st["dparam"])
+    print(f"PARITY {views}x{people} vs oracle, {clips} clips x {frames} tracked frames = {st['frames']} clip-frames: n "
+          f"{min(st['n'])}..{max(st['n'])}, ALS iterations {min(st['iters'])}..{max(st['iters'])} all identical, X_bin identical, "
+          f"ids/lifecycle/matches identical; max |dst| diff {st['dst']:.2e} px, max |sim| diff {st['sim']:.2e}; IK: "
+          f"{st['solves']} solves, nfev identical on {st['nfev_same']}, joints median {np.median(dj)*1e3:.2f} mm p90 "
+          f"{np.percentile(dj, 90)*1e3:.2f} mm, params median {np.median(dp):.3f} p90 {np.percentile(dp, 90):.3f} (rad|m), "
+          f"relative cost diff median {np.median(st['dcost']):.2e}")
+    assert st["frames"] == clips * frames
+    assert np.median(dj) <= 7e-3
+    assert st["nfev_same"] >= 0.9 * st["solves"]
 
 
 def test_shelf_free_running(cuda):

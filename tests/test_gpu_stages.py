@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import stage_checks as SC
-from helpers import golden
+from helpers import WARM, golden
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -42,6 +42,18 @@ def test_als_synthetic(cuda, name, Pmax, Tmax):
     fr = _frames(name)
     N = -(-(Tmax + 8 * Pmax) // 32) * 32
     assert SC.check_als(DEV, name, fr, N=N, rmax=2 * max(Pmax, Tmax)) == len(fr)
+
+
+@pytest.mark.parametrize("name,Pmax,Tmax", WARM)
+def test_affinity_and_als_warm_goldens(cuda, name, Pmax, Tmax):
+    """Stage level, on the reference's own tracked frames at the BASELINE shapes (8 x 32: n up to ~230, r = 64 - the tile
+    grid and blocked inverse the benchmark runs): dst <= 1e-7 px; X_bin and the stopping iteration bit-exact."""
+    fr = _frames(name)
+    worst = SC.check_affinity(DEV, name, fr, Pmax=Pmax, Tmax=Tmax)
+    N = -(-(Tmax + 8 * Pmax) // 32) * 32
+    assert SC.check_als(DEV, name, fr, N=N, rmax=2 * max(Pmax, Tmax)) == len(fr)
+    SC.check_assign(DEV, name, fr, Pmax=Pmax, Tmax=Tmax, max_new=Pmax)
+    print(f"PARITY {name} stages vs reference: {len(fr)} frames, max |dst - reference| {worst:.2e} px, X_bin + iterations identical")
 
 
 def test_assign_shelf_all_frames(cuda):
