@@ -332,12 +332,133 @@ __global__ void __launch_bounds__(AFF_TILE* AFF_TILE)
 }
 
 // ------------------------------------------------------------------------------------------------
+// NumPy's float32 arithmetic, restated (the reference's no-track affinity, mv_math_util.py:348-350, is float32 NumPy and
+// its last bit decides assignments when the matcher does not converge). None of this is in /root/reference: it is NumPy
+// (requirements.txt numpy==1.17.4; container 2.3.5), restated from its published algorithms and checked bit for bit against
+// the container's NumPy (tests/test_oracle_golden.py::test_numpy_float32_restatement, tests/stage_checks.py):
+//   * add.reduce over a contiguous float32 array = pairwise summation (numpy/_core/src/umath/loops_utils.h.src
+//     pairwise_sum): blocks of <= 128 elements summed with 8 strided accumulators, combined as ((r0+r1)+(r2+r3))+((r4+r5)+
+//     (r6+r7)) plus a sequential remainder; longer ranges split at n/2 rounded down to a multiple of 8;
+//   * mean = sum / count, var = sum((x - mean)^2) / count, std = sqrt(var), all float32 (numpy/_core/_methods.py _mean, _var);
+//   * exp (numpy/_core/src/umath/loops_exponent_log.dispatch.c.src, AVX2/AVX512F kernel): k = round(x log2 e) by the
+//     1.5 2^23 trick, Cody-Waite reduction r = x - k ln2 in two FMAs, a (5,2) rational minimax in r by Horner FMAs, one
+//     division, scaling by 2^k.
+// Every operation is an explicitly rounded intrinsic so that nvcc cannot contract a multiply and an add into an FMA where
+// NumPy has two roundings (or the other way round).
+// ------------------------------------------------------------------------------------------------
+namespace np32 {
+constexpr int MAX_LEAVES = 2048;   // n*n <= 102400 elements, leaves hold 64..128
+#ifdef MVMC_EMU
+__device__ __forceinline__ float fadd(float a, float b) { volatile float r = a + b; return r; }
+__device__ __forceinline__ float fsub(float a, float b) { volatile float r = a - b; return r; }
+__device__ __forceinline__ float fmul(float a, float b) { volatile float r = a * b; return r; }
+__device__ __forceinline__ float fdiv(float a, float b) { volatile float r = a / b; return r; }
+__device__ __forceinline__ float fsqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ float ffma(float a, float b, float c) { return fmaf(a, b, c); }
+#else
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#endif
+
+__device__ __forceinline__ float exp(float x) {
+    if (x != x) return x;
+    if (x > 88.72283905206835f) return INFINITY;
+    if (x < -103.97208121f) return 0.0f;
+    const float magic = 12582912.0f;   // 1.5 * 2^23
+    float k = fmul(x, 1.442695040888963407359924681001892137f);
+    k = fsub(fadd(k, magic), magic);
+    float r = ffma(k, -6.93145752e-1f, x);
+    r = ffma(k, -1.42860677e-6f, r);
+    float num = ffma(5.082762527590693718096e-04f, r, 6.757896990527504603057e-03f);
+    num = ffma(num, r, 5.114512081637298353406e-02f);
+    num = ffma(num, r, 2.473615434895520810817e-01f);
+    num = ffma(num, r, 7.257664613233124478488e-01f);
+    num = ffma(num, r, 9.999999999980870924916e-01f);
+    float den = ffma(2.159509375685829852307e-02f, r, -2.742335390411667452936e-01f);
+    den = ffma(den, r, 1.0f);
+    return ldexpf(fdiv(num, den), (int)k);
+}
+
+// element e of the n x n matrix (row pitch N doubles, values are float32), optionally (x - mean)^2
+__device__ __forceinline__ float elem(const double* D, int n, int N, int e, float mean, bool sq) {
+    const float v = (float)D[(size_t)(e / n) * N + (e % n)];
+    if (!sq) return v;
+    const float x = fsub(v, mean);
+    return fmul(x, x);
+}
+__device__ float leaf_sum(const double* D, int n, int N, int off, int len, float mean, bool sq) {
+    if (len < 8) {
+        float res = 0.0f;
+        for (int i = 0; i < len; i++) res = fadd(res, elem(D, n, N, off + i, mean, sq));
+        return res;
+    }
+    float r[8];
+    for (int j = 0; j < 8; j++) r[j] = elem(D, n, N, off + j, mean, sq);
+    int i = 8;
+    for (; i < len - (len % 8); i += 8)
+        for (int j = 0; j < 8; j++) r[j] = fadd(r[j], elem(D, n, N, off + i + j, mean, sq));
+    float res = fadd(fadd(fadd(r[0], r[1]), fadd(r[2], r[3])), fadd(fadd(r[4], r[5]), fadd(r[6], r[7])));
+    for (; i < len; i++) res = fadd(res, elem(D, n, N, off + i, mean, sq));
+    return res;
+}
+// leaves of the pairwise recursion over [off, off + len), left to right
+__device__ void split(int off, int len, int* leaf, int& nl) {
+    if (len <= 128) {
+        leaf[nl++] = off;
+        return;
+    }
+    int n2 = len / 2;
+    n2 -= n2 % 8;
+    split(off, n2, leaf, nl);
+    split(off + n2, len - n2, leaf, nl);
+}
+__device__ float combine(int len, const float* sum, int& k) {
+    if (len <= 128) return sum[k++];
+    int n2 = len / 2;
+    n2 -= n2 % 8;
+    const float a = combine(n2, sum, k);
+    const float b = combine(len - n2, sum, k);
+    return fadd(a, b);
+}
+// np.add.reduce of the flattened matrix (or of (x - mean)^2), float32; every thread of the CTA calls it and gets the result
+__device__ float reduce_sum(const double* D, int n, int N, float mean, bool sq, int* s_leaf, float* s_sum, int& s_nleaf) {
+    const int total = n * n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nl = 0;
+        split(0, total, s_leaf, nl);
+        s_leaf[nl] = total;
+        s_nleaf = nl;
+    }
+    __syncthreads();
+    const int nl = s_nleaf;
+    for (int q = threadIdx.x; q < nl; q += blockDim.x) s_sum[q] = leaf_sum(D, n, N, s_leaf[q], s_leaf[q + 1] - s_leaf[q], mean, sq);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int k = 0;
+        s_sum[0] = fadd(0.0f, combine(total, s_sum, k));   // the reduction starts from add's identity
+    }
+    __syncthreads();
+    const float r = s_sum[0];
+    __syncthreads();
+    return r;
+}
+}  // namespace np32
+
+// ------------------------------------------------------------------------------------------------
 // NaN fill + similarity. One CTA per clip (n*n <= 102400 entries).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     k_simfill(const int* __restrict__ n_trk, const int* __restrict__ dim_groups, int C, int N, double* __restrict__ dst,
               double* __restrict__ sim) {
     __shared__ double scratch[32];
+    __shared__ int s_leaf[np32::MAX_LEAVES + 1];
+    __shared__ float s_sum[np32::MAX_LEAVES];
+    __shared__ int s_nleaf;
     const int b = blockIdx.x;
     const int n = dim_groups[b * (C + 2) + C + 1];
     double* D = dst + (size_t)b * N * N;
@@ -365,22 +486,17 @@ __global__ void __launch_bounds__(256)
             S[o] = s;
         }
     } else {
-        // affinity = sigmoid(5 * -(D - mean)/std) in float32 (mv_math_util.py:348-350)
-        double sum = 0.0;
-        for (int e = threadIdx.x; e < n * n; e += blockDim.x) sum += D[(size_t)(e / n) * N + (e % n)];
-        sum = block_sum(sum, scratch);
-        const float mean = (float)(sum / ((double)n * n));
-        double sq = 0.0;
-        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-            const float x = (float)D[(size_t)(e / n) * N + (e % n)] - mean;
-            sq += (double)(x * x);
-        }
-        sq = block_sum(sq, scratch);
-        const float sd = sqrtf((float)(sq / ((double)n * n)));
-        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        // affinity = sigmoid(5 * -(D - mean)/std) in float32 (mv_math_util.py:348-350), bit for bit what NumPy computes
+        // (np32 below): pairwise float32 sums for mean and std, NumPy's own float32 exp.
+        const int nn = n * n;
+        const float cnt = (float)nn;
+        const float mean = np32::fdiv(np32::reduce_sum(D, n, N, 0.0f, false, s_leaf, s_sum, s_nleaf), cnt);
+        const float var = np32::fdiv(np32::reduce_sum(D, n, N, mean, true, s_leaf, s_sum, s_nleaf), cnt);
+        const float sd = np32::fsqrt(var);
+        for (int e = threadIdx.x; e < nn; e += blockDim.x) {
             const size_t o = (size_t)(e / n) * N + (e % n);
-            const float a = -((float)D[o] - mean) / sd;
-            const float s = 1.0f / (1.0f + expf(-5.0f * a));
+            const float a = np32::fdiv(-np32::fsub((float)D[o], mean), sd);
+            const float s = np32::fdiv(1.0f, np32::fadd(1.0f, np32::exp(np32::fmul(-5.0f, a))));
             S[o] = (double)s;
         }
     }

@@ -147,9 +147,11 @@ def run_side_by_side_with_oracle(dev, n_views, n_people, n_clips, n_frames, seed
             dst, sim, xb, dg = cb.read_matrices(0)
             tag = (n_views, n_people, ci, f)
             assert dst.shape == a.dst.shape, tag
-            st["dst"] = max(st["dst"], float(np.abs(dst - a.dst).max()))
-            st["sim"] = max(st["sim"], float(np.abs(sim - a.sim).max()))
-            assert np.abs(dst - a.dst).max() <= 1e-7 and np.abs(sim - a.sim).max() <= 1e-9, tag
+            # 1e-7 px, relative 1e-12 where a distance is huge (a track re-projected from nearly behind a camera: 1e5 px)
+            dd = float((np.abs(dst - a.dst) / np.maximum(1.0, np.abs(a.dst) * 1e-5)).max())
+            ds = float(np.abs(sim - a.sim).max())
+            st["dst"], st["sim"] = max(st["dst"], dd), max(st["sim"], ds)
+            assert dd <= 1e-7 and ds <= 1e-9, tag + (dd, ds, float(np.abs(a.dst).max()))
             assert np.array_equal(xb, a.x_bin), tag + ("X_bin",)
             assert int(rec["als_iters"]) == a.n_iter, tag + ("ALS iterations", int(rec["als_iters"]), a.n_iter)
             n_alive = int(rec["n_alive"])
