@@ -81,7 +81,7 @@ int mvmc_affinity(const double* kps, const double* P, const double* F, const flo
  * f32_first_iter [B] (may be NULL): 1 where `sim` came from the float32 no-track path (A7).
  * rand_stream: device copy of mvmc_rand_stream_host with at least N*rmax entries.
  * workspace: mvmc_match_als_workspace_bytes(B, N, rmax) bytes of device memory.
- * xbin [B,N,N/32 words] row bitmasks of X_bin; n_iter [B]. N must be a multiple of 32. */
+ * xbin [B,N,(N+31)/32 words] row bitmasks of X_bin (bit j of row i = X_bin[i][j]); n_iter [B]. */
 size_t mvmc_match_als_workspace_bytes(int B, int N, int rmax);
 int mvmc_match_als(const double* sim, const int* dim_groups, int n_groups, const int* f32_first_iter,
                    const double* rand_stream, int B, int N, int rmax, void* workspace, uint32_t* xbin,
@@ -97,10 +97,23 @@ int mvmc_match_als(const double* sim, const int* dim_groups, int n_groups, const
  *   groups that rule shrank to a single pose (listed by the reference, never born), [2] groups with more than
  *   MVMC_MAX_SEL poses, of which only the first MVMC_MAX_SEL are kept (no-track frames of crowded scenes, where the
  *   reference's float32 affinity merges dozens of poses of different people into one group), [3] reserved;
- *   err [B]: 0 or MVMC_ERR_CAPACITY. */
+ *   err [B]: 0 or MVMC_ERR_CAPACITY. N <= MVMC_MAX_TRACKS + MVMC_MAX_VIEWS * MVMC_MAX_POSES. */
 int mvmc_assign(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose,
                 const int* n_trk, int B, int C, int N, int Tmax, int max_new, int* trk_nsel, int* trk_sel,
                 int* new_n, int* new_nsel, int* new_sel, int* counts, int* err, void* stream);
+
+/* The same with the reference's full `spatial_matches` list recoverable (the `associate_tracking` seam returns it):
+ * new_seq [B,Nb] (may be NULL) = position of each stored group among ALL 2D-only groups, singles [B,Nb,3] (may be NULL) =
+ * (position, view, pose id) of the counts[1] single-pose groups. */
+int mvmc_assign_listed(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose,
+                       const int* n_trk, int B, int C, int N, int Tmax, int max_new, int* trk_nsel, int* trk_sel,
+                       int* new_n, int* new_nsel, int* new_sel, int* counts, int* err, int* new_seq, int* singles,
+                       void* stream);
+
+/* A6, first half alone — mv_association.py:99-121 transform_closure (what match_als returns as `match_mat`).
+ * xbin [B,N,(N+31)/32] as written by mvmc_match_als, n [B] live size of each instance ->
+ * match_mat [B,N,N] bytes (leading n x n block written): match[j][i] = 1 iff i is a leader and j belongs to it. */
+int mvmc_transform_closure(const uint32_t* xbin, const int* n, int B, int N, uint8_t* match_mat, void* stream);
 
 /* B1 + B2 — mv_math_util.py:152-240 (DLT per joint + optional 2-nfev TRF refine).
  * obs [M,V,K,3] (x,y,score), Psel [M,V,3,4], n_views [M] (<= V <= MVMC_MAX_SEL), K <= 18 joints.
@@ -212,6 +225,22 @@ int mvmc_clips_step_host(mvmc_clips* h, const double* kps_host, const int* n_pos
  * (the host side's ClipStreams steps groups of clips that way). */
 int mvmc_clips_step_host_async(mvmc_clips* h, const double* kps_host, const int* n_pose_host, int frame_idx,
                                mvmc_step_out* out_host, void* stream);
+
+/* Ingest — motion_capture.py:974-1005 parse_openpose_kps / extract_frame_data_from_openpose and
+ * pose_def.py:262-270 conversion_openpose_25_to_coco.
+ * mvmc_parse_openpose_host: the text of one OpenPose `*_keypoints.json` -> out [max_people,25,3] (x, y, score; zero padded),
+ *   *n_people = len(people) (people beyond max_people are dropped). Native scanner, no Python.
+ * mvmc_parse_openpose_files_host: n_files paths -> out [n_files,max_people,25,3], n_people [n_files], n_threads worker threads.
+ * mvmc_ingest_body25 (DEVICE pointers): kps25 [B,C,Pin,25,3], n_people [B,C] -> kps [B,C,Pmax,17,3] COCO, n_pose [B,C].
+ * mvmc_clips_step_body25_host: HOST BODY_25 buffers [B,C,Pmax,25,3] + [B,C] -> copy, gather on the device, step, records
+ *   back (asynchronous like mvmc_clips_step_host_async). */
+int mvmc_parse_openpose_host(const char* text, size_t len, int max_people, double* out, int* n_people);
+int mvmc_parse_openpose_files_host(const char* const* paths, int n_files, int max_people, double* out, int* n_people,
+                                   int n_threads);
+int mvmc_ingest_body25(const double* kps25, const int* n_people, int B, int C, int Pin, int Pmax, double* kps, int* n_pose,
+                       void* stream);
+int mvmc_clips_step_body25_host(mvmc_clips* h, const double* kps25_host, const int* n_people_host, int frame_idx,
+                                mvmc_step_out* out_host, void* stream);
 
 /* Teacher forcing / checkpoint-resume: overwrite the alive-track table of every clip.
  * n_trk [B]; ids, state, hits, tsu, length [B,Tmax]; param [B,Tmax,68]; joints [B,Tmax,18,3];

@@ -45,6 +45,8 @@ _SIGNATURES = {
     "mvmc_match_als_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "mvmc_match_als": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "mvmc_assign": (c_int, [_P] * 5 + [c_int] * 5 + [_P] * 7 + [_P]),
+    "mvmc_assign_listed": (c_int, [_P] * 5 + [c_int] * 5 + [_P] * 9 + [_P]),
+    "mvmc_transform_closure": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "mvmc_triangulate": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_double, c_int, _P, _P]),
     "mvmc_fk": (c_int, [_P, c_int, _P, _P]),
     "mvmc_fk_chain": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P]),
@@ -61,6 +63,10 @@ _SIGNATURES = {
     "mvmc_clips_last_out": (c_void_p, [c_void_p]),
     "mvmc_clips_step_host": (c_int, [c_void_p, _P, _P, c_int, _P, _P]),
     "mvmc_clips_step_host_async": (c_int, [c_void_p, _P, _P, c_int, _P, _P]),
+    "mvmc_parse_openpose_host": (c_int, [c_char_p, c_size_t, c_int, _P, _P]),
+    "mvmc_parse_openpose_files_host": (c_int, [_P, c_int, c_int, _P, _P, c_int]),
+    "mvmc_ingest_body25": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "mvmc_clips_step_body25_host": (c_int, [c_void_p, _P, _P, c_int, _P, _P]),
     "mvmc_clips_set_tracks_host": (c_int, [c_void_p] + [_P] * 9 + [_P]),
     "mvmc_clips_read_matrices_host": (c_int, [c_void_p, c_int, _P, _P, _P, _P, _P, _P]),
     "mvmc_clips_stats_host": (c_int, [c_void_p, _P, c_int, _P]),
@@ -75,6 +81,7 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 _lib = None
 _lib_path = None
+_device = None
 
 
 class MvmcError(RuntimeError):
@@ -91,21 +98,19 @@ def _bind(lib):
     return lib
 
 
-def use_library(path):
-    """Bind an explicit shared object. Used by the CPU test tier to load the kernel-emulator build
-    (tests/emu/libmvmc_emu.so); product code never calls this."""
-    global _lib, _lib_path
+def use_library(path, device=None):
+    """Bind an explicit build of the C-ABI (same header, same symbols) and, optionally, the torch device its buffers
+    live on. The product never calls this; get_lib() binds the in-tree CUDA build and the device is CUDA."""
+    global _lib, _lib_path, _device
     _lib = _bind(ctypes.CDLL(path))
     _lib_path = path
+    _device = device
     return _lib
 
 
 def get_lib():
     """The CUDA library. Raises if it has not been built (run `python __graft_entry__.py` / build())."""
     global _lib, _lib_path
-    if _lib is None and os.environ.get("MVMC_LIBRARY"):
-        # explicit override of the shared object (the test tier points CLI subprocesses at the kernel emulator with it)
-        return use_library(os.environ["MVMC_LIBRARY"])
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise MvmcError(f"{LIB_PATH} is missing: the CUDA extension has not been built "
@@ -119,8 +124,15 @@ def lib_path():
     return _lib_path
 
 
-def is_emulator():
-    return _lib_path is not None and "emu" in os.path.basename(_lib_path)
+def default_device():
+    """torch device of the library's buffers: the current CUDA device (raises without one - no CPU fallback)."""
+    import torch
+    get_lib()
+    if _device is not None:
+        return torch.device(_device)
+    if not torch.cuda.is_available():
+        raise MvmcError("no CUDA device: the capture path has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
 
 
 def check(rc, what=""):

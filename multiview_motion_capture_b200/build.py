@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmvmc.so")
-SOURCES = ["affinity.cu", "als.cu", "assign.cu", "ik.cu", "pipeline.cu"]
+SOURCES = ["affinity.cu", "als.cu", "assign.cu", "ik.cu", "ingest.cu", "pipeline.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 

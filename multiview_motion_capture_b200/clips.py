@@ -14,9 +14,7 @@ class ClipBatch:
                  nfev_update=5, nfev_birth=50):
         lib = _lib.get_lib()
         self.lib = lib
-        if device is None:
-            device = "cpu" if _lib.is_emulator() else "cuda"
-        self.device = torch.device(device)
+        self.device = torch.device(device) if device is not None else _lib.default_device()
         if self.device.type == "cuda":
             if self.device.index is None:
                 self.device = torch.device("cuda", torch.cuda.current_device())
@@ -109,6 +107,21 @@ class ClipBatch:
         if (rec["error"] != 0).any():
             bad = np.nonzero(rec["error"])[0]
             raise _lib.MvmcError(f"capacity exceeded in clips {bad[:8].tolist()} (raise max_tracks / max_new)")
+        return rec
+
+    def step_body25(self, kps25, n_people, frame_idx):
+        """Ingest + step (mvmc_clips_step_body25_host): raw OpenPose BODY_25 detections kps25 [B,C,Pmax,25,3] and people
+        counts [B,C]; the BODY_25 -> COCO gather runs on the device. Returns the records like step()."""
+        if not hasattr(self, "_kps25_host"):
+            self._kps25_host = self._host_buffer(self.B * self.C * self.Pmax * 75, np.float64)
+        self._kps25_host.numpy()[:] = np.asarray(kps25, dtype=np.float64).reshape(-1)
+        self._np_host.numpy()[:] = np.asarray(n_people, dtype=np.int32).reshape(-1)
+        check(self.lib.mvmc_clips_step_body25_host(self._h, ptr(self._kps25_host), ptr(self._np_host), int(frame_idx),
+                                                   ptr(self._out_host), self._stream()), "mvmc_clips_step_body25_host")
+        self.sync()
+        rec = self._out_host.numpy().view(STEP_OUT_DTYPE)
+        if (rec["error"] != 0).any():
+            raise _lib.MvmcError(f"capacity exceeded in clips {np.nonzero(rec['error'])[0][:8].tolist()} (raise max_tracks / max_new)")
         return rec
 
     @property

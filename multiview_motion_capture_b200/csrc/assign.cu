@@ -14,7 +14,8 @@ __global__ void __launch_bounds__(32)
     k_assign(const uint32_t* __restrict__ xbin, const int* __restrict__ dim_groups, const int* __restrict__ idx_view,
              const int* __restrict__ idx_pose, const int* __restrict__ n_trk, int C, int N, int Tmax, int max_new,
              int* __restrict__ trk_nsel, int* __restrict__ trk_sel, int* __restrict__ new_n, int* __restrict__ new_nsel,
-             int* __restrict__ new_sel, int* __restrict__ counts, int* __restrict__ err) {
+             int* __restrict__ new_sel, int* __restrict__ counts, int* __restrict__ err, int* __restrict__ new_seq,
+             int* __restrict__ singles) {
     const int b = blockIdx.x, lane = threadIdx.x;
     const int NW = (N + 31) / 32;
     const int n = dim_groups[b * (C + 2) + C + 1];
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(32)
     const uint32_t last_row = (lane < NW) ? xb[(size_t)(n - 1) * NW + lane] : 0u;
     uint32_t vis = 0;       // this lane's word of `vis`
     uint32_t assigned = 0;  // this lane's word of "row already attached to a kept column"
-    int n_new = 0, dup = 0, error = 0, n_single = 0, n_trunc = 0;
+    int n_new = 0, dup = 0, error = 0, n_single = 0, n_trunc = 0, seq = 0;   // seq: position among the 2D-only groups
     const bool has_trk = T > 0;
     for (int i = 0; i < n; i++) {
         const uint32_t vw = __shfl_sync(MVMC_FULL, vis, i >> 5);
@@ -109,8 +110,18 @@ __global__ void __launch_bounds__(32)
                         ts[(t_idx * MVMC_MAX_SEL + q) * 2 + 1] = sel[q][1];
                     }
                 } else if (nsel < 2) {
-                    n_single++;  // a 2D-only group the one-pose-per-view rule shrank to one pose: never born
+                    // a 2D-only group the one-pose-per-view rule shrank to one pose: listed by the reference, never born
+                    if (singles && n_single < max_new) {
+                        int* sg = singles + ((size_t)b * max_new + n_single) * 3;
+                        sg[0] = seq;
+                        sg[1] = sel[0][0];
+                        sg[2] = sel[0][1];
+                    }
+                    n_single++;
+                    seq++;
                 } else if (n_new < max_new) {
+                    if (new_seq) new_seq[(size_t)b * max_new + n_new] = seq;
+                    seq++;
                     nn_[n_new] = nsel;
                     for (int q = 0; q < nsel; q++) {
                         ns[(n_new * MVMC_MAX_SEL + q) * 2] = sel[q][0];
@@ -133,21 +144,67 @@ __global__ void __launch_bounds__(32)
     }
 }
 
+// A6, first half on its own (the drop-in `mv_association.transform_closure` / `match_als` seams return this matrix):
+// match[j][i] = 1 for every unvisited leader i and every j with temp[i][j], temp = X | X[:, n-1] (x) X[n-1, :].
+// One warp per instance, lane w owns bit-word w of a row; output as bytes [N][N] (leading n x n block written).
+__global__ void __launch_bounds__(32)
+    k_closure(const uint32_t* __restrict__ xbin, const int* __restrict__ n_of, int N, uint8_t* __restrict__ match) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int NW = (N + 31) / 32;
+    const int n = min(n_of[b], N);
+    const uint32_t* xb = xbin + (size_t)b * N * NW;
+    uint8_t* M = match + (size_t)b * N * N;
+    for (int e = lane; e < n * n; e += 32) M[(size_t)(e / n) * N + (e % n)] = 0;
+    __syncwarp();
+    if (n <= 0) return;
+    const uint32_t last_row = (lane < NW) ? xb[(size_t)(n - 1) * NW + lane] : 0u;
+    uint32_t vis = 0;
+    for (int i = 0; i < n; i++) {
+        const uint32_t vw = __shfl_sync(MVMC_FULL, vis, i >> 5);
+        if ((vw >> (i & 31)) & 1u) continue;
+        uint32_t row = (lane < NW) ? xb[(size_t)i * NW + lane] : 0u;
+        const uint32_t lw = __shfl_sync(MVMC_FULL, row, (n - 1) >> 5);
+        if ((lw >> ((n - 1) & 31)) & 1u) row |= last_row;
+        vis |= row;
+        uint32_t x = row;
+        while (x) {
+            const int j = lane * 32 + __ffs((int)x) - 1;
+            if (j < n) M[(size_t)j * N + i] = 1;
+            x &= x - 1;
+        }
+    }
+}
+
 }  // namespace mvmc
 
 using namespace mvmc;
 
-extern "C" int mvmc_assign(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose,
-                           const int* n_trk, int B, int C, int N, int Tmax, int max_new, int* trk_nsel, int* trk_sel,
-                           int* new_n, int* new_nsel, int* new_sel, int* counts, int* err, void* stream) {
+extern "C" int mvmc_transform_closure(const uint32_t* xbin, const int* n, int B, int N, uint8_t* match_mat, void* stream) {
+    if (!xbin || !n || !match_mat || B <= 0 || N <= 0 || N > 1024) return MVMC_ERR_INVALID;
+    MVMC_LAUNCH(k_closure, dim3(B), dim3(32), 0, stream, xbin, n, N, match_mat);
+    MVMC_CHECK_LAUNCH("k_closure");
+    return MVMC_OK;
+}
+
+extern "C" int mvmc_assign_listed(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose,
+                                  const int* n_trk, int B, int C, int N, int Tmax, int max_new, int* trk_nsel, int* trk_sel,
+                                  int* new_n, int* new_nsel, int* new_sel, int* counts, int* err, int* new_seq, int* singles,
+                                  void* stream) {
     if (!xbin || !dim_groups || !idx_view || !idx_pose || !n_trk || !trk_nsel || !trk_sel || !new_n || !new_nsel ||
         !new_sel || !counts || !err)
         return MVMC_ERR_INVALID;
-    if (B <= 0 || N <= 0 || N > 1024 || C <= 0 || C > MVMC_MAX_VIEWS || Tmax < 0 || Tmax > MVMC_MAX_TRACKS ||
-        max_new <= 0)
-        return MVMC_ERR_INVALID;
+    if (B <= 0 || N <= 0 || N > MVMC_MAX_TRACKS + MVMC_MAX_VIEWS * MVMC_MAX_POSES || C <= 0 || C > MVMC_MAX_VIEWS || Tmax < 0 ||
+        Tmax > MVMC_MAX_TRACKS || max_new <= 0)
+        return MVMC_ERR_INVALID;   // (k_assign lists a group's members in shared memory sized for the largest layout)
     MVMC_LAUNCH(k_assign, dim3(B), dim3(32), 0, stream, xbin, dim_groups, idx_view, idx_pose, n_trk, C, N, Tmax, max_new,
-                trk_nsel, trk_sel, new_n, new_nsel, new_sel, counts, err);
+                trk_nsel, trk_sel, new_n, new_nsel, new_sel, counts, err, new_seq, singles);
     MVMC_CHECK_LAUNCH("k_assign");
     return MVMC_OK;
+}
+
+extern "C" int mvmc_assign(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose,
+                           const int* n_trk, int B, int C, int N, int Tmax, int max_new, int* trk_nsel, int* trk_sel,
+                           int* new_n, int* new_nsel, int* new_sel, int* counts, int* err, void* stream) {
+    return mvmc_assign_listed(xbin, dim_groups, idx_view, idx_pose, n_trk, B, C, N, Tmax, max_new, trk_nsel, trk_sel, new_n,
+                              new_nsel, new_sel, counts, err, nullptr, nullptr, stream);
 }

@@ -405,8 +405,8 @@ struct mvmc_clips {
     // state
     ClipState st;
     // per-step work
-    double *kps_in = nullptr;
-    int* npose_in = nullptr;
+    double *kps_in = nullptr, *kps25_in = nullptr;   // (kps25_in: BODY_25 staging of mvmc_clips_step_body25_host, allocated on first use)
+    int *npose_in = nullptr, *npeople_in = nullptr;
     uint8_t* keep = nullptr;
     int *dim_groups = nullptr, *idx_view = nullptr, *idx_pose = nullptr, *f32_flag = nullptr;
     double *dst = nullptr, *sim = nullptr, *rand_stream = nullptr;
@@ -747,6 +747,34 @@ extern "C" int mvmc_clips_step_host_async(mvmc_clips* h, const double* kps_host,
     MVMC_CUDA_OK(cudaMemcpyAsync(h->kps_in, kps_host, nk * sizeof(double), cudaMemcpyHostToDevice, s));
     MVMC_CUDA_OK(cudaMemcpyAsync(h->npose_in, n_pose_host, (size_t)h->B * h->C * sizeof(int), cudaMemcpyHostToDevice, s));
     int rc = mvmc_clips_step(h, h->kps_in, h->npose_in, frame_idx, stream);
+    if (rc) return rc;
+    if (out_host)
+        MVMC_CUDA_OK(cudaMemcpyAsync(out_host, h->out, (size_t)h->B * sizeof(mvmc_step_out), cudaMemcpyDeviceToHost, s));
+    return MVMC_OK;
+}
+
+int mvmc_ingest_body25(const double* kps25, const int* n_people, int B, int C, int Pin, int Pmax, double* kps, int* n_pose,
+                       void* stream);
+
+// Ingest + step: raw OpenPose BODY_25 detections [B,C,Pmax,25,3] + people counts [B,C] (HOST, e.g. straight from
+// mvmc_parse_openpose_files_host) -> device, BODY_25 -> COCO gather on the device, then the step. Asynchronous like
+// mvmc_clips_step_host_async.
+extern "C" int mvmc_clips_step_body25_host(mvmc_clips* h, const double* kps25_host, const int* n_people_host, int frame_idx,
+                                           mvmc_step_out* out_host, void* stream) {
+    if (!h || !kps25_host || !n_people_host) return MVMC_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n25 = (size_t)h->B * h->C * h->Pmax * 75;
+    if (!h->kps25_in) {
+        int rc = h->alloc(&h->kps25_in, n25);
+        if (rc) return rc;
+        rc = h->alloc(&h->npeople_in, (size_t)h->B * h->C);
+        if (rc) return rc;
+    }
+    MVMC_CUDA_OK(cudaMemcpyAsync(h->kps25_in, kps25_host, n25 * sizeof(double), cudaMemcpyHostToDevice, s));
+    MVMC_CUDA_OK(cudaMemcpyAsync(h->npeople_in, n_people_host, (size_t)h->B * h->C * sizeof(int), cudaMemcpyHostToDevice, s));
+    int rc = mvmc_ingest_body25(h->kps25_in, h->npeople_in, h->B, h->C, h->Pmax, h->Pmax, h->kps_in, h->npose_in, stream);
+    if (rc) return rc;
+    rc = mvmc_clips_step(h, h->kps_in, h->npose_in, frame_idx, stream);
     if (rc) return rc;
     if (out_host)
         MVMC_CUDA_OK(cudaMemcpyAsync(out_host, h->out, (size_t)h->B * sizeof(mvmc_step_out), cudaMemcpyDeviceToHost, s));

@@ -61,14 +61,8 @@ def load_skeleton() -> Skeleton:
 
 
 def _device():
-    import torch
     from multiview_motion_capture_b200 import _lib
-    _lib.get_lib()
-    if _lib.is_emulator():
-        return torch.device("cpu")
-    if not torch.cuda.is_available():
-        raise _lib.MvmcError("no CUDA device: the capture path has no CPU fallback")
-    return torch.device("cuda", torch.cuda.current_device())
+    return _lib.default_device()
 
 
 def _pack(param: PoseShapeParam) -> np.ndarray:
@@ -81,12 +75,13 @@ def _unpack(x: np.ndarray) -> PoseShapeParam:
 
 
 def foward_kinematics(skel: Skeleton, param: PoseShapeParam):
-    """(18, 3) joint positions of `param` on the BASIC_18 skeleton (the reference also returns the 4x4 chain; the
-    capture path only ever uses the positions)."""
+    """(g_pos (18, 3), g_transforms) like the reference (src/inverse_kinematics.py:176-199): every reference caller unpacks
+    two values. The positions come from the CUDA kernel (mvmc_fk); the second value is None - nothing on the capture path
+    reads the 4x4 chain (the callers write `locs, _ = foward_kinematics(...)`)."""
     import torch
     from multiview_motion_capture_b200 import stages
     x = torch.as_tensor(_pack(param)[None], dtype=torch.float64, device=_device())
-    return stages.fk(x).cpu().numpy()[0]
+    return stages.fk(x).cpu().numpy()[0], None
 
 
 class PoseSolver:

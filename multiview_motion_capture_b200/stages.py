@@ -101,6 +101,27 @@ def unpack_xbin(xbin, n):
     return bits[:n, :n].astype(bool)
 
 
+def transform_closure(xbin, n):
+    """mv_association.py:99-121 on the device. xbin [B,N,NW] int32 bit rows, n [B] int32 -> match_mat [B,N,N] uint8."""
+    xbin, n = _c(xbin, i32), _c(n, i32)
+    B, N, _ = xbin.shape
+    out = torch.zeros((B, N, N), dtype=torch.uint8, device=xbin.device)
+    check(_lib.get_lib().mvmc_transform_closure(ptr(xbin), ptr(n), B, N, ptr(out), _stream(xbin)), "mvmc_transform_closure")
+    return out
+
+
+def pack_xbin(x_bin, N=None):
+    """(n,n) bool numpy -> [N,NW] int32 bit rows (inverse of unpack_xbin)."""
+    import numpy as np
+    n = x_bin.shape[0]
+    N = N or n
+    NW = (N + 31) // 32
+    bits = np.zeros((N, NW * 32), dtype=np.uint32)
+    bits[:n, :n] = x_bin
+    words = (bits.reshape(N, NW, 32) << np.arange(32, dtype=np.uint32)).sum(-1).astype(np.uint32)
+    return torch.from_numpy(words.view(np.int32).copy())
+
+
 def assign(xbin, prep, n_trk, C, max_new):
     """closure + parse + decode. Returns dict of int tensors (see include/mvmc.h mvmc_assign)."""
     xbin, n_trk = _c(xbin, i32), _c(n_trk, i32)
@@ -109,11 +130,12 @@ def assign(xbin, prep, n_trk, C, max_new):
     dev = xbin.device
     z = lambda *s: torch.zeros(s, dtype=i32, device=dev)
     out = dict(trk_nsel=z(B, max(Tmax, 1)), trk_sel=z(B, max(Tmax, 1), MAX_SEL, 2), new_n=z(B), new_nsel=z(B, max_new),
-               new_sel=z(B, max_new, MAX_SEL, 2), counts=z(B, 4), err=z(B))
-    check(_lib.get_lib().mvmc_assign(ptr(xbin), ptr(prep["dim_groups"]), ptr(prep["idx_view"]), ptr(prep["idx_pose"]),
-                                     ptr(n_trk), B, C, N, Tmax, max_new, ptr(out["trk_nsel"]), ptr(out["trk_sel"]),
-                                     ptr(out["new_n"]), ptr(out["new_nsel"]), ptr(out["new_sel"]), ptr(out["counts"]),
-                                     ptr(out["err"]), _stream(xbin)), "mvmc_assign")
+               new_sel=z(B, max_new, MAX_SEL, 2), counts=z(B, 4), err=z(B), new_seq=z(B, max_new), singles=z(B, max_new, 3))
+    check(_lib.get_lib().mvmc_assign_listed(ptr(xbin), ptr(prep["dim_groups"]), ptr(prep["idx_view"]), ptr(prep["idx_pose"]),
+                                            ptr(n_trk), B, C, N, Tmax, max_new, ptr(out["trk_nsel"]), ptr(out["trk_sel"]),
+                                            ptr(out["new_n"]), ptr(out["new_nsel"]), ptr(out["new_sel"]), ptr(out["counts"]),
+                                            ptr(out["err"]), ptr(out["new_seq"]), ptr(out["singles"]), _stream(xbin)),
+          "mvmc_assign_listed")
     return out
 
 

@@ -274,6 +274,68 @@ def build_dst_sim_no_tracks(view_kps: Sequence[np.ndarray], Ks, Rts):
 
 
 # ----------------------------------------------------------------------------------------------
+# NumPy's float32 kernels restated (third party, not under /root/reference): what `D.mean()`, `D.std()` and `np.exp`
+# compute on the float32 distance matrix of the no-track path (src/mv_math_util.py:348-350). The CUDA side
+# (csrc/affinity.cu, namespace np32) follows these; tests pin them bit for bit against the container's NumPy.
+# ----------------------------------------------------------------------------------------------
+_f32 = np.float32
+
+
+def np32_pairwise_sum(a: np.ndarray):
+    """numpy/_core/src/umath/loops_utils.h.src pairwise_sum for a contiguous float32 vector."""
+    n = len(a)
+    if n < 8:
+        r = _f32(0.0)
+        for v in a:
+            r = _f32(r + v)
+        return r
+    if n <= 128:
+        r = [_f32(a[j]) for j in range(8)]
+        i = 8
+        while i < n - (n % 8):
+            for j in range(8):
+                r[j] = _f32(r[j] + a[i + j])
+            i += 8
+        res = _f32(_f32(_f32(r[0] + r[1]) + _f32(r[2] + r[3])) + _f32(_f32(r[4] + r[5]) + _f32(r[6] + r[7])))
+        while i < n:
+            res = _f32(res + a[i])
+            i += 1
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return _f32(np32_pairwise_sum(a[:n2]) + np32_pairwise_sum(a[n2:]))
+
+
+def np32_mean_std(D: np.ndarray):
+    """(D.mean(), D.std()) of a float32 matrix, as numpy/_core/_methods.py _mean/_var compute them."""
+    flat = np.ascontiguousarray(D, dtype=_f32).reshape(-1)
+    cnt = _f32(len(flat))
+    mean = _f32(_f32(_f32(0) + np32_pairwise_sum(flat)) / cnt)
+    x = (flat - mean).astype(_f32)
+    x = (x * x).astype(_f32)
+    return mean, np.sqrt(_f32(_f32(_f32(0) + np32_pairwise_sum(x)) / cnt))
+
+
+def np32_exp(x: np.ndarray) -> np.ndarray:
+    """NumPy's float32 exp (loops_exponent_log.dispatch.c.src, AVX2 / AVX512F kernel): Cody-Waite reduction and a (5,2)
+    rational approximation evaluated with FMAs. Valid for |x| < 88."""
+    def fma(a, b, c):   # a*b is exact in float64; the sum is rounded once more (double rounding is negligible for a test aid)
+        return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(_f32)
+    x = np.asarray(x, dtype=_f32)
+    magic = _f32(12582912.0)
+    k = (x * _f32(1.442695040888963407359924681001892137)).astype(_f32)
+    k = ((k + magic).astype(_f32) - magic).astype(_f32)
+    r = fma(k, _f32(-6.93145752e-1), x)
+    r = fma(k, _f32(-1.42860677e-6), r)
+    num = fma(_f32(5.082762527590693718096e-04), r, _f32(6.757896990527504603057e-03))
+    for c in (5.114512081637298353406e-02, 2.473615434895520810817e-01, 7.257664613233124478488e-01, 9.999999999980870924916e-01):
+        num = fma(num, r, _f32(c))
+    den = fma(_f32(2.159509375685829852307e-02), r, _f32(-2.742335390411667452936e-01))
+    den = fma(den, r, _f32(1.0))
+    return np.ldexp((num / den).astype(_f32), k.astype(np.int32)).astype(_f32)
+
+
+# ----------------------------------------------------------------------------------------------
 # A5  ALS / ADMM low-rank multi-way matcher   (src/mv_association.py:222-318)
 # ----------------------------------------------------------------------------------------------
 def match_als(W: np.ndarray, dim_groups, alpha=50, beta=0.1, tol=1e-4, max_iter=1000):

@@ -21,10 +21,10 @@ def emu():
     from multiview_motion_capture_b200 import _lib
     from emu.build_emu import build_emulator
     path = build_emulator()
-    old = (_lib._lib, _lib._lib_path)
-    lib = _lib.use_library(path)
+    old = (_lib._lib, _lib._lib_path, _lib._device)
+    lib = _lib.use_library(path, device="cpu")
     yield lib
-    _lib._lib, _lib._lib_path = old
+    _lib._lib, _lib._lib_path, _lib._device = old
 
 
 @pytest.fixture(scope="module")
@@ -34,7 +34,7 @@ def cuda():
     from multiview_motion_capture_b200 import _lib
     assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
     assert os.path.exists(_lib.LIB_PATH), "libmvmc.so is missing: run __graft_entry__.build() (no CPU fallback)"
-    old = (_lib._lib, _lib._lib_path)
+    old = (_lib._lib, _lib._lib_path, _lib._device)
     lib = _lib.use_library(_lib.LIB_PATH)
     yield lib
-    _lib._lib, _lib._lib_path = old
+    _lib._lib, _lib._lib_path, _lib._device = old

@@ -8,7 +8,7 @@ OUT="$HERE/libmvmc_emu.so"
 FLAGS="-O1 -g -fPIC -std=c++17 -DMVMC_EMU -ffp-contract=off -I$ROOT/include -I$HERE -I$SRC -Wno-unused-variable"
 objs=""
 pids=""
-for f in affinity als assign ik pipeline; do
+for f in affinity als assign ik ingest pipeline; do
   rm -f "$HERE/$f.emu.o"
   g++ $FLAGS -x c++ -c "$SRC/$f.cu" -o "$HERE/$f.emu.o" &
   pids="$pids $!"
@@ -17,5 +17,5 @@ done
 g++ $FLAGS -c "$HERE/emu_main.cpp" -o "$HERE/emu_main.emu.o" &
 pids="$pids $!"
 for p in $pids; do wait $p; done   # (a bare `wait` would swallow a failed compile and relink the stale object)
-g++ -shared -o "$OUT" $objs "$HERE/emu_main.emu.o"
+g++ -shared -o "$OUT" $objs "$HERE/emu_main.emu.o" -lpthread
 echo "built $OUT"

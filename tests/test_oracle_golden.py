@@ -174,3 +174,17 @@ def test_closure_quirk_matches_reference_loop():
                     vis[j] = 1
                     mm[j, i] = 1
         assert np.array_equal(o.transform_closure(x), mm)
+
+
+def test_numpy_float32_restatement():
+    """The float32 NumPy kernels the no-track affinity depends on (mean/std by pairwise summation, exp), restated in the
+    oracle and on the device (csrc/affinity.cu np32): bit-identical to this container's NumPy."""
+    rng = np.random.default_rng(1)
+    for M in (3, 10, 12, 36, 81, 100, 193, 296):
+        D = rng.uniform(0, 60, size=(M, M)).astype(np.float32)
+        np.fill_diagonal(D, 0)
+        mean, std = o.np32_mean_std(D)
+        assert mean == D.mean() and std == D.std(), M
+    for lo, hi in ((-20, 20), (-5, 5), (-80, 80)):
+        x = rng.uniform(lo, hi, size=1_000_000).astype(np.float32)
+        assert np.array_equal(np.exp(x), o.np32_exp(x)), (lo, hi)

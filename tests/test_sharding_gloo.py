@@ -38,7 +38,7 @@ def _track(clip_ids):
     emulator then needs tens, not a thousand, matcher iterations per clip); returns their records."""
     from multiview_motion_capture_b200 import _lib
     from multiview_motion_capture_b200.clips import ClipBatch
-    _lib.use_library(EMU_LIB)
+    _lib.use_library(EMU_LIB, device="cpu")
     inp, g, kps, frames = _inputs(max(clip_ids) + 1)
     B = len(clip_ids)
     cb = ClipBatch(B, 4, 4, max_tracks=8, max_new=4, device="cpu")

@@ -23,7 +23,7 @@ def main():
     args = ap.parse_args()
     from multiview_motion_capture_b200 import _lib
     if args.emu:
-        _lib.use_library(os.path.join(ROOT, "tests", "emu", "libmvmc_emu.so"))
+        _lib.use_library(os.path.join(ROOT, "tests", "emu", "libmvmc_emu.so"), device="cpu")
     from multiview_motion_capture_b200.clips import ClipBatch
     import mvmc_oracle as o
     inp = np.load(os.path.join(ROOT, "tests", "golden", "shelf_inputs.npz"))
