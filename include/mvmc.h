@@ -216,6 +216,11 @@ size_t mvmc_sizeof_step_out(void);
 /* DEVICE pointer to the B records written by the last step (valid until the next step). */
 const mvmc_step_out* mvmc_clips_last_out(const mvmc_clips* h);
 
+/* Compact fixed-stride records of the tracks solved in the last step, for gathering results across GPUs (the path's only
+ * collective): rec [B,cap,128] doubles (DEVICE) = (clip0 + b, track id, frame, state, hits, views used,
+ * 68 parameters, 54 joint coordinates) = 1 KB per track-frame; count [B] (DEVICE) = tracks solved in that clip. */
+int mvmc_clips_pack_records(mvmc_clips* h, int cap, int clip0, double* rec, int* count, void* stream);
+
 /* Same step with HOST buffers: copies kps/n_pose host->device, steps, copies the B records back and
  * synchronises the stream. out_host may be NULL (then only `n_alive`-sized summaries stay on device). */
 int mvmc_clips_step_host(mvmc_clips* h, const double* kps_host, const int* n_pose_host, int frame_idx,

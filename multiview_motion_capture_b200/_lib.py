@@ -61,6 +61,7 @@ _SIGNATURES = {
     "mvmc_clips_step": (c_int, [c_void_p, _P, _P, c_int, _P]),
     "mvmc_sizeof_step_out": (c_size_t, []),
     "mvmc_clips_last_out": (c_void_p, [c_void_p]),
+    "mvmc_clips_pack_records": (c_int, [c_void_p, c_int, c_int, _P, _P, _P]),
     "mvmc_clips_step_host": (c_int, [c_void_p, _P, _P, c_int, _P, _P]),
     "mvmc_clips_step_host_async": (c_int, [c_void_p, _P, _P, c_int, _P, _P]),
     "mvmc_parse_openpose_host": (c_int, [c_char_p, c_size_t, c_int, _P, _P]),

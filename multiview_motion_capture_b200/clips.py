@@ -132,6 +132,16 @@ class ClipBatch:
     def n_pose_host(self):
         return self._np_host.numpy().reshape(self.B, self.C)
 
+    def pack_records(self, cap, clip0=0, rec=None, count=None):
+        """Compact records of the tracks solved in the last step (mvmc_clips_pack_records): rec [B,cap,128] f64 and count [B]
+        i32 device tensors (allocated when not given). Asynchronous on the current stream."""
+        if rec is None:
+            rec = torch.empty((self.B, cap, 128), dtype=torch.float64, device=self.device)
+            count = torch.empty((self.B,), dtype=torch.int32, device=self.device)
+        check(self.lib.mvmc_clips_pack_records(self._h, int(cap), int(clip0), ptr(rec), ptr(count), self._stream()),
+              "mvmc_clips_pack_records")
+        return rec, count
+
     def set_tracks(self, n_trk, ids, state, hits, tsu, length, param, joints, next_id):
         a = lambda x, dt, shape: np.ascontiguousarray(np.asarray(x, dtype=dt).reshape(shape))
         B, T = self.B, self.Tmax

@@ -735,6 +735,51 @@ extern "C" int mvmc_clips_profile(mvmc_clips* h, int enable, double* out_ms, int
     return MVMC_OK;
 }
 
+// Compact result records for gathering (per track-frame (clip, track id, frame, 68 params, 54 joint
+// coordinates) = 1 KB): the tracks SOLVED in the last step of every clip, in track-list order.
+//   rec [B,cap,128] doubles: [0] clip id (clip0 + b), [1] track id, [2] frame, [3] state, [4] hits, [5] views used,
+//   [6..73] parameters, [74..127] joints;   count [B] (tracks solved; rows beyond min(count, cap) are zero)
+__global__ void __launch_bounds__(128)
+    k_pack_records(const mvmc_step_out* __restrict__ out, int cap, int clip0, double* __restrict__ rec, int* __restrict__ count) {
+    __shared__ int s_row[MVMC_MAX_TRACKS];
+    const int b = blockIdx.x;
+    const mvmc_step_out& o = out[b];
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int t = 0; t < o.n_alive; t++) s_row[t] = o.tracks[t].updated > 0 ? n++ : -1;
+        count[b] = n;
+    }
+    __syncthreads();
+    double* R = rec + (size_t)b * cap * 128;
+    for (int e = threadIdx.x; e < cap * 128; e += blockDim.x) R[e] = 0.0;
+    __syncthreads();
+    for (int t = 0; t < o.n_alive; t++) {
+        const int r = s_row[t];
+        if (r < 0 || r >= cap) continue;
+        const mvmc_track_out& tr = o.tracks[t];
+        double* q = R + (size_t)r * 128;
+        for (int e = threadIdx.x; e < 128; e += blockDim.x) {
+            double v;
+            if (e == 0) v = (double)(clip0 + b);
+            else if (e == 1) v = (double)tr.track_id;
+            else if (e == 2) v = (double)o.frame_idx;
+            else if (e == 3) v = (double)tr.state;
+            else if (e == 4) v = (double)tr.hits;
+            else if (e == 5) v = (double)tr.n_sel;
+            else if (e < 6 + MVMC_N_PARAM) v = tr.param[e - 6];
+            else v = tr.joints[e - 6 - MVMC_N_PARAM];
+            q[e] = v;
+        }
+    }
+}
+
+extern "C" int mvmc_clips_pack_records(mvmc_clips* h, int cap, int clip0, double* rec, int* count, void* stream) {
+    if (!h || !rec || !count || cap <= 0 || cap > MVMC_MAX_TRACKS) return MVMC_ERR_INVALID;
+    MVMC_LAUNCH(k_pack_records, dim3(h->B), dim3(128), 0, stream, h->out, cap, clip0, rec, count);
+    MVMC_CHECK_LAUNCH("k_pack_records");
+    return MVMC_OK;
+}
+
 extern "C" size_t mvmc_sizeof_step_out(void) { return sizeof(mvmc_step_out); }
 
 extern "C" const mvmc_step_out* mvmc_clips_last_out(const mvmc_clips* h) { return h ? h->out : nullptr; }

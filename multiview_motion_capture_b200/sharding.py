@@ -50,3 +50,22 @@ def reduce_max(value: float, device=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def gather_track_records(rec: torch.Tensor, count: torch.Tensor, dst: int = 0):
+    """The path's one collective: every rank's compact track records of a step (ClipBatch.pack_records: rec [B,cap,128]
+    f64, count [B] i32, device tensors) gathered on rank `dst` over NCCL (gloo in the CPU test tier). Ranks must hold the
+    same B (pad the last shard). Returns (recs [world,B,cap,128], counts [world,B]) on `dst`, (None, None) elsewhere;
+    without a process group the inputs come back with a leading axis of one."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return rec[None], count[None]
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if rank == dst:
+        recs = torch.empty((world,) + tuple(rec.shape), dtype=rec.dtype, device=rec.device)
+        cnts = torch.empty((world,) + tuple(count.shape), dtype=count.dtype, device=count.device)
+        dist.gather(rec, list(recs.unbind(0)), dst=dst)
+        dist.gather(count, list(cnts.unbind(0)), dst=dst)
+        return recs, cnts
+    dist.gather(rec, None, dst=dst)
+    dist.gather(count, None, dst=dst)
+    return None, None

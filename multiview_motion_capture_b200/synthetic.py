@@ -188,3 +188,93 @@ def make_batch(n_clips, n_views, n_people, n_frames, seed=1000, max_poses=None, 
     n_pose = np.stack([c["n_pose"] for c in clips], 1)
     return dict(kps=np.ascontiguousarray(kps), n_pose=np.ascontiguousarray(n_pose), K=np.stack([c["K"] for c in clips]),
                 RT=np.stack([c["RT"] for c in clips]), clips=clips)
+
+
+class SceneStream:
+    """The same scene model as make_clip, vectorised over B independent clips and generated frame by frame (bench.py: 1184
+    distinct 8 x 32 clips per GPU, or 4096 clips x 600 frames streamed without holding them in memory). Deterministic in
+    (seed, n_clips); clip b of a stream is NOT clip b of make_clip (different use of the random stream), the
+    distribution is the same. `clip_offset` lets a rank generate its own slice of a larger job's clips: clip b of the
+    stream draws from default_rng([seed, clip_offset + b]), so a clip's data does not depend on how clips are sharded."""
+
+    def __init__(self, n_clips, n_views=8, n_people=32, seed=1000, clip_offset=0, img_wh=(1920, 1080), noise_px=2.0,
+                 p_joint_drop=0.05, p_person_miss=0.10, fps=30.0, floor=10.0, shelf_calib=None, clip_ids=None):
+        B, N = n_clips, n_people
+        self.B, self.N, self.fps, self.noise_px, self.p_drop, self.p_miss = B, N, fps, noise_px, p_joint_drop, p_person_miss
+        ids = np.asarray(clip_ids) if clip_ids is not None else clip_offset + np.arange(B)
+        self.rngs = [np.random.default_rng([seed, int(i)]) for i in ids]
+        if shelf_calib is not None:
+            K1, RT1, img_wh = np.asarray(shelf_calib[0]), np.asarray(shelf_calib[1]), tuple(int(x) for x in shelf_calib[2])
+            self.K, self.RT = np.repeat(K1[None], B, 0), np.repeat(RT1[None], B, 0)
+            floor = 4.0
+        else:
+            cams = [make_cameras(r, n_views, img_wh) for r in self.rngs]
+            self.K, self.RT = np.stack([c[0] for c in cams]), np.stack([c[1] for c in cams])
+        self.C = self.K.shape[1]
+        self.W, self.H = img_wh
+        self.floor = floor
+        self.P = np.einsum("bvij,bvjk->bvik", self.K, self.RT)
+        g = int(np.ceil(np.sqrt(N)))
+        cell = floor / g
+        jit = max(0.0, (cell - 0.8) / 2)
+        cells = np.stack([r.permutation(g * g)[:N] for r in self.rngs])
+        xy = np.stack([(cells % g + 0.5) * cell - floor / 2, (cells // g + 0.5) * cell - floor / 2], -1)
+        if jit > 0:
+            xy = xy + self._draw(lambda r: r.uniform(-jit, jit, size=(N, 2)))
+        self.scale = self._draw(lambda r: r.uniform(0.9, 1.1, size=N))
+        self.root = np.concatenate([xy, 0.95 * self.scale[..., None]], -1)
+        self.euler = self._draw(lambda r: r.normal(0, 0.15, size=(N, 18, 3))).clip(-0.8, 0.8)
+        self.euler[:, :, 0, 2] = self._draw(lambda r: r.uniform(-0.8, 0.8, size=N))
+        self.euler[:, :, LEAF_JOINTS] = 0.0
+        self.vel = self._draw(lambda r: r.normal(0, 0.5, size=(N, 2)))
+        self.frame = -1
+
+    def _draw(self, f):
+        return np.stack([f(r) for r in self.rngs])
+
+    def next(self):
+        """Advance one frame. Returns dict(kps25 [B,C,N,25,3], n_pose [B,C], gt_person [B,C,N], gt_root, gt_euler)."""
+        B, N, C, D = self.B, self.N, self.C, self._draw      # (every draw comes from the clip's own generator)
+        self.frame += 1
+        if self.frame > 0:
+            self.euler = (self.euler + D(lambda r: r.normal(0, 0.02, size=(N, 18, 3)))).clip(-0.8, 0.8)
+            self.euler[:, :, LEAF_JOINTS] = 0.0
+            self.vel = self.vel + D(lambda r: r.normal(0, 0.05, size=(N, 2)))
+            sp = np.linalg.norm(self.vel, axis=-1, keepdims=True)
+            self.vel = np.where(sp > 1.5, self.vel * 1.5 / np.maximum(sp, 1e-9), self.vel)
+            self.root[..., :2] = (self.root[..., :2] + self.vel / self.fps).clip(-self.floor / 2, self.floor / 2)
+        J = fk_batch(self.root, self.euler, self.scale)                 # [B,N,18,3]
+        X = np.zeros((B, N, 25, 3))
+        has = np.zeros(25, dtype=bool)
+        for b25, b18 in _B25_FROM_B18.items():
+            X[:, :, b25] = J[:, :, b18]
+            has[b25] = True
+        ear = J[:, :, 16] - J[:, :, 17]
+        ear /= np.maximum(np.linalg.norm(ear, axis=-1, keepdims=True), 1e-9)
+        X[:, :, 16] = J[:, :, 15] + 0.03 * ear
+        X[:, :, 15] = J[:, :, 15] - 0.03 * ear
+        has[[15, 16]] = True
+        Xh = np.concatenate([X, np.ones((B, N, 25, 1))], -1)
+        uvw = np.einsum("bnjk,bvik->bvnji", Xh, self.P)                 # [B,C,N,25,3]
+        z = uvw[..., 2]
+        uv = uvw[..., :2] / np.where(np.abs(z) < 1e-9, 1e-9, z)[..., None]
+        uv = uv + D(lambda r: r.normal(0, self.noise_px, size=(C, N, 25, 2)))
+        score = D(lambda r: r.uniform(0.6, 0.95, size=(C, N, 25)))
+        ok = has & (z > 0.3) & (uv[..., 0] >= 0) & (uv[..., 0] < self.W) & (uv[..., 1] >= 0) & (uv[..., 1] < self.H)
+        ok &= D(lambda r: r.uniform(size=(C, N, 25))) >= self.p_drop
+        det = np.concatenate([uv, score[..., None]], -1) * ok[..., None]
+        seen = (ok[..., BODY25_TO_COCO].sum(-1) >= 6) & (D(lambda r: r.uniform(size=(C, N))) >= self.p_miss)
+        key = np.where(seen, D(lambda r: r.uniform(size=(C, N))), 2.0)          # random order of the seen people, unseen last
+        order = np.argsort(key, axis=-1)
+        n_pose = seen.sum(-1).astype(np.int32)
+        kps25 = np.take_along_axis(det, order[..., None, None], axis=2)
+        live = np.arange(N)[None, None, :] < n_pose[..., None]
+        kps25 = kps25 * live[..., None, None]
+        gt_person = np.where(live, order, -1).astype(np.int32)
+        return dict(kps25=kps25, n_pose=n_pose, gt_person=gt_person, gt_root=self.root.copy(), gt_euler=self.euler.copy(),
+                    gt_joints=J)
+
+    def gt_params(self, side_bone_lens):
+        """[B,N,68] pose parameters of the CURRENT frame's ground truth (root, euler, scaled side bone lengths)."""
+        lens = np.asarray(side_bone_lens)[None, None, :] * self.scale[..., None]
+        return np.concatenate([self.root, self.euler.reshape(self.B, self.N, 54), lens], -1)

@@ -36,14 +36,12 @@ def run_golden_clip(dev, name, Pmax, Tmax, forced, B=1, max_new=8, frames=None):
             st["first_mismatch"] = min(st["first_mismatch"], f)
         same_upd = upd["track_id"].tolist() == g[k + "upd_ids"].tolist()
         st["upd"] += int(same_upd)
-        # No-track frames run the reference's float32 affinity (numpy float32 mean/std/exp, whose last bit depends on
-        # the host CPU's SIMD path); ours agrees to 1 ulp of float32. When the reference's ALS does not converge there
-        # (1000 iterations), X_bin is sensitive to that last bit: such frames are reported, not asserted.
-        unstable = len(g[k + "alive_before"]) == 0 and int(g[k + "als_iters"]) >= 1000
+        # No-track frames run the reference's float32 affinity (NumPy float32 mean / std / exp): restated bit for bit on the
+        # device (csrc/affinity.cu np32), so X_bin is asserted there too, even where the reference's ALS stops at its 1000-iteration cap.
         st.setdefault("unstable_frames", [])
-        if unstable:
+        if len(g[k + "alive_before"]) == 0 and int(g[k + "als_iters"]) >= 1000:
             st["unstable_frames"].append((f, bool(same_x)))
-        if forced and not unstable:
+        if forced:
             assert same_x, (name, f, "X_bin")
             assert rec["n_dup_view"] == int(g[k + "printed"])
             assert tr["track_id"].tolist() == g[k + "alive_after"].tolist(), (name, f, "track ids")

@@ -31,9 +31,14 @@ def test_shelf_teacher_forced_300_frames_identical_tracking(cuda):
 @pytest.mark.parametrize("name,Pmax,Tmax", [("synth_c4p3", 4, 8), ("synth_c8p6", 8, 12), ("synth_c8p12", 12, 16)])
 def test_synthetic_teacher_forced(cuda, name, Pmax, Tmax):
     st = _run(name, Pmax, Tmax, forced=True, max_new=2 * Pmax)
-    ok = st["frames"] - sum(1 for _, same in st["unstable_frames"] if not same)
-    print(name, "unstable no-track frames (frame, X_bin identical):", st["unstable_frames"])
-    assert st["xbin"] >= ok and st["alive"] >= ok and st["upd"] >= ok
+    print(f"PARITY {name} vs reference, teacher-forced incl. the no-track frame 1: frames {st['frames']} X_bin {st['xbin']} "
+          f"ALS-iterations {st['iters']} track-ids {st['alive']}; non-converged no-track frames (frame, X_bin identical): {st['unstable_frames']}")
+    assert st["xbin"] == st["iters"] == st["alive"] == st["upd"] == st["frames"]
+    # free-running from frame 1 (births from the no-track frame feed the next associations): the reference's track ids
+    fr = _run(name, Pmax, Tmax, forced=False, max_new=2 * Pmax)
+    print(f"PARITY {name} free-running from frame 1: frames {fr['frames']} X_bin {fr['xbin']} track-ids {fr['alive']} "
+          f"alive-count {fr['n_alive']} first mismatch {fr['first_mismatch'] if fr['first_mismatch'] < 10**9 else None}")
+    assert fr["alive"] == fr["frames"], "track ids of a free-running synthetic clip differ from the reference's"
 
 
 @pytest.mark.parametrize("name,Pmax,Tmax", WARM)

@@ -48,8 +48,10 @@ def _track(clip_ids):
     k = np.stack([pad_poses(kps[frames[c]], 4) for c in clip_ids])
     n = np.stack([inp["n_pose"][frames[c]] for c in clip_ids])
     rec = cb.step(k, n, 1).copy()
+    packed, count = cb.pack_records(8, clip0=0)
+    packed, count = packed.clone(), count.clone()
     cb.close()
-    return rec
+    return rec, packed, count
 
 
 def _worker(rank, world, port, n_clips, out_dir):
@@ -58,12 +60,20 @@ def _worker(rank, world, port, n_clips, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         mine = sharding.shard_clips(n_clips, rank, world)
-        rec = _track(mine.tolist())
+        rec, packed, count = _track(mine.tolist())
         allrec = sharding.gather_records(rec, n_clips)
         slowest = sharding.reduce_max(float(rank + 1))
+        # the compact track records, gathered on rank 0 (equal shard sizes: pad the short shard with an empty clip)
+        per = -(-n_clips // world)
+        if packed.shape[0] < per:
+            packed = torch.cat([packed, torch.zeros((per - packed.shape[0],) + tuple(packed.shape[1:]), dtype=packed.dtype)])
+            count = torch.cat([count, torch.zeros(per - count.shape[0], dtype=count.dtype)])
+        recs, cnts = sharding.gather_track_records(packed, count, dst=0)
         if rank == 0:
             np.save(os.path.join(out_dir, "gathered.npy"), allrec.view(np.uint8))
             np.save(os.path.join(out_dir, "max.npy"), np.array([slowest]))
+            np.save(os.path.join(out_dir, "packed.npy"), recs.numpy())
+            np.save(os.path.join(out_dir, "counts.npy"), cnts.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -74,9 +84,19 @@ def test_two_ranks_equal_single_process(tmp_path, emu):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, n_clips, str(tmp_path)), nprocs=world, join=True)
     got = np.load(tmp_path / "gathered.npy").view(STEP_OUT_DTYPE).reshape(n_clips)
-    ref = _track(list(range(n_clips)))
+    ref, ref_packed, ref_count = _track(list(range(n_clips)))
     assert float(np.load(tmp_path / "max.npy")[0]) == 2.0
     for c in range(n_clips):
         n = int(ref[c]["n_alive"])
         assert n == int(got[c]["n_alive"]) and n >= 2
         assert got[c].tobytes() == ref[c].tobytes(), c      # bit-identical records wherever a clip is tracked
+    # compact records (mvmc_clips_pack_records + gather_track_records): clip c sits at [c % world, c // world]
+    packed, counts = np.load(tmp_path / "packed.npy"), np.load(tmp_path / "counts.npy")
+    for c in range(n_clips):
+        n = int(ref_count[c])
+        assert n == int(counts[c % world, c // world]) == int((ref[c]["tracks"]["updated"][:int(ref[c]["n_alive"])] > 0).sum())
+        a, b = packed[c % world, c // world, :n], ref_packed[c, :n].numpy()
+        assert np.array_equal(a[:, 1:], b[:, 1:])             # (column 0 is the clip id relative to each call's clip0)
+        upd = ref[c]["tracks"][:int(ref[c]["n_alive"])]
+        upd = upd[upd["updated"] > 0]
+        assert np.array_equal(a[:, 1], upd["track_id"]) and np.array_equal(a[:, 6:74], upd["param"]) and np.array_equal(a[:, 74:], upd["joints"])
