@@ -282,6 +282,10 @@ int mvmc_fp64_tensor_probe(int blocks, int iters, double* sink, void* stream);
 #define MVMC_ALS_N_PHASES 20
 int mvmc_als_phase_profile(int enable, double* out);
 
+/* Measurement aid: which tile build of the ALS kernel mvmc_match_als runs: -1 = by shape (default), 0 = 64 x 96 CTA tiles /
+ * 8 warps, 1 = 48 x 48 tiles / 4 warps. Results do not depend on it. */
+int mvmc_als_force_variant(int v);
+
 /* number of kernel launches enqueued by this library since load (for bench.py's gpu_launches) */
 unsigned long long mvmc_launch_count(void);
 

@@ -75,6 +75,7 @@ _SIGNATURES = {
     "mvmc_fp64_probe": (c_int, [c_int, c_int, _P, _P]),
     "mvmc_fp64_tensor_probe": (c_int, [c_int, c_int, _P, _P]),
     "mvmc_als_phase_profile": (c_int, [c_int, _P]),
+    "mvmc_als_force_variant": (c_int, [c_int]),
     "mvmc_launch_count": (c_ulonglong, []),
 }
 

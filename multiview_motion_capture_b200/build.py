@@ -13,6 +13,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmvmc.so")
 SOURCES = ["affinity.cu", "als.cu", "assign.cu", "ik.cu", "ingest.cu", "pipeline.cu"]
+# the same source built again with other tile shapes (see als.cu: AL_VARIANT)
+VARIANTS = [("als.cu", "als_small.o", ["-DAL_VARIANT=small", "-DAL_FM_=3", "-DAL_THREADS_=128"])]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
@@ -37,12 +39,12 @@ def build_cuda(force=False, verbose=True):
     nvcc = _nvcc()
     objs = []
     jobs = []
-    for s in SOURCES:
+    for s, name, extra in [(s, s.replace(".cu", ".o"), []) for s in SOURCES] + VARIANTS:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(LIBDIR, s.replace(".cu", ".o"))
+        obj = os.path.join(LIBDIR, name)
         objs.append(obj)
-        if force or _stale(obj, [src] + headers):
-            jobs.append([nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj])
+        if force or _stale(obj, [src] + headers + [os.path.abspath(__file__)]):
+            jobs.append([nvcc] + NVCC_FLAGS + extra + ["-c", src, "-o", obj])
 
     def run(cmd):
         if verbose:

@@ -29,15 +29,32 @@
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #endif
 
+// This file is compiled more than once with different tile shapes (-DAL_FM_=3 -DAL_THREADS_=128 -DAL_VARIANT=small for
+// the small problems of 8 x 16 scenes): each build lives in its own namespace and exports its launcher under its own name;
+// the default build also holds the shape dispatcher and the shared C entry points.
+#ifdef AL_VARIANT
+#define AL_CAT2(a, b) a##b
+#define AL_CAT(a, b) AL_CAT2(a, b)
+#define AL_NSNAME AL_CAT(als_, AL_VARIANT)
+#define AL_LAUNCHER AL_CAT(mvmc_match_als_ordered_, AL_VARIANT)
+#else
+#define AL_NSNAME als_default
+#define AL_LAUNCHER mvmc_match_als_ordered_default
+#endif
 namespace mvmc {
+namespace AL_NSNAME {
 
 #ifndef AL_THREADS_
 #define AL_THREADS_ 256
 #endif
+#ifndef AL_FM_
+#define AL_FM_ 4
+#endif
 constexpr int AL_THREADS = AL_THREADS_;   // 8 warps: 2 along M x 4 along N, warp tile 32 x 24 (4 warps: 2 x 2, four CTAs per SM)
 constexpr int AL_WARPS = AL_THREADS / 32;
 constexpr int AL_KC = 16;                 // k-chunk (one 128-byte swizzle row of doubles)
-constexpr int AL_TM = 64;                 // CTA tile rows
+constexpr int AL_FM = AL_FM_;             // 8-row fragments per warp along M (4: warp tile 32 x 24; 3: 24 x 24)
+constexpr int AL_TM = 16 * AL_FM;         // CTA tile rows (two warps along M)
 constexpr int AL_TN = 24 * (AL_WARPS / 2); // CTA tile columns (warp columns x 24)
 constexpr int AL_STAGE_M = AL_TM * AL_KC; // doubles: 8 KB
 constexpr int AL_STAGE_N = AL_TN * AL_KC; // 12 KB
@@ -342,21 +359,21 @@ __device__ __forceinline__ void cta_gemm(Ring& rg, const Operand Mop, const Oper
     }
     FragTab ftab;
     ftab.init(lane);
-    FragAddr<MK, 4> fm;   // M operand: rows 32 wm + 8 a
-    FragAddr<NK, 3> fn;   // N operand: columns 24 wn + 8 b
-    fm.init(ftab, 32 * wm);
+    FragAddr<MK, AL_FM> fm;   // M operand: rows 8 AL_FM wm + 8 a
+    FragAddr<NK, 3> fn;       // N operand: columns 24 wn + 8 b
+    fm.init(ftab, 8 * AL_FM * wm);
     fn.init(ftab, 24 * wn);
     const saddr_t ring0 = saddr_of(rg.stages);
     int c = 0;
     for (int m0 = 0; m0 < M; m0 += AL_TM) {
-        const int mw0 = m0 + 32 * wm;
-        const int mt = mw0 >= M ? 0 : min(4, (M - mw0 + 7) >> 3);       // live row tiles of this warp
+        const int mw0 = m0 + 8 * AL_FM * wm;
+        const int mt = mw0 >= M ? 0 : min(AL_FM, (M - mw0 + 7) >> 3);       // live row tiles of this warp
         for (int n0 = 0; n0 < N; n0 += AL_TN) {
             const int nw0 = n0 + 24 * wn;
             const int nt = (nw0 >= N || mt == 0) ? 0 : min(3, (N - nw0 + 7) >> 3);
-            double acc[4][3][2];
+            double acc[AL_FM][3][2];
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+            for (int a = 0; a < AL_FM; a++)
 #pragma unroll
                 for (int b = 0; b < 3; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
             // fragment s = 3a + b of this thread: row, first column, liveness
@@ -377,21 +394,21 @@ __device__ __forceinline__ void cta_gemm(Ring& rg, const Operand Mop, const Oper
                     // step s+1 are issued before the DMMAs of step s.
                     const saddr_t Sm = ring0 + st * (AL_STAGE * 8);
                     const saddr_t Sn = Sm + AL_STAGE_M * 8;
-                    double af[2][4], bf[2][3];
+                    double af[2][AL_FM], bf[2][3];
 #pragma unroll
                     for (int b = 0; b < 3; b++) bf[0][b] = lds64(fn.at(Sn, b, 0));
 #pragma unroll
-                    for (int a = 0; a < 4; a++) af[0][a] = lds64(fm.at(Sm, a, 0));
+                    for (int a = 0; a < AL_FM; a++) af[0][a] = lds64(fm.at(Sm, a, 0));
 #pragma unroll
                     for (int s = 0; s < 4; s++) {
                         if (s + 1 < 4) {
 #pragma unroll
                             for (int b = 0; b < 3; b++) bf[(s + 1) & 1][b] = lds64(fn.at(Sn, b, s + 1));
 #pragma unroll
-                            for (int a = 0; a < 4; a++) af[(s + 1) & 1][a] = lds64(fm.at(Sm, a, s + 1));
+                            for (int a = 0; a < AL_FM; a++) af[(s + 1) & 1][a] = lds64(fm.at(Sm, a, s + 1));
                         }
 #pragma unroll
-                        for (int a = 0; a < 4; a++)
+                        for (int a = 0; a < AL_FM; a++)
 #pragma unroll
                             for (int b = 0; b < 3; b++) dmma(acc[a][b][0], acc[a][b][1], af[s & 1][a], bf[s & 1][b]);
                     }
@@ -405,8 +422,8 @@ __device__ __forceinline__ void cta_gemm(Ring& rg, const Operand Mop, const Oper
                 }
             }
 #pragma unroll
-            for (int s = 0; s < 12; s++) {
-                if (s + 2 < 12 && f_on(s + 2)) ep.load(buf[(s + 2) % 3], f_m(s + 2), f_n(s + 2));
+            for (int s = 0; s < 3 * AL_FM; s++) {
+                if (s + 2 < 3 * AL_FM && f_on(s + 2)) ep.load(buf[(s + 2) % 3], f_m(s + 2), f_n(s + 2));
                 if (f_on(s)) ep.apply(buf[s % 3], f_m(s), f_n(s), acc[s / 3][s % 3][0], acc[s / 3][s % 3][1]);
             }
         }
@@ -1088,26 +1105,32 @@ __global__ void __launch_bounds__(1024) k_als_order(const int* __restrict__ prev
     }
 }
 
+}  // namespace AL_NSNAME
 }  // namespace mvmc
 
 using namespace mvmc;
+using namespace mvmc::AL_NSNAME;
 
+#ifndef AL_VARIANT
 int mvmc_als_order(const int* prev_iter, int B, int* order, void* stream) {
     if (!prev_iter || !order || B <= 0) return MVMC_ERR_INVALID;
     MVMC_LAUNCH(k_als_order, dim3(1), dim3(1024), 0, stream, prev_iter, B, order);
     MVMC_CHECK_LAUNCH("k_als_order");
     return MVMC_OK;
 }
+#endif
 
 static size_t als_smem_bytes(int N) {
     return 1024 + (size_t)(AL_NS * AL_STAGE + 32 + 4 * GJ_LD) * sizeof(double) + (2 * AL_NS + 2 * AL_PASS_NS) * sizeof(mbar_t) +
            (size_t)(N + 2) * sizeof(int);
 }
 
+#ifndef AL_VARIANT
 extern "C" size_t mvmc_match_als_workspace_bytes(int B, int N, int rmax) {
     const AlsLayout L(N, rmax);
     return (size_t)B * L.per * sizeof(double);
 }
+#endif
 
 // ---- tensor maps over the workspace ----
 #ifndef MVMC_EMU
@@ -1203,9 +1226,9 @@ static int als_build_maps(AlsMaps* M, double* ws, int B, int N, int rmax) {
 
 // `order` (device, [B], may be null): clip index solved by CTA i - the pipeline passes the clips sorted by their previous
 // frame's iteration count, longest first, so the last wave of CTAs is the short solves.
-int mvmc_match_als_ordered(const double* sim, const int* dim_groups, int n_groups, const int* f32_first_iter,
-                           const double* rand_stream, const int* order, int B, int N, int rmax, void* workspace, uint32_t* xbin,
-                           int* n_iter, void* stream) {
+int AL_LAUNCHER(const double* sim, const int* dim_groups, int n_groups, const int* f32_first_iter,
+                const double* rand_stream, const int* order, int B, int N, int rmax, void* workspace, uint32_t* xbin,
+                int* n_iter, void* stream) {
     if (!sim || !dim_groups || !rand_stream || !workspace || !xbin || !n_iter) return MVMC_ERR_INVALID;
     if (B <= 0 || N <= 0 || N > 1024 || rmax <= 0 || rmax > 128 || n_groups <= 0 || n_groups > MVMC_MAX_VIEWS + 1)
         return MVMC_ERR_INVALID;
@@ -1219,6 +1242,30 @@ int mvmc_match_als_ordered(const double* sim, const int* dim_groups, int n_group
                 order, N, rmax, (double*)workspace, xbin, n_iter, 50.0, 0.1, 1e-4, 1000);
     MVMC_CHECK_LAUNCH("k_als");
     return MVMC_OK;
+}
+
+#ifndef AL_VARIANT
+// Tile shape by problem size: rmax <= 32 (scenes of up to 16 people per view: n ~ 130, r = 32) runs the build with 48 x 48
+// CTA tiles and 4-warp CTAs (als.cu compiled with -DAL_VARIANT=small -DAL_FM_=3 -DAL_THREADS_=128) - 64 x 96 tiles leave most
+// of their fragments on padding there (n = 131 is two 64-row tiles plus 3 rows). Same arithmetic per element; the two
+// builds differ in which rows a CTA's warps own, never in a summation order along k.
+int mvmc_match_als_ordered_small(const double* sim, const int* dim_groups, int n_groups, const int* f32_first_iter,
+                                 const double* rand_stream, const int* order, int B, int N, int rmax, void* workspace,
+                                 uint32_t* xbin, int* n_iter, void* stream);
+static int g_als_force_variant = -1;   // -1 auto, 0 default tiles, 1 small tiles (mvmc_als_force_variant: measurements)
+extern "C" int mvmc_als_force_variant(int v) {
+    g_als_force_variant = v;
+    return MVMC_OK;
+}
+int mvmc_match_als_ordered(const double* sim, const int* dim_groups, int n_groups, const int* f32_first_iter,
+                           const double* rand_stream, const int* order, int B, int N, int rmax, void* workspace, uint32_t* xbin,
+                           int* n_iter, void* stream) {
+    const bool small = g_als_force_variant < 0 ? rmax <= 32 : g_als_force_variant == 1;
+    if (small)
+        return mvmc_match_als_ordered_small(sim, dim_groups, n_groups, f32_first_iter, rand_stream, order, B, N, rmax, workspace,
+                                            xbin, n_iter, stream);
+    return mvmc_match_als_ordered_default(sim, dim_groups, n_groups, f32_first_iter, rand_stream, order, B, N, rmax, workspace,
+                                          xbin, n_iter, stream);
 }
 
 // enable != 0: start counting (resets); enable == 0: stop. out (may be null) receives the PH_COUNT cycle sums so far.
@@ -1247,3 +1294,4 @@ extern "C" int mvmc_match_als(const double* sim, const int* dim_groups, int n_gr
     return mvmc_match_als_ordered(sim, dim_groups, n_groups, f32_first_iter, rand_stream, nullptr, B, N, rmax, workspace, xbin,
                                   n_iter, stream);
 }
+#endif   // AL_VARIANT

@@ -14,6 +14,10 @@ for f in affinity als assign ik ingest pipeline; do
   pids="$pids $!"
   objs="$objs $HERE/$f.emu.o"
 done
+rm -f "$HERE/als_small.emu.o"
+g++ $FLAGS -DAL_VARIANT=small -DAL_FM_=3 -DAL_THREADS_=128 -x c++ -c "$SRC/als.cu" -o "$HERE/als_small.emu.o" &
+pids="$pids $!"
+objs="$objs $HERE/als_small.emu.o"
 g++ $FLAGS -c "$HERE/emu_main.cpp" -o "$HERE/emu_main.emu.o" &
 pids="$pids $!"
 for p in $pids; do wait $p; done   # (a bare `wait` would swallow a failed compile and relink the stale object)
