@@ -278,3 +278,109 @@ class SceneStream:
         """[B,N,68] pose parameters of the CURRENT frame's ground truth (root, euler, scaled side bone lengths)."""
         lens = np.asarray(side_bone_lens)[None, None, :] * self.scale[..., None]
         return np.concatenate([self.root, self.euler.reshape(self.B, self.N, 54), lens], -1)
+
+
+class DeviceSceneStream:
+    """SceneStream's scene model with the per-frame work done by torch on the device the clips are tracked on, so that a
+    long job (BASELINE config 5: 4096 clips x 600 frames) can synthesise its detections without the host: every random
+    number is a counter-based hash (splitmix64) of (seed, clip id, frame, draw, element), so a clip's data depends on
+    nothing but its id - not on the batch it is generated in, nor on the rank. The scene itself (cameras, people, start
+    poses) is SceneStream's. Benchmark input synthesis only; not part of the capture path."""
+
+    _M1, _M2, _G = -4658895280553007687, -7723592293110705685, -7046029254386353131   # splitmix64 constants as int64
+
+    def __init__(self, clip_ids, n_views=8, n_people=32, seed=1000, device="cuda", shuffle=True, **kw):
+        import torch
+        self.t = torch
+        self.shuffle = shuffle     # False: pose slot p of every view is person p (an unseen person is an all-zero pose)
+        host = SceneStream(len(clip_ids), n_views, n_people, seed=seed, clip_ids=clip_ids, **kw)
+        self.B, self.N, self.C = host.B, host.N, host.C
+        self.W, self.H, self.floor, self.fps = host.W, host.H, host.floor, host.fps
+        self.noise_px, self.p_drop, self.p_miss = host.noise_px, host.p_drop, host.p_miss
+        self.K, self.RT = host.K, host.RT
+        d = lambda a: torch.as_tensor(a, dtype=torch.float64, device=device)
+        self.P, self.root, self.euler, self.scale, self.vel = d(host.P), d(host.root), d(host.euler), d(host.scale), d(host.vel)
+        self.ids = torch.as_tensor(np.asarray(clip_ids, dtype=np.int64), device=device)
+        self.seed, self.device, self.frame = int(seed), device, -1
+        self.off = d(B18_OFFSETS)
+        self.leaf = torch.as_tensor(LEAF_JOINTS, device=device)
+        self.b25_src = torch.as_tensor([_B25_FROM_B18.get(j, 0) for j in range(25)], device=device)
+        self.has = torch.zeros(25, dtype=torch.bool, device=device)
+        self.has[list(_B25_FROM_B18) + [15, 16]] = True
+        self.coco = torch.as_tensor(BODY25_TO_COCO, device=device)
+
+    def _mix(self, z):
+        t = self.t
+        z = z + self._G
+        z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * self._M1
+        z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * self._M2
+        return z ^ ((z >> 31) & ((1 << 33) - 1))
+
+    def _uniform(self, draw, shape):
+        """[B, *shape] uniforms in [0, 1): hash of (seed, clip id, frame, draw, element index)."""
+        t = self.t
+        n = int(np.prod(shape))
+        key = self._mix(self.ids * 1000003 + self.seed) ^ self._mix(t.full_like(self.ids, self.frame * 64 + draw))
+        z = self._mix(key[:, None] * 2654435761 + t.arange(n, device=self.device, dtype=t.int64)[None, :])
+        u = ((z >> 11) & ((1 << 53) - 1)).to(t.float64) * (1.0 / (1 << 53))
+        return u.reshape((self.B,) + tuple(shape))
+
+    def _normal(self, draw, shape, sigma):
+        t = self.t
+        u1, u2 = self._uniform(draw, shape), self._uniform(draw + 32, shape)
+        return sigma * t.sqrt(-2.0 * t.log(1.0 - u1)) * t.cos(2.0 * np.pi * u2)
+
+    def _fk(self):
+        t = self.t
+        a, b, c = self.euler[..., 0], self.euler[..., 1], self.euler[..., 2]
+        ca, sa, cb, sb, cc, sc = t.cos(a), t.sin(a), t.cos(b), t.sin(b), t.cos(c), t.sin(c)
+        z, o = t.zeros_like(a), t.ones_like(a)
+        rx = t.stack([o, z, z, z, ca, -sa, z, sa, ca], -1).reshape(a.shape + (3, 3))
+        ry = t.stack([cb, z, sb, z, o, z, -sb, z, cb], -1).reshape(a.shape + (3, 3))
+        rz = t.stack([cc, -sc, z, sc, cc, z, z, z, o], -1).reshape(a.shape + (3, 3))
+        R = rx @ ry @ rz                                           # [B,N,18,3,3]
+        pos, G = [self.root], [R[:, :, 0]]
+        for j in range(1, 18):
+            p = int(B18_PARENTS[j])
+            off = self.off[j][None, None, :] * self.scale[..., None]
+            pos.append(pos[p] + (G[p] @ off[..., None])[..., 0])
+            G.append(G[p] @ R[:, :, j])
+        return t.stack(pos, 2)                                     # [B,N,18,3]
+
+    def next(self):
+        """Advance one frame: (kps [B,C,N,17,3] float64 COCO detections, n_pose [B,C] int32) on the device."""
+        t = self.t
+        B, N, C = self.B, self.N, self.C
+        self.frame += 1
+        if self.frame > 0:
+            self.euler = (self.euler + self._normal(0, (N, 18, 3), 0.02)).clamp(-0.8, 0.8)
+            self.euler[:, :, self.leaf] = 0.0
+            self.vel = self.vel + self._normal(1, (N, 2), 0.05)
+            sp = self.vel.norm(dim=-1, keepdim=True)
+            self.vel = t.where(sp > 1.5, self.vel * 1.5 / sp.clamp_min(1e-9), self.vel)
+            self.root[..., :2] = (self.root[..., :2] + self.vel / self.fps).clamp(-self.floor / 2, self.floor / 2)
+        J = self._fk()
+        X = J[:, :, self.b25_src]                                  # [B,N,25,3]
+        ear = J[:, :, 16] - J[:, :, 17]
+        ear = ear / ear.norm(dim=-1, keepdim=True).clamp_min(1e-9)
+        X[:, :, 16] = J[:, :, 15] + 0.03 * ear
+        X[:, :, 15] = J[:, :, 15] - 0.03 * ear
+        Xh = t.cat([X, t.ones((B, N, 25, 1), dtype=t.float64, device=self.device)], -1)
+        uvw = t.einsum("bnjk,bvik->bvnji", Xh, self.P)             # [B,C,N,25,3]
+        z = uvw[..., 2]
+        uv = uvw[..., :2] / t.where(z.abs() < 1e-9, t.full_like(z, 1e-9), z)[..., None]
+        uv = uv + self._normal(2, (C, N, 25, 2), self.noise_px)
+        score = 0.6 + 0.35 * self._uniform(3, (C, N, 25))
+        ok = self.has & (z > 0.3) & (uv[..., 0] >= 0) & (uv[..., 0] < self.W) & (uv[..., 1] >= 0) & (uv[..., 1] < self.H)
+        ok = ok & (self._uniform(4, (C, N, 25)) >= self.p_drop)
+        det = t.cat([uv, score[..., None]], -1) * ok[..., None]
+        seen = (ok[..., self.coco].sum(-1) >= 6) & (self._uniform(5, (C, N)) >= self.p_miss)
+        key = t.where(seen, self._uniform(6, (C, N)), t.full((B, C, N), 2.0, dtype=t.float64, device=self.device))
+        order = key.argsort(dim=-1)
+        n_pose = seen.sum(-1).to(t.int32)
+        det = det[..., self.coco, :]                               # COCO-17
+        if not self.shuffle:
+            return (det * seen[..., None, None]).contiguous(), t.full((B, C), N, dtype=t.int32, device=self.device)
+        kps = t.take_along_dim(det, order[..., None, None], dim=2)
+        live = t.arange(N, device=self.device)[None, None, :] < n_pose[..., None]
+        return (kps * live[..., None, None]).contiguous(), n_pose.contiguous()
