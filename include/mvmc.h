@@ -144,6 +144,14 @@ int mvmc_ik_solve(const double* kps2d, const double* Psel, const int* n_views, c
                   const uint8_t* birth, const int* max_nfev, const uint8_t* free_mask, int M, int V,
                   void* workspace, double* x_out, double* joints, int* info, double* cost, void* stream);
 
+/* SURVEY.md 8f-4 — inverse_kinematics.py:280-336 solve_pose / solve_pose_bone_lens, the 3D-target variants behind
+ * PoseSolver's `use_only_reproj = False` (:402-415): residual = (FK joint - triangulated point) * point score over the 16
+ * IK joints. target [M,16,4] = (x, y, z, score) gathered at the IK joints (BASIC_18 idx 1..7, 9..17 <- 18-point observation
+ * idx 11,13,15,12,14,16,17,5,7,9,6,8,10,0,3,4); x0 [M,68]; max_nfev [M]; stages: bit 0 = solve_pose (root + angles), bit 1 =
+ * solve_pose_bone_lens (+ 11 side lengths), run in that order. Outputs as mvmc_ik_solve (a stage not run reports nfev 0). */
+int mvmc_ik_solve_targets(const double* target, const double* x0, const int* max_nfev, int stages, int M, double* x_out,
+                          double* joints, int* info, double* cost, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Clip-batch pipeline: B independent clips advance one frame per step
  * (reference: MvTracker.update_4d, motion_capture.py:873-963, one call per clip and frame).

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "mvmc_fk_chain": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P]),
     "mvmc_ik_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mvmc_ik_solve": (c_int, [_P] * 7 + [c_int, c_int] + [_P] * 6),
+    "mvmc_ik_solve_targets": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
     "mvmc_default_config": (None, [POINTER(Config)]),
     "mvmc_clips_create": (c_int, [POINTER(Config), POINTER(c_void_p)]),
     "mvmc_clips_destroy": (None, [c_void_p]),

@@ -279,6 +279,60 @@ struct IkRes {
     }
 };
 
+// ---- 3D-target residual (inverse_kinematics.py:280-336 solve_pose / solve_pose_bone_lens): FK joints against triangulated
+// points, rows (observed joint q, coordinate c) -> 3 q + c, weighted by the point's score; 48 rows = 6 chunks of 8 ----
+struct Ik3dRes {
+    const double* tgt;   // [16][4] (x, y, z, score), gathered at the IK joints (shared)
+    double* posb;        // [16][3] scratch (shared)
+    double* Rloc;        // [18][9] (shared)
+    __device__ int m() const { return MVMC_N_IKJ * 3; }
+    __device__ int n_chunks() const { return MVMC_N_IKJ * 3 / 8; }
+    __device__ int chunk_rows(int) const { return 8; }
+    __device__ int chunk_row0(int c) const { return 8 * c; }
+    __device__ __noinline__ void eval(const double* x, double* f) {
+        MVMC_ASSUME_SHARED(x);
+        MVMC_ASSUME_SHARED(f);
+        MVMC_ASSUME_SHARED(tgt);
+        MVMC_ASSUME_SHARED(posb);
+        MVMC_ASSUME_SHARED(Rloc);
+        const int lane = threadIdx.x & 31;
+        local_rots(x, Rloc);
+        fk_store(x, Rloc, -1, 0.0, posb, 1, true, lane == 0);
+        __syncwarp();
+        for (int it = lane; it < MVMC_N_IKJ * 3; it += 32) {
+            const int q = it / 3, c = it % 3;
+            f[it] = DMUL(DSUB(posb[q * 3 + c], tgt[q * 4 + c]), tgt[q * 4 + 3]);
+        }
+        __syncwarp();
+    }
+    __device__ void fd_prepare(TrfWarp& s, int ncol) {
+        const int lane = threadIdx.x & 31;
+        double* S = s.A;
+        local_rots(s.x, Rloc);
+        for (int c0 = 0; c0 < ncol; c0 += 32) {
+            const int c = c0 + lane;
+            const bool on = c < ncol;
+            fk_store(s.x, Rloc, on ? s.act[c] : -1, on ? s.w[c] : 0.0, S + c, WS_NC, true, on);
+        }
+    }
+    __device__ __forceinline__ void fd_chunk(TrfWarp& s, int ncol, int ch, const double* f) {
+        MVMC_ASSUME_SHARED(&s);
+        MVMC_ASSUME_SHARED(f);
+        MVMC_ASSUME_SHARED(tgt);
+        const int lane = threadIdx.x & 31;
+        const double* S = s.A;
+        for (int c = lane; c < ncol; c += 32) {
+            const double rdx = 1.0 / s.dx[c];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int row = 8 * ch + r, q = row / 3, cc = row % 3;
+                const double v = DMUL(DSUB(S[(q * 3 + cc) * WS_NC + c], tgt[q * 4 + cc]), tgt[q * 4 + 3]);
+                s.Jc[r * WS_LDJ + c] = DMUL(DSUB(v, f[row]), rdx);
+            }
+        }
+    }
+};
+
 // ---- triangulation refine residual (mv_math_util.py:190-202): rows (view v, point k) -> v*K + k ----
 // a chunk = a third of the points of one view (K <= 18: at most 6 rows)
 struct TriRes {
@@ -624,6 +678,61 @@ __global__ void __launch_bounds__(32)
     }
 }
 
+// 3D-target solves (the reference's `use_only_reproj = False` branch, inverse_kinematics.py:409-415): one warp per solve.
+// target [M,16,4]; stages bit 0 = solve_pose (root + angles), bit 1 = solve_pose_bone_lens (+ the 11 side lengths).
+struct Ik3dSh {
+    TrfWarp t;
+    double f[64], fn[64];
+    double tgt[MVMC_N_IKJ * 4];
+    double posb[MVMC_N_IKJ * 3];
+    double Rloc[MVMC_N_B18 * 9];
+};
+__global__ void __launch_bounds__(32)
+    k_ik_targets(const double* __restrict__ target, const double* __restrict__ x0, const int* __restrict__ max_nfev, int stages,
+                 int M, double* __restrict__ x_out, double* __restrict__ joints, int* __restrict__ info, double* __restrict__ cost_out) {
+    MVMC_DYN_SMEM(Ik3dSh, shp);
+    Ik3dSh& sh = *shp;
+    const int lane = threadIdx.x & 31;
+    for (int mI = blockIdx.x; mI < M; mI += gridDim.x) {
+        __syncwarp();
+        for (int e = lane; e < MVMC_N_IKJ * 4; e += 32) sh.tgt[e] = target[(size_t)mI * MVMC_N_IKJ * 4 + e];
+        for (int e = lane; e < MVMC_N_PARAM; e += 32) sh.t.x[e] = x0[(size_t)mI * MVMC_N_PARAM + e];
+        __syncwarp();
+        Ik3dRes res{sh.tgt, sh.posb, sh.Rloc};
+        TrfResult r[2];
+        int ncols[2] = {0, 0};
+#pragma unroll 1
+        for (int stage = 0; stage < 2; stage++) {
+            r[stage].nfev = 0;
+            r[stage].njev = 0;
+            r[stage].status = 0;
+            r[stage].cost = 0.0;
+            if (!((stages >> stage) & 1)) continue;
+            int n_opt;
+            double x2_dead;
+            bool has_dead;
+            const int ncol = ik_columns(sh.t, nullptr, stage == 0 ? 57 : MVMC_N_PARAM, n_opt, x2_dead, has_dead);
+            ncols[stage] = n_opt;
+            if (ncol > WS_NC) r[stage].status = -2;
+            else if (ncol > 0) r[stage] = trf_solve_warp(sh.t, res, ncol, n_opt, x2_dead, has_dead, max_nfev[mI], sh.f, sh.fn);
+            __syncwarp();
+        }
+        for (int e = lane; e < MVMC_N_PARAM; e += 32) x_out[(size_t)mI * MVMC_N_PARAM + e] = sh.t.x[e];
+        local_rots(sh.t.x, sh.Rloc);
+        fk_store(sh.t.x, sh.Rloc, -1, 0.0, joints + (size_t)mI * MVMC_N_B18 * 3, 1, false, lane == 0);
+        if (lane == 0) {
+            for (int q = 0; q < 2; q++) {
+                info[(size_t)mI * 8 + 4 * q] = r[q].nfev;
+                info[(size_t)mI * 8 + 4 * q + 1] = r[q].njev;
+                info[(size_t)mI * 8 + 4 * q + 2] = r[q].status;
+                info[(size_t)mI * 8 + 4 * q + 3] = ncols[q];
+                cost_out[(size_t)mI * 2 + q] = r[q].cost;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void k_fk(const double* __restrict__ params, int M, double* __restrict__ joints) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
@@ -770,6 +879,19 @@ extern "C" int mvmc_ik_solve(const double* kps2d, const double* Psel, const int*
     if (M <= 0 || V < 2 || V > MVMC_MAX_SEL) return MVMC_ERR_INVALID;
     return mvmc_ik_launch(kps2d, Psel, n_views, x0, birth, max_nfev, free_mask, M, M, M, 0, V, V, (int*)workspace, x_out,
                           joints, info, cost, stream);
+}
+
+extern "C" int mvmc_ik_solve_targets(const double* target, const double* x0, const int* max_nfev, int stages, int M,
+                                     double* x_out, double* joints, int* info, double* cost, void* stream) {
+    if (!target || !x0 || !max_nfev || !x_out || !joints || !info || !cost || M <= 0 || stages < 1 || stages > 3)
+        return MVMC_ERR_INVALID;
+    int rc = ensure_skeleton();
+    if (rc) return rc;
+    MVMC_CUDA_OK(cudaFuncSetAttribute(k_ik_targets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ik3dSh)));
+    MVMC_LAUNCH(k_ik_targets, dim3(ik_grid(M)), dim3(32), sizeof(Ik3dSh), stream, target, x0, max_nfev, stages, M, x_out, joints,
+                info, cost);
+    MVMC_CHECK_LAUNCH("k_ik_targets");
+    return MVMC_OK;
 }
 
 extern "C" int mvmc_triangulate(const double* obs, const double* Psel, const int* n_views, int M, int V, int K,

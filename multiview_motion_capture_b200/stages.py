@@ -189,3 +189,18 @@ def ik_solve(kps2d, Psel, n_views, x0, birth=None, max_nfev=None, free_mask=None
     check(lib.mvmc_ik_solve(ptr(kps2d), ptr(Psel), ptr(n_views), ptr(x0), bp, ptr(max_nfev), fp, M, V, ptr(ws), ptr(x_out),
                             ptr(joints), ptr(info), ptr(cost), _stream(kps2d)), "mvmc_ik_solve")
     return x_out, joints, info, cost
+
+
+def ik_solve_targets(target, x0, max_nfev, stages=3):
+    """inverse_kinematics.py:280-336 (solve_pose, solve_pose_bone_lens) batched: target [M,16,4] (x, y, z, score at the 16 IK
+    joints), x0 [M,68], max_nfev [M]; stages bit 0 = root + angles, bit 1 = + bone lengths. Returns like ik_solve."""
+    target, x0, max_nfev = _c(target, f64), _c(x0, f64), _c(max_nfev, i32)
+    M = target.shape[0]
+    dev = target.device
+    x_out = torch.zeros((M, N_PARAM), dtype=f64, device=dev)
+    joints = torch.zeros((M, N_B18, 3), dtype=f64, device=dev)
+    info = torch.zeros((M, 2, 4), dtype=i32, device=dev)
+    cost = torch.zeros((M, 2), dtype=f64, device=dev)
+    check(_lib.get_lib().mvmc_ik_solve_targets(ptr(target), ptr(x0), ptr(max_nfev), int(stages), M, ptr(x_out), ptr(joints), ptr(info),
+                                               ptr(cost), _stream(target)), "mvmc_ik_solve_targets")
+    return x_out, joints, info, cost

@@ -320,14 +320,83 @@ def _pose_ids(tlet, d_frames):
     return ids
 
 
+def make_ik3d_golden(n_records=10):
+    """The 3D-target IK variants (src/inverse_kinematics.py:280-336, dead behind `use_only_reproj = True`) run by the
+    REFERENCE on the solves of the Shelf golden: for each recorded update / birth, triangulate (post_optimize) then
+    solve_pose and solve_pose_bone_lens with the reference's own functions. -> tests/golden/ik3d_ref.npz"""
+    ref = ref_shim.load()
+    ik = ref.ik
+    skel = ik.load_skeleton()
+    inp = np.load(os.path.join(GOLD, "shelf_inputs.npz"))
+    g = np.load(os.path.join(GOLD, "shelf_ref.npz"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import GoldenTable, fkey
+    tab = GoldenTable(g)
+    coco = ref.pose_def.conversion_openpose_25_to_coco
+    out, n = {}, 0
+    solver_cls = ik.PoseSolver
+    for f in (1, 2, 3, 30, 31):
+        k = fkey(f)
+        ids_before = tab.seek(f)
+        for u, tid in enumerate(g[k + "upd_ids"].tolist()):
+            if n >= n_records:
+                break
+            views = np.nonzero(g[k + "upd_views"][u])[0]
+            pids = g[k + "upd_pose_ids"][u][views]
+            cam_kps = [coco(inp["kps25"][f, v, p]) for v, p in zip(views, pids)]
+            Ps = [inp["K"][v] @ inp["RT"][v] for v in views]
+            birth = tid not in ids_before
+            ps = solver_cls(skel, None, [c.copy() for c in cam_kps], Ps, ref.pose_def.KpsFormat.COCO)   # adds the mid spine, builds the index maps
+            obs3d = ref.mvu.triangulate_point_groups_from_multiple_views_linear(ps.cam_projs, ps.cam_poses_2d, 0.01, True)
+            if birth:
+                root = 0.5 * (obs3d[ps.obs_kps_idx_map[ref.pose_def.KpsType.L_Hip], :3] + obs3d[ps.obs_kps_idx_map[ref.pose_def.KpsType.R_Hip], :3])
+                init = ik.PoseShapeParam(root, np.zeros((18, 3)), skel.ref_side_bone_lens.copy())
+                nfev = 50
+            else:
+                x = tab.table[tid]["param"]
+                init = ik.PoseShapeParam(x[:3].copy(), x[3:57].reshape(18, 3).copy(), x[57:].copy())
+                nfev = 5
+            calls = []
+            real = ik.least_squares
+
+            def spy(fun, x0, **kw):
+                r = real(fun, x0, **kw)
+                calls.append(r)
+                return r
+            ik.least_squares = spy
+            try:
+                p1 = ik.solve_pose(skel, obs3d, ps.obs_kps_idxs, ps.skel_kps_idxs, init, nfev)
+                p2 = ik.solve_pose_bone_lens(skel, obs3d, ps.obs_kps_idxs, ps.skel_kps_idxs, p1, nfev)
+            finally:
+                ik.least_squares = real
+            locs, _ = ik.foward_kinematics(skel, p2)
+            pre = f"r{n}_"
+            out[pre + "frame"], out[pre + "birth"], out[pre + "nfev_cap"] = np.int32(f), np.int32(birth), np.int32(nfev)
+            out[pre + "cam_kps"], out[pre + "P"] = np.array(cam_kps), np.array(Ps)
+            out[pre + "obs3d"] = obs3d
+            out[pre + "obs_idx"], out[pre + "skel_idx"] = np.array(ps.obs_kps_idxs, dtype=np.int32), np.array(ps.skel_kps_idxs, dtype=np.int32)
+            pk = lambda q: np.concatenate([q.root.flatten(), q.euler_angles.flatten(), q.bone_lens.flatten()])
+            out[pre + "x0"], out[pre + "x1"], out[pre + "x2"], out[pre + "joints"] = pk(init), pk(p1), pk(p2), np.array(locs)
+            out[pre + "meta"] = np.array([[c.nfev, c.njev, c.status] for c in calls], dtype=np.int32)
+            out[pre + "cost"] = np.array([c.cost for c in calls])
+            print(f"record {n}: frame {f} track {tid} birth {birth} views {len(views)} meta {out[pre + 'meta'].tolist()} cost {out[pre + 'cost']}")
+            n += 1
+    out["count"] = np.int32(n)
+    np.savez_compressed(os.path.join(GOLD, "ik3d_ref.npz"), **out)
+    print("wrote ik3d_ref.npz", n)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["shelf", "synth", "warm"])
+    ap.add_argument("what", choices=["shelf", "synth", "warm", "ik3d"])
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--out", default=None)
     ap.add_argument("--scene", default=None, help="warm: one scene of synthetic.WARM_SCENES (default all)")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
+    if args.what == "ik3d":
+        make_ik3d_golden()
+        return
     if args.what == "warm":
         # tracked (steady-state) frames at the BASELINE shapes: the reference's tracker is seeded from the generator's
         # ground truth at frame `first - 1` (warm_start_tracks) and then runs frames first..last itself

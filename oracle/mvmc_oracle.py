@@ -845,6 +845,51 @@ def solve_ik(skel: Skeleton, init: Optional[PoseParam], cam_kps: Sequence[np.nda
     return p2, joints
 
 
+def _joints3d_residual(skel: Skeleton, target: np.ndarray, root, euler, lens) -> np.ndarray:
+    """target (16,4) = obs_pose_3d[obs_kps_idxs] (x, y, z, score)."""
+    pos, _ = forward_kinematics(skel, root, euler, lens)
+    d = pos[IK_SKEL_IDX, :] - target[:, :3]
+    d = d * target[:, -1:]
+    return d.flatten()
+
+
+def solve_pose_3d(skel: Skeleton, obs_pose_3d: np.ndarray, init: PoseParam, max_nfev=5, lsq=None):
+    """solve_pose (src/inverse_kinematics.py:280-306): root + angles against 3D targets, bone lengths fixed."""
+    lsq = lsq or trf_least_squares
+    target = obs_pose_3d[IK_OBS_IDX, :]
+    x0 = np.concatenate([init.root.flatten(), init.euler.flatten()])
+    r = lsq(lambda x: _joints3d_residual(skel, target, x[:3], x[3:].reshape((-1, 3)), init.bone_lens), x0, max_nfev)
+    return PoseParam(r.x[:3], r.x[3:].reshape((-1, 3)), init.bone_lens), r
+
+
+def solve_pose_bone_lens_3d(skel: Skeleton, obs_pose_3d: np.ndarray, init: PoseParam, max_nfev=5, lsq=None):
+    """solve_pose_bone_lens (src/inverse_kinematics.py:309-336): + the 11 side bone lengths."""
+    lsq = lsq or trf_least_squares
+    target = obs_pose_3d[IK_OBS_IDX, :]
+    nj = skel.n_joints
+    x0 = np.concatenate([init.root.flatten(), init.euler.flatten(), init.bone_lens.flatten()])
+    r = lsq(lambda x: _joints3d_residual(skel, target, x[:3], x[3:3 + nj * 3].reshape((-1, 3)), x[3 + nj * 3:]), x0, max_nfev)
+    return PoseParam(r.x[:3], r.x[3:3 + nj * 3].reshape((-1, 3)), r.x[3 + nj * 3:]), r
+
+
+def solve_ik_3d(skel: Skeleton, init: Optional[PoseParam], cam_kps: Sequence[np.ndarray], Ps: Sequence[np.ndarray], lsq=None):
+    """PoseSolver.solve with use_only_reproj = False (src/inverse_kinematics.py:385-415): triangulate (with the 2-nfev
+    refine), then solve_pose and solve_pose_bone_lens against the triangulated points. Returns (PoseParam, joints, log)."""
+    obs18 = [add_mid_spine(k) for k in cam_kps]
+    if init is None:
+        p3 = triangulate_groups(Ps, obs18, 0.01, True)
+        root = 0.5 * (p3[COCO_L_HIP, :3] + p3[COCO_R_HIP, :3])
+        init = PoseParam(root, np.zeros((skel.n_joints, 3), dtype=root.dtype), skel.side_bone_lens.copy())
+        max_nfev = 50
+    else:
+        max_nfev = 5
+    obs_pose_3d = triangulate_groups(Ps, obs18, 0.01, True)
+    p1, r1 = solve_pose_3d(skel, obs_pose_3d, init, max_nfev, lsq)
+    p2, r2 = solve_pose_bone_lens_3d(skel, obs_pose_3d, p1, max_nfev, lsq)
+    joints, _ = forward_kinematics(skel, p2.root, p2.euler, p2.bone_lens)
+    return p2, joints, dict(obs_pose_3d=obs_pose_3d, r1=r1, r2=r2, init=init)
+
+
 def _triangulate_groups_with(lsq, Ps, groups, min_score):
     out = triangulate_groups(Ps, groups, min_score, False)
     n_cams = len(Ps)

@@ -67,3 +67,8 @@ def test_clip_streams_equal_clip_batch(emu):
     """The grouped host-side runner (ClipStreams) returns the records of ClipBatch, clip for clip."""
     from pipeline_checks import check_clip_streams_equal_clip_batch
     check_clip_streams_equal_clip_batch(DEV, B=2, frames=(2,))
+
+
+def test_ik_3d_target_variants(emu):
+    """SURVEY.md 8f-4 through the emulator: two births and two updates of tests/golden/ik3d_ref.npz."""
+    print(SC.check_ik_targets(DEV, limit=4))

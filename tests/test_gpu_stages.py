@@ -158,3 +158,9 @@ def test_ik_teacher_forced_inside_reference_noise_envelope(cuda):
     assert q(dang)[0] <= 1.5 * q(eang)[0]
     assert q(rel)[0] <= 2.0 * q(erel)[0] + 1e-6 and q(rel)[1] <= 2.0 * q(erel)[1] + 1e-6
     assert dleaf.max() <= 1e-6                   # structurally unobservable DOFs stay put (reference: <= 6.4e-8)
+
+
+def test_ik_3d_target_variants(cuda):
+    w = SC.check_ik_targets(DEV)
+    print(f"PARITY 3D-target IK (solve_pose / solve_pose_bone_lens) vs reference: births max joint diff {w['birth_joints']:.2e} m, "
+          f"updates max joint diff {w['upd_joints']*1e3:.2f} mm, max relative final-cost diff {w['upd_cost']:.2e}")

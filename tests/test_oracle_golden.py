@@ -188,3 +188,20 @@ def test_numpy_float32_restatement():
     for lo, hi in ((-20, 20), (-5, 5), (-80, 80)):
         x = rng.uniform(lo, hi, size=1_000_000).astype(np.float32)
         assert np.array_equal(np.exp(x), o.np32_exp(x)), (lo, hi)
+
+
+def test_ik_3d_target_variants_bit_exact():
+    """the oracle's solve_pose / solve_pose_bone_lens against the REAL reference's
+    (tests/golden/ik3d_ref.npz): parameters bit-identical, same (nfev, njev, status)."""
+    import os
+    from helpers import GOLD
+    g = np.load(os.path.join(GOLD, "ik3d_ref.npz"))
+    skel = o.load_skeleton()
+    for i in range(int(g["count"])):
+        init = None if int(g[f"r{i}_birth"]) else o.PoseParam.unpack(g[f"r{i}_x0"].copy())
+        p2, joints, log = o.solve_ik_3d(skel, init, list(g[f"r{i}_cam_kps"]), list(g[f"r{i}_P"]))
+        assert np.array_equal(log["obs_pose_3d"], g[f"r{i}_obs3d"]), i
+        assert np.array_equal(log["init"].pack(), g[f"r{i}_x0"]), i
+        for r, m in zip((log["r1"], log["r2"]), g[f"r{i}_meta"]):
+            assert (r.nfev, r.njev, r.status) == tuple(int(v) for v in m), i
+        assert np.array_equal(p2.pack(), g[f"r{i}_x2"]) and np.array_equal(joints, g[f"r{i}_joints"]), i
