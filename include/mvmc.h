@@ -115,6 +115,38 @@ int mvmc_assign_listed(const uint32_t* xbin, const int* dim_groups, const int* i
  * match_mat [B,N,N] bytes (leading n x n block written): match[j][i] = 1 iff i is a leader and j belongs to it. */
 int mvmc_transform_closure(const uint32_t* xbin, const int* n, int B, int N, uint8_t* match_mat, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Alternative matchers: kept for A/B against the ALS matcher.
+ * ---------------------------------------------------------------------------------------------- */
+/* The float64 distance matrix alone: A2 (calc_epipolar_error) for 2D-2D pairs, A3 for 2D-3D pairs, NaN for same-view and
+ * 3D-3D pairs, 0 on the diagonal - with or without tracks (mvmc_affinity switches to the float32 path without tracks). */
+int mvmc_distances(const double* kps, const double* P, const double* F, const double* trk_joints, const int* n_trk,
+                   const int* dim_groups, const int* idx_view, const int* idx_pose, int B, int C, int Pmax, int Tmax,
+                   double* dst, void* stream);
+/* scipy.optimize.linear_sum_assignment (third party; rectangular shortest-augmenting-path algorithm, Crouse 2016, with
+ * SciPy's scan order and tie rule) for B problems: cost [B,R,Cc] row-major, n_rows/n_cols [B] live sizes ->
+ * col_of_row [B,R] (-1 = unassigned), status [B] (0, -1 = NaN / infeasible: SciPy raises). min(R,Cc) <= 64, max <= 256. */
+int mvmc_linear_sum_assignment(const double* cost, const int* n_rows, const int* n_cols, int B, int R, int Cc,
+                               int* col_of_row, int* status, void* stream);
+/* motion_capture.py:166-241 match_objects_across_views with PoseAssociation.calc_epipolar_error (:81-93): the view with the
+ * most poses seeds one group per pose; every other view (ascending) is assigned to the groups by a Hungarian step on the
+ * mean epipolar distance to the group's members; a matched pose whose running distance sum exceeds `threshold` starts its
+ * own group, as does every unmatched pose. dst = mvmc_distances' matrix [B,N,N], dim_groups as mvmc_prepare writes them.
+ * group_of [B,N]: group index of every 2D pose (-1 for track slots / padding), groups numbered in creation order;
+ * n_groups [B]; status [B]. workspace: mvmc_match_views_workspace_bytes(B). */
+size_t mvmc_match_views_workspace_bytes(int B);
+int mvmc_match_views_hungarian(const double* dst, const int* dim_groups, int B, int C, int N, double threshold,
+                               void* workspace, int* group_of, int* n_groups, int* status, void* stream);
+/* motion_capture.py:844-871 tracklet_to_poses_association with :845-850 tracklet_to_pose_2d_cost and
+ * mv_math_util.py:11-32 (unproject_uv_to_rays, points_to_lines_distances): per (clip, view) the cost of (track t, pose p) is
+ * the mean distance of the track's 3D joints to the camera rays through the pose's 2D joints (15 common joints, no score
+ * mask), assigned by a Hungarian step, matches dearer than max_dst dropped.
+ * Kr_inv [B,C,3,3] = R^T K^-1, cam_loc [B,C,3] (common.py:7-17), keep [B,C,Pmax] (mvmc_prepare) ->
+ * match [B,C,Tmax] pose id or -1, cost [B,C,Tmax,Pmax] (may be NULL), status [B*C]. */
+int mvmc_tracklet_pose_association(const double* trk_joints, const int* n_trk, const double* kps, const uint8_t* keep,
+                                   const double* Kr_inv, const double* cam_loc, int B, int C, int Pmax, int Tmax,
+                                   double max_dst, int* match, double* cost, int* status, void* stream);
+
 /* B1 + B2 — mv_math_util.py:152-240 (DLT per joint + optional 2-nfev TRF refine).
  * obs [M,V,K,3] (x,y,score), Psel [M,V,3,4], n_views [M] (<= V <= MVMC_MAX_SEL), K <= 18 joints.
  * out [M,K,4] = (x,y,z,mean score). refine_nfev = 0 disables the refine. */

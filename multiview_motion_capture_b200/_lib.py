@@ -46,6 +46,11 @@ _SIGNATURES = {
     "mvmc_match_als": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "mvmc_assign": (c_int, [_P] * 5 + [c_int] * 5 + [_P] * 7 + [_P]),
     "mvmc_assign_listed": (c_int, [_P] * 5 + [c_int] * 5 + [_P] * 9 + [_P]),
+    "mvmc_distances": (c_int, [_P] * 8 + [c_int] * 4 + [_P, _P]),
+    "mvmc_linear_sum_assignment": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "mvmc_match_views_workspace_bytes": (c_size_t, [c_int]),
+    "mvmc_match_views_hungarian": (c_int, [_P, _P, c_int, c_int, c_int, c_double, _P, _P, _P, _P, _P]),
+    "mvmc_tracklet_pose_association": (c_int, [_P] * 6 + [c_int] * 4 + [c_double, _P, _P, _P, _P]),
     "mvmc_transform_closure": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "mvmc_triangulate": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_double, c_int, _P, _P]),
     "mvmc_fk": (c_int, [_P, c_int, _P, _P]),

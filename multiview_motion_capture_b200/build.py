@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmvmc.so")
-SOURCES = ["affinity.cu", "als.cu", "assign.cu", "ik.cu", "ingest.cu", "pipeline.cu"]
+SOURCES = ["affinity.cu", "als.cu", "assign.cu", "ik.cu", "ingest.cu", "matchers.cu", "pipeline.cu"]
 # the same source built again with other tile shapes (see als.cu: AL_VARIANT)
 VARIANTS = [("als.cu", "als_small.o", ["-DAL_VARIANT=small", "-DAL_FM_=3", "-DAL_THREADS_=128"])]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

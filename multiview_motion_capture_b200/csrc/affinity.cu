@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(AFF_TILE* AFF_TILE)
     k_affinity(const double* __restrict__ kps, const double* __restrict__ P, const double* __restrict__ F,
                const float* __restrict__ F32, const double* __restrict__ trk_joints, const int* __restrict__ n_trk,
                const int* __restrict__ dim_groups, const int* __restrict__ idx_view, const int* __restrict__ idx_pose,
-               int C, int Pmax, int Tmax, double* __restrict__ dst) {
+               int C, int Pmax, int Tmax, int force_f64, double* __restrict__ dst) {
     const int b = blockIdx.z;
     const int N = Tmax + C * Pmax;
     const int n = dim_groups[b * (C + 2) + C + 1];
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(AFF_TILE* AFF_TILE)
     const double* ki = s_item[threadIdx.y];
     const double* kj = s_item[AFF_TILE + threadIdx.x];
     double d;
-    if (T > 0) {
+    if (T > 0 || force_f64) {
         if (i == j) d = 0.0;
         else if (vi >= 0 && vi == vj) d = NAN;
         else if (vi >= 0 && vj >= 0) d = epipolar_error(F + ((size_t)(b * C + vi) * C + vj) * 9, ki, kj);
@@ -546,9 +546,25 @@ extern "C" int mvmc_affinity(const double* kps, const double* P, const double* F
     const int N = Tmax + C * Pmax;
     const int tiles = (N + AFF_TILE - 1) / AFF_TILE;
     MVMC_LAUNCH(k_affinity, dim3(tiles, tiles, B), dim3(AFF_TILE, AFF_TILE), 0, stream, kps, P, F, F32, trk_joints, n_trk,
-                dim_groups, idx_view, idx_pose, C, Pmax, Tmax, dst);
+                dim_groups, idx_view, idx_pose, C, Pmax, Tmax, 0, dst);
     MVMC_CHECK_LAUNCH("k_affinity");
     MVMC_LAUNCH(k_simfill, dim3(B), dim3(256), 0, stream, n_trk, dim_groups, C, N, dst, sim);
     MVMC_CHECK_LAUNCH("k_simfill");
+    return MVMC_OK;
+}
+
+// The float64 distance matrix alone (A2 / A3 entries, NaN for same-view and track-track pairs, no NaN fill, no similarity),
+// also when a clip has no tracks: what the Hungarian matchers of matchers.cu take their costs from.
+extern "C" int mvmc_distances(const double* kps, const double* P, const double* F, const double* trk_joints, const int* n_trk,
+                              const int* dim_groups, const int* idx_view, const int* idx_pose, int B, int C, int Pmax, int Tmax,
+                              double* dst, void* stream) {
+    if (!kps || !P || !F || !trk_joints || !n_trk || !dim_groups || !idx_view || !idx_pose || !dst) return MVMC_ERR_INVALID;
+    if (B <= 0 || C <= 0 || C > MVMC_MAX_VIEWS || Pmax <= 0 || Pmax > MVMC_MAX_POSES || Tmax < 0 || Tmax > MVMC_MAX_TRACKS)
+        return MVMC_ERR_INVALID;
+    const int N = Tmax + C * Pmax;
+    const int tiles = (N + AFF_TILE - 1) / AFF_TILE;
+    MVMC_LAUNCH(k_affinity, dim3(tiles, tiles, B), dim3(AFF_TILE, AFF_TILE), 0, stream, kps, P, F, (const float*)nullptr, trk_joints,
+                n_trk, dim_groups, idx_view, idx_pose, C, Pmax, Tmax, 1, dst);
+    MVMC_CHECK_LAUNCH("k_affinity");
     return MVMC_OK;
 }

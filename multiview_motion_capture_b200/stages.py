@@ -204,3 +204,61 @@ def ik_solve_targets(target, x0, max_nfev, stages=3):
     check(_lib.get_lib().mvmc_ik_solve_targets(ptr(target), ptr(x0), ptr(max_nfev), int(stages), M, ptr(x_out), ptr(joints), ptr(info),
                                                ptr(cost), _stream(target)), "mvmc_ik_solve_targets")
     return x_out, joints, info, cost
+
+
+def distances(kps, P, F, trk_joints, n_trk, prep):
+    """Float64 distance matrix only (mvmc_distances): [B,N,N]."""
+    kps, P, F, trk_joints, n_trk = _c(kps, f64), _c(P, f64), _c(F, f64), _c(trk_joints, f64), _c(n_trk, i32)
+    B, C, Pmax = kps.shape[:3]
+    Tmax, N = prep["Tmax"], prep["N"]
+    dst = torch.zeros((B, N, N), dtype=f64, device=kps.device)
+    check(_lib.get_lib().mvmc_distances(ptr(kps), ptr(P), ptr(F), ptr(trk_joints), ptr(n_trk), ptr(prep["dim_groups"]),
+                                        ptr(prep["idx_view"]), ptr(prep["idx_pose"]), B, C, Pmax, Tmax, ptr(dst), _stream(kps)),
+          "mvmc_distances")
+    return dst
+
+
+def linear_sum_assignment(cost, n_rows=None, n_cols=None):
+    """scipy.optimize.linear_sum_assignment batched on the device: cost [B,R,C] -> col_of_row [B,R] (-1 unassigned), status [B]."""
+    cost = _c(cost, f64)
+    B, R, Cc = cost.shape
+    dev = cost.device
+    n_rows = torch.full((B,), R, dtype=i32, device=dev) if n_rows is None else _c(n_rows, i32)
+    n_cols = torch.full((B,), Cc, dtype=i32, device=dev) if n_cols is None else _c(n_cols, i32)
+    col = torch.full((B, R), -1, dtype=i32, device=dev)
+    status = torch.zeros((B,), dtype=i32, device=dev)
+    check(_lib.get_lib().mvmc_linear_sum_assignment(ptr(cost), ptr(n_rows), ptr(n_cols), B, R, Cc, ptr(col), ptr(status), _stream(cost)),
+          "mvmc_linear_sum_assignment")
+    return col, status
+
+
+def match_views_hungarian(dst, dim_groups, threshold):
+    """motion_capture.py:166-241 on the device: dst [B,N,N] (distances()), dim_groups [B,C+2] -> group_of [B,N], n_groups [B], status [B]."""
+    dst, dim_groups = _c(dst, f64), _c(dim_groups, i32)
+    B, N, _ = dst.shape
+    C = dim_groups.shape[1] - 2
+    dev = dst.device
+    lib = _lib.get_lib()
+    ws = torch.empty(lib.mvmc_match_views_workspace_bytes(B) // 8, dtype=f64, device=dev)
+    gof = torch.full((B, N), -1, dtype=i32, device=dev)
+    ng = torch.zeros((B,), dtype=i32, device=dev)
+    status = torch.zeros((B,), dtype=i32, device=dev)
+    check(lib.mvmc_match_views_hungarian(ptr(dst), ptr(dim_groups), B, C, N, float(threshold), ptr(ws), ptr(gof), ptr(ng), ptr(status),
+                                         _stream(dst)), "mvmc_match_views_hungarian")
+    return gof, ng, status
+
+
+def tracklet_pose_association(trk_joints, n_trk, kps, keep, Kr_inv, cam_loc, max_dst=0.1):
+    """motion_capture.py:844-871 on the device -> match [B,C,Tmax] (pose id or -1), cost [B,C,Tmax,Pmax], status [B*C]."""
+    trk_joints, n_trk, kps, Kr_inv, cam_loc = _c(trk_joints, f64), _c(n_trk, i32), _c(kps, f64), _c(Kr_inv, f64), _c(cam_loc, f64)
+    keep = _c(keep, torch.uint8)
+    B, C, Pmax = kps.shape[:3]
+    Tmax = trk_joints.shape[1]
+    dev = kps.device
+    match = torch.full((B, C, Tmax), -1, dtype=i32, device=dev)
+    cost = torch.zeros((B, C, Tmax, Pmax), dtype=f64, device=dev)
+    status = torch.zeros((B * C,), dtype=i32, device=dev)
+    check(_lib.get_lib().mvmc_tracklet_pose_association(ptr(trk_joints), ptr(n_trk), ptr(kps), ptr(keep), ptr(Kr_inv), ptr(cam_loc), B, C,
+                                                        Pmax, Tmax, float(max_dst), ptr(match), ptr(cost), ptr(status), _stream(kps)),
+          "mvmc_tracklet_pose_association")
+    return match, cost, status

@@ -386,9 +386,69 @@ def make_ik3d_golden(n_records=10):
     print("wrote ik3d_ref.npz", n)
 
 
+def make_alt_matcher_golden():
+    """The reference's alternative matchers (dead code there) run by the REFERENCE on golden frames:
+    match_objects_across_views (src/motion_capture.py:166-241) and MvTracker.tracklet_to_poses_association (:852-871).
+    -> tests/golden/altmatch_ref.npz"""
+    ref = ref_shim.load()
+    mc = ref.mc
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import GoldenTable, fkey
+    import contextlib
+    import io
+    out, n = {}, 0
+    src_idx, dst_idx = ref.pose_def.get_common_kps_idxs(ref.pose_def.KpsFormat.COCO, ref.pose_def.KpsFormat.BASIC_18)
+    out["common_coco"], out["common_b18"] = np.array(src_idx, dtype=np.int32), np.array(dst_idx, dtype=np.int32)
+    for name, frames in (("shelf", (1, 2, 50, 120, 250)), ("synth_c8p6", (2, 3)), ("warm_c8p16", (3,)), ("warm_c8p32", (3,))):
+        inp = np.load(os.path.join(GOLD, f"{name}_inputs.npz"))
+        g = np.load(os.path.join(GOLD, f"{name}_ref.npz"))
+        packed = {k: inp[k] for k in inp.files}
+        calibs = calibs_from_packed(ref, packed)
+        tab = GoldenTable(g)
+        for f in frames:
+            d_frames = frames_from_packed(ref, packed, f, calibs)
+            with contextlib.redirect_stdout(io.StringIO()):
+                d_frames = [mc.filter_bad_pose(fr, 0.01, 4, 5) for fr in d_frames]
+            pre = f"r{n}_"
+            out[pre + "scene"], out[pre + "frame"] = np.array(name), np.int32(f)
+            for ti, thr in enumerate((200.0, 25.0)):
+                try:
+                    grps = mc.match_objects_across_views(f, d_frames, False, thr, 0.01)
+                    rows = [(gi, vid - 1, pid) for gi, gr in enumerate(grps) for vid, (pid, _) in zip(gr.view_ids, gr.id_poses)]
+                    out[pre + f"raises{ti}"] = np.int32(0)
+                except ValueError:     # a pose pair without a commonly visible joint: NaN cost, SciPy's assignment raises
+                    rows = []
+                    out[pre + f"raises{ti}"] = np.int32(1)
+                out[pre + f"groups{ti}"] = np.array(rows, dtype=np.int32).reshape(-1, 3)
+                out[pre + f"thr{ti}"] = np.float64(thr)
+            # 3D ray association against the reference's own tracks before this frame
+            joints = tab.joints(f)
+
+            class _T:
+                def __init__(self, j):
+                    self.last_pose_3d = ref.pose_def.Pose(ref.pose_def.KpsFormat.BASIC_18, j.reshape(18, 3), np.ones((18, 1)), None)
+            tl = [_T(j) for j in joints]
+            rows, costs = [], []
+            for v, fr in enumerate(d_frames):
+                for dmax in (0.1,):
+                    m = mc.MvTracker.tracklet_to_poses_association(tl, fr, max_dst=dmax)
+                    rows += [(v, t, p) for t, p in m]
+                for t, tlet in enumerate(tl):
+                    for pid, pose in fr.poses.items():
+                        costs.append((v, t, pid, mc.MvTracker.tracklet_to_pose_2d_cost(tlet, pose, fr.calib)))
+            out[pre + "ray_matches"] = np.array(rows, dtype=np.int32).reshape(-1, 3)
+            out[pre + "ray_costs"] = np.array(costs, dtype=np.float64).reshape(-1, 4)
+            print(f"record {n}: {name} frame {f}: groups {len(set(out[pre + 'groups0'][:, 0].tolist()))} / "
+                  f"{len(set(out[pre + 'groups1'][:, 0].tolist()))}, ray matches {len(rows)}")
+            n += 1
+    out["count"] = np.int32(n)
+    np.savez_compressed(os.path.join(GOLD, "altmatch_ref.npz"), **out)
+    print("wrote altmatch_ref.npz", n)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["shelf", "synth", "warm", "ik3d"])
+    ap.add_argument("what", choices=["shelf", "synth", "warm", "ik3d", "altmatch"])
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--out", default=None)
     ap.add_argument("--scene", default=None, help="warm: one scene of synthetic.WARM_SCENES (default all)")
@@ -396,6 +456,9 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     if args.what == "ik3d":
         make_ik3d_golden()
+        return
+    if args.what == "altmatch":
+        make_alt_matcher_golden()
         return
     if args.what == "warm":
         # tracked (steady-state) frames at the BASELINE shapes: the reference's tracker is seeded from the generator's

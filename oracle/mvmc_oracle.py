@@ -945,6 +945,95 @@ def chain_fk(offsets: np.ndarray, parents: np.ndarray, rotmats: np.ndarray, root
 
 
 # ----------------------------------------------------------------------------------------------
+# SURVEY.md 8f-3  alternative matchers (dead code in the reference, kept for A/B):
+#   match_objects_across_views  src/motion_capture.py:166-241 with PoseAssociation :44-101
+#   tracklet_to_poses_association  src/motion_capture.py:844-871 with src/mv_math_util.py:11-32
+# scipy.optimize.linear_sum_assignment is third party (called directly, as the reference does).
+# ----------------------------------------------------------------------------------------------
+# COCO / BASIC_18 indices of the 15 common joints in COCO order (get_common_kps_idxs(COCO, BASIC_18), src/pose_def.py:288-298)
+RAY_COCO = np.array([0, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16])
+RAY_B18 = np.array([15, 16, 17, 9, 12, 10, 13, 11, 14, 1, 4, 2, 5, 3, 6])
+
+
+def epipolar_matrix(view_kps: Sequence[np.ndarray], Ps: Sequence[np.ndarray]):
+    """(n, n) calc_epipolar_error of every ordered cross-view pose pair (NaN: same view, or no commonly valid joint), and the
+    views' offsets [0, P_0, P_0 + P_1, ...]."""
+    off = np.cumsum([0] + [len(v) for v in view_kps])
+    n = int(off[-1])
+    D = np.full((n, n), np.nan)
+    np.fill_diagonal(D, 0.0)
+    for vi in range(len(view_kps)):
+        for vj in range(len(view_kps)):
+            if vi == vj:
+                continue
+            Fm = fundamental_from_projections(Ps[vi], Ps[vj])
+            for a in range(len(view_kps[vi])):
+                for b in range(len(view_kps[vj])):
+                    D[off[vi] + a, off[vj] + b] = epipolar_error(Fm, view_kps[vi][a], view_kps[vj][b], 0.1)
+    return D, off
+
+
+def match_views_hungarian(dst: np.ndarray, view_offsets, threshold: float):
+    """dst: (n, n) matrix whose 2D-2D entries are calc_epipolar_error(row pose, column pose) (build_dst_sim's `dst` before
+    the NaN fill, or the pair errors themselves); view_offsets: cumulative offsets of the views' poses in dst
+    [o_0, o_1, ..., o_C]. Returns the groups as lists of global indices, in the reference's creation / merge order."""
+    from scipy.optimize import linear_sum_assignment
+    counts = np.diff(view_offsets)
+    init = int(np.argmax(counts))
+    groups = [[g] for g in range(view_offsets[init], view_offsets[init + 1])]
+    for v in range(len(counts)):
+        if v == init or counts[v] < 1:
+            continue
+        poses = list(range(view_offsets[v], view_offsets[v + 1]))
+        cost = np.zeros((len(groups), len(poses)))
+        mask = np.zeros_like(cost).astype(np.int32)
+        for pi, g in enumerate(poses):
+            for hi, h in enumerate(groups):
+                total, too_wrong = 0, False
+                for q in h:
+                    total += dst[q, g]
+                    if total > threshold:
+                        too_wrong = True
+                cost[hi, pi] = total / len(h)
+                mask[hi, pi] = int(too_wrong)
+        rows, cols = linear_sum_assignment(cost)
+        matched = set()
+        for hi, pi in zip(rows, cols):
+            matched.add(pi)
+            if mask[hi, pi] == 1:
+                groups.append([poses[pi]])
+            else:
+                groups[hi].append(poses[pi])
+        for pi, g in enumerate(poses):
+            if pi not in matched:
+                groups.append([g])
+    return groups
+
+
+def tracklet_pose_costs(track_joints: Sequence[np.ndarray], kps_view: np.ndarray, Kr_inv: np.ndarray, cam_loc: np.ndarray):
+    """cost[t, p] = tracklet_to_pose_2d_cost (src/motion_capture.py:845-850): mean over the 15 common joints of the
+    distance between the track's 3D joint and the camera ray through the pose's 2D joint."""
+    cost = np.zeros((len(track_joints), len(kps_view)))
+    for t, j3 in enumerate(track_joints):
+        for p, k2 in enumerate(kps_view):
+            pts = np.concatenate([k2[RAY_COCO, :2], np.ones((15, 1))], axis=1)
+            rays = (Kr_inv @ pts.T).T
+            rays = rays / np.linalg.norm(rays, axis=-1, keepdims=True)
+            d = [np.linalg.norm(np.cross(j3[RAY_B18[i], :3] - cam_loc, rays[i, :3])) for i in range(15)]
+            cost[t, p] = np.mean(d)
+    return cost
+
+
+def tracklet_pose_association(track_joints, kps_view, pose_ids, Kr_inv, cam_loc, max_dst=0.1):
+    from scipy.optimize import linear_sum_assignment
+    if not len(track_joints) or not len(kps_view):
+        return [], np.zeros((len(track_joints), len(kps_view)))
+    cost = tracklet_pose_costs(track_joints, kps_view, Kr_inv, cam_loc)
+    rows, cols = linear_sum_assignment(cost)
+    return [(int(t), int(pose_ids[p])) for t, p in zip(rows, cols) if not cost[t, p] > max_dst], cost
+
+
+# ----------------------------------------------------------------------------------------------
 # L1  tracker lifecycle   (src/motion_capture.py:288-400, 873-963, run loop :1046-1129)
 # ----------------------------------------------------------------------------------------------
 TENTATIVE, CONFIRMED, DEAD = 1, 2, 3

@@ -8,7 +8,7 @@ OUT="$HERE/libmvmc_emu.so"
 FLAGS="-O1 -g -fPIC -std=c++17 -DMVMC_EMU -ffp-contract=off -I$ROOT/include -I$HERE -I$SRC -Wno-unused-variable"
 objs=""
 pids=""
-for f in affinity als assign ik ingest pipeline; do
+for f in affinity als assign ik ingest matchers pipeline; do
   rm -f "$HERE/$f.emu.o"
   g++ $FLAGS -x c++ -c "$SRC/$f.cu" -o "$HERE/$f.emu.o" &
   pids="$pids $!"

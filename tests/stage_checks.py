@@ -400,3 +400,96 @@ def check_ik_targets(dev, limit=None):
             worst["upd_cost"] = max(worst["upd_cost"], abs(both[3][q, 1] - cost[1]) / cost[1])
             assert dj <= 2e-2 and both[3][q, 1] <= cost[0] * (1 + 1e-9), (i, dj)
     return worst
+
+
+# ---------------------------------------------------------------------------------------------------
+def _alt_records():
+    import os
+    from helpers import GOLD
+    g = np.load(os.path.join(GOLD, "altmatch_ref.npz"))
+    return g, [dict(scene=str(g[f"r{i}_scene"]), frame=int(g[f"r{i}_frame"]), i=i) for i in range(int(g["count"]))]
+
+
+def check_lsap(dev, seed=0):
+    """mvmc_linear_sum_assignment against scipy.optimize.linear_sum_assignment: random rectangular problems (assignment and
+    cost identical), ties (cost identical, assignment valid), NaN (status -1, SciPy raises)."""
+    from scipy.optimize import linear_sum_assignment
+    rng = np.random.default_rng(seed)
+    shapes = [(1, 1), (3, 5), (5, 3), (8, 8), (17, 32), (40, 9), (64, 64), (64, 200), (230, 30)]
+    for R, Cc in shapes:
+        B = 4
+        cost = rng.uniform(0, 100, size=(B, R, Cc))
+        cost[1] = np.round(cost[1] / 25)            # many exact ties
+        nr = np.array([R, R, max(1, R - 1), R], np.int32)
+        nc = np.array([Cc, Cc, Cc, max(1, Cc - 2)], np.int32)
+        col, status = S.linear_sum_assignment(T(cost, dev), T(nr, dev, i32), T(nc, dev, i32))
+        col, status = col.cpu().numpy(), status.cpu().numpy()
+        assert (status == 0).all(), (R, Cc, status)
+        for b in range(B):
+            sub = cost[b, :nr[b], :nc[b]]
+            rows, cols = linear_sum_assignment(sub)
+            got_rows = np.nonzero(col[b, :nr[b]] >= 0)[0]
+            got_cols = col[b, got_rows]
+            assert len(got_rows) == min(nr[b], nc[b]) and len(set(got_cols.tolist())) == len(got_cols), (R, Cc, b)
+            assert abs(sub[got_rows, got_cols].sum() - sub[rows, cols].sum()) <= 1e-9 * max(1.0, abs(sub[rows, cols].sum())), (R, Cc, b)
+            if b != 1:
+                assert np.array_equal(got_rows, rows) and np.array_equal(got_cols, cols), (R, Cc, b)
+            assert (col[b, nr[b]:] == -1).all()
+    bad = rng.uniform(size=(1, 4, 6))
+    bad[0, 2, 3] = np.nan
+    _, status = S.linear_sum_assignment(T(bad, dev))
+    assert int(status.cpu().numpy()[0]) == -1
+
+
+def check_alt_matchers(dev, limit=None):
+    """SURVEY.md 8f-3 against what the REAL reference computed (tests/golden/altmatch_ref.npz): the view-by-view Hungarian
+    grouping (match_objects_across_views) at two thresholds - identical groups in identical order, or the same failure where
+    SciPy raises on a NaN cost - and the 3D ray association (tracklet_to_poses_association): costs <= 1e-9 m, identical matches."""
+    g, recs = _alt_records()
+    assert g["common_coco"].tolist() == o.RAY_COCO.tolist() and g["common_b18"].tolist() == o.RAY_B18.tolist()
+    worst = 0.0
+    for r in recs[:limit]:
+        inp, gg = golden(r["scene"])
+        f, i = r["frame"], r["i"]
+        kps = o.body25_to_coco(inp["kps25"])
+        C, Pm = kps.shape[1:3]
+        Pmax = max(Pm, 1)
+        tab = GoldenTable(gg)
+        tj = tab.joints(f)
+        Tn = len(tj)
+        Tmax = max(Tn, 1)
+        kp, n_pose, n_trk, trk = _forced_inputs(r["scene"], f, Pmax, Tmax, tab)
+        Ps = np.array(o.projections(inp["K"], inp["RT"]))
+        prep0 = S.prepare(T(kp, dev), T(n_pose, dev, i32), T(np.zeros(1, np.int32), dev, i32), 0)     # poses only: T = 0
+        D = S.distances(T(kp, dev), T(Ps[None], dev), S.fundamental(T(Ps[None], dev)), T(np.zeros((1, 1, 18, 3)), dev),
+                        T(np.zeros(1, np.int32), dev, i32), prep0)
+        iv, ip = prep0["idx_view"].cpu().numpy()[0], prep0["idx_pose"].cpu().numpy()[0]
+        for ti in (0, 1):
+            gof, ng, status = S.match_views_hungarian(D, prep0["dim_groups"], float(g[f"r{i}_thr{ti}"]))
+            gof, ng, status = gof.cpu().numpy()[0], int(ng.cpu().numpy()[0]), int(status.cpu().numpy()[0])
+            if int(g[f"r{i}_raises{ti}"]):
+                assert status == -1, (r, ti)
+                continue
+            assert status == 0, (r, ti)
+            ref_rows = g[f"r{i}_groups{ti}"]
+            n = int(prep0["dim_groups"].cpu().numpy()[0][-1])
+            got = sorted((int(gof[q]), int(iv[q]), int(ip[q])) for q in range(n))
+            assert ng == len(set(ref_rows[:, 0].tolist())), (r, ti)
+            assert got == sorted(map(tuple, ref_rows.tolist())), (r, ti)
+        # 3D ray association
+        if Tn == 0:
+            assert len(g[f"r{i}_ray_matches"]) == 0
+            continue
+        Kr_inv = np.stack([inp["RT"][v][:3, :3].T @ np.linalg.inv(inp["K"][v]) for v in range(C)])
+        cam_loc = np.stack([-inp["RT"][v][:3, :3].T @ inp["RT"][v][:3, 3] for v in range(C)])
+        prep = S.prepare(T(kp, dev), T(n_pose, dev, i32), T(n_trk, dev, i32), Tmax)
+        match, cost, status = S.tracklet_pose_association(T(trk, dev), T(n_trk, dev, i32), T(kp, dev), prep["keep"], T(Kr_inv[None], dev),
+                                                          T(cam_loc[None], dev), 0.1)
+        match, cost = match.cpu().numpy()[0], cost.cpu().numpy()[0]
+        assert (status.cpu().numpy() == 0).all()
+        for v, t, p, c in g[f"r{i}_ray_costs"]:
+            worst = max(worst, abs(cost[int(v), int(t), int(p)] - c))
+        got = sorted((v, t, int(match[v, t])) for v in range(C) for t in range(Tn) if match[v, t] >= 0)
+        assert got == sorted(map(tuple, g[f"r{i}_ray_matches"].tolist())), (r, got[:5])
+    assert worst <= 1e-9, worst
+    return worst

@@ -72,3 +72,12 @@ def test_clip_streams_equal_clip_batch(emu):
 def test_ik_3d_target_variants(emu):
     """SURVEY.md 8f-4 through the emulator: two births and two updates of tests/golden/ik3d_ref.npz."""
     print(SC.check_ik_targets(DEV, limit=4))
+
+
+def test_linear_sum_assignment(emu):
+    SC.check_lsap(DEV)
+
+
+def test_alternative_matchers(emu):
+    """SURVEY.md 8f-3 through the emulator on the Shelf records."""
+    SC.check_alt_matchers(DEV, limit=6)
