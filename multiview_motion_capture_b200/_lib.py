@@ -132,6 +132,27 @@ def lib_path():
     return _lib_path
 
 
+TORCH_EXT_PATH = os.path.join(_HERE, "lib", "libmvmc_torch.so")
+_ops = None
+
+
+def torch_ops():
+    """`torch.ops.mvmc`: the PyTorch C++ extension over the C-ABI (csrc/torch_ext.cpp), loaded next to the in-tree CUDA
+    library. None when another build of the C-ABI was bound explicitly (use_library). Raises if the extension is missing:
+    build() produces both files."""
+    global _ops
+    if _ops is None:
+        get_lib()
+        if _lib_path != LIB_PATH:
+            return None
+        if not os.path.exists(TORCH_EXT_PATH):
+            raise MvmcError(f"{TORCH_EXT_PATH} is missing: run __graft_entry__.build()")
+        import torch
+        torch.ops.load_library(TORCH_EXT_PATH)
+        _ops = torch.ops.mvmc
+    return _ops
+
+
 def default_device():
     """torch device of the library's buffers: the current CUDA device (raises without one - no CPU fallback)."""
     import torch

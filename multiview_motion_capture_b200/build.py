@@ -58,5 +58,29 @@ def build_cuda(force=False, verbose=True):
     return LIB
 
 
+TORCH_EXT = os.path.join(LIBDIR, "libmvmc_torch.so")
+
+
+def build_torch_ext(force=False, verbose=True):
+    """The PyTorch C++ extension over the C-ABI (csrc/torch_ext.cpp -> lib/libmvmc_torch.so): g++ against the installed
+    torch's headers, linked to libmvmc.so next to it ($ORIGIN rpath). Needs no GPU."""
+    import torch
+    from torch.utils import cpp_extension as ce
+    src = os.path.join(CSRC, "torch_ext.cpp")
+    if not (force or _stale(TORCH_EXT, [src, os.path.join(ROOT, "include", "mvmc.h"), LIB])):
+        return TORCH_EXT
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=libmvmc_torch",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", "-I" + os.path.join(ROOT, "include"),
+           "-I/usr/local/cuda/include"] + ["-isystem" + p for p in ce.include_paths()] + [
+           src, "-o", TORCH_EXT, "-L" + LIBDIR, "-lmvmc", "-L" + tlib, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch",
+           "-Wl,-rpath,$ORIGIN", "-Wl,--no-as-needed"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
+    return TORCH_EXT
+
+
 if __name__ == "__main__":
     print(build_cuda(force="--force" in sys.argv))
+    print(build_torch_ext(force="--force" in sys.argv))

@@ -80,7 +80,11 @@ class ClipBatch:
     def step_device(self, kps, n_pose, frame_idx):
         """Device-resident step: kps [B,C,Pmax,17,3] f64, n_pose [B,C] i32 torch tensors on self.device. Async."""
         assert kps.dtype == torch.float64 and n_pose.dtype == torch.int32 and kps.is_contiguous() and n_pose.is_contiguous()
-        check(self.lib.mvmc_clips_step(self._h, ptr(kps), ptr(n_pose), int(frame_idx), self._stream()), "mvmc_clips_step")
+        ops = _lib.torch_ops() if kps.is_cuda else None
+        if ops is not None:     # the PyTorch C++ extension over the C-ABI (csrc/torch_ext.cpp)
+            ops.clips_step(int(self._h.value), kps, n_pose, int(frame_idx))
+        else:
+            check(self.lib.mvmc_clips_step(self._h, ptr(kps), ptr(n_pose), int(frame_idx), self._stream()), "mvmc_clips_step")
 
     def last_out_device(self):
         """uint8 view [B, sizeof(mvmc_step_out)] of the device records of the last step (no copy)."""
@@ -138,8 +142,12 @@ class ClipBatch:
         if rec is None:
             rec = torch.empty((self.B, cap, 128), dtype=torch.float64, device=self.device)
             count = torch.empty((self.B,), dtype=torch.int32, device=self.device)
-        check(self.lib.mvmc_clips_pack_records(self._h, int(cap), int(clip0), ptr(rec), ptr(count), self._stream()),
-              "mvmc_clips_pack_records")
+        ops = _lib.torch_ops() if rec.is_cuda else None
+        if ops is not None:
+            ops.clips_pack_records(int(self._h.value), int(cap), int(clip0), rec, count)
+        else:
+            check(self.lib.mvmc_clips_pack_records(self._h, int(cap), int(clip0), ptr(rec), ptr(count), self._stream()),
+                  "mvmc_clips_pack_records")
         return rec, count
 
     def set_tracks(self, n_trk, ids, state, hits, tsu, length, param, joints, next_id):

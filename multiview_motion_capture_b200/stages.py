@@ -142,6 +142,8 @@ def assign(xbin, prep, n_trk, C, max_new):
 def triangulate(obs, Psel, n_views, min_score, refine_nfev=0):
     """mv_math_util.py:152-240. obs [M,V,K,3], Psel [M,V,3,4], n_views [M] -> [M,K,4]."""
     obs, Psel, n_views = _c(obs, f64), _c(Psel, f64), _c(n_views, i32)
+    if obs.is_cuda and _lib.torch_ops() is not None:
+        return _lib.torch_ops().triangulate(obs, Psel, n_views, float(min_score), int(refine_nfev))
     M, V, K = obs.shape[:3]
     out = torch.zeros((M, K, 4), dtype=f64, device=obs.device)
     check(_lib.get_lib().mvmc_triangulate(ptr(obs), ptr(Psel), ptr(n_views), M, V, K, float(min_score), int(refine_nfev),
@@ -152,6 +154,8 @@ def triangulate(obs, Psel, n_views, min_score, refine_nfev=0):
 def fk(params):
     """inverse_kinematics.py:176-199. params [M,68] -> joints [M,18,3]."""
     params = _c(params, f64)
+    if params.is_cuda and _lib.torch_ops() is not None:
+        return _lib.torch_ops().fk(params)
     M = params.shape[0]
     out = torch.empty((M, N_B18, 3), dtype=f64, device=params.device)
     check(_lib.get_lib().mvmc_fk(ptr(params), M, ptr(out), _stream(params)), "mvmc_fk")
@@ -179,6 +183,9 @@ def ik_solve(kps2d, Psel, n_views, x0, birth=None, max_nfev=None, free_mask=None
     if max_nfev is None:
         max_nfev = torch.full((M,), 5, dtype=i32, device=dev)
     max_nfev = _c(max_nfev, i32)
+    if kps2d.is_cuda and _lib.torch_ops() is not None:
+        return _lib.torch_ops().ik_solve(kps2d, Psel, n_views, x0, _c(birth, torch.uint8) if birth is not None else None, max_nfev,
+                                         _c(free_mask, torch.uint8) if free_mask is not None else None)
     bp = ptr(_c(birth, torch.uint8)) if birth is not None else None
     fp = ptr(_c(free_mask, torch.uint8)) if free_mask is not None else None
     ws = torch.empty(lib.mvmc_ik_workspace_bytes(M, V) // 8, dtype=f64, device=dev)

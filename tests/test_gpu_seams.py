@@ -102,3 +102,24 @@ def test_step_body25_equals_step(cuda):
         rb = b.step_body25(k25, inp["n_pose"][f][None], f).copy()
         assert ra.tobytes() == rb.tobytes(), f
     a.close(); b.close()
+
+
+def test_torch_extension_is_the_binding_of_the_hot_path(cuda):
+    """The PyTorch C++ extension (csrc/torch_ext.cpp -> lib/libmvmc_torch.so) is loaded on the GPU box, its operators are
+    what stages.* and ClipBatch.step_device call, and they give the bits the raw C-ABI (ctypes) gives."""
+    import ctypes
+    import torch
+    from multiview_motion_capture_b200 import _lib, stages
+    from multiview_motion_capture_b200._lib import check, ptr
+    ops = _lib.torch_ops()
+    assert ops is not None and os.path.exists(_lib.TORCH_EXT_PATH)
+    rng = np.random.default_rng(0)
+    x = torch.as_tensor(rng.normal(0, 0.3, size=(64, 68)), device="cuda:0")
+    a = torch.ops.mvmc.fk(x)
+    b = torch.empty_like(a)
+    check(_lib.get_lib().mvmc_fk(ptr(x), 64, ptr(b), torch.cuda.current_stream().cuda_stream), "mvmc_fk")
+    assert torch.equal(a, b) and torch.equal(stages.fk(x), a)
+    with pytest.raises(RuntimeError):
+        torch.ops.mvmc.fk(x.cpu())          # no CPU implementation is registered: no fallback
+    loaded = open("/proc/self/maps").read()
+    assert "libmvmc_torch.so" in loaded and "libmvmc.so" in loaded
