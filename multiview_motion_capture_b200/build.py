@@ -13,6 +13,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmvmc.so")
 SOURCES = ["affinity.cu", "als.cu", "assign.cu", "ik.cu", "ingest.cu", "matchers.cu", "pipeline.cu"]
+# ik.cu: no implicit FMA contraction (every fused operation in the solver is an explicit fma()), so that the CPU build of
+# the same sources (tests/emu, g++ -ffp-contract=off) reproduces the GPU's results bit for bit (parity of I4)
+PER_FILE_FLAGS = {"ik.cu": ["-fmad=false"]}
 # the same source built again with other tile shapes (see als.cu: AL_VARIANT)
 VARIANTS = [("als.cu", "als_small.o", ["-DAL_VARIANT=small", "-DAL_FM_=3", "-DAL_THREADS_=128"])]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -39,7 +42,7 @@ def build_cuda(force=False, verbose=True):
     nvcc = _nvcc()
     objs = []
     jobs = []
-    for s, name, extra in [(s, s.replace(".cu", ".o"), []) for s in SOURCES] + VARIANTS:
+    for s, name, extra in [(s, s.replace(".cu", ".o"), PER_FILE_FLAGS.get(s, [])) for s in SOURCES] + VARIANTS:
         src = os.path.join(CSRC, s)
         obj = os.path.join(LIBDIR, name)
         objs.append(obj)

@@ -12,6 +12,7 @@
 // half a camera view at a time and folded into J^T J by 8x8 register tiles. 4 resident CTAs per SM (53 KB of
 // shared memory each); FP64 CUDA-core work throughout (no dense contraction large enough for tensor cores).
 #include "trf_warp.cuh"
+#include "det_math.cuh"
 
 namespace mvmc {
 
@@ -47,9 +48,11 @@ struct Topo {
 __device__ __forceinline__ void euler_to_mat(double ea, double eb, double ec, double* m) {
     const double k = 1.0 / (1.0 + 1e-10);  // axis / (|axis| + 1e-10), Quaternions.py:444
     double sx, cx, sy, cy, sz, cz;
-    sincos(ea / 2.0, &sx, &cx);
-    sincos(eb / 2.0, &sy, &cy);
-    sincos(ec / 2.0, &sz, &cz);
+    // (own sincos and no implicit FMA contraction in this file - it is compiled with -fmad=false, every fused operation
+    //  is an explicit fma(): the solver's results are then bit-identical on the GPU and in the CPU build of these sources)
+    det_sincos(ea / 2.0, &sx, &cx);
+    det_sincos(eb / 2.0, &sy, &cy);
+    det_sincos(ec / 2.0, &sz, &cz);
     sx *= k;
     sy *= k;
     sz *= k;

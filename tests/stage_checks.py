@@ -493,3 +493,54 @@ def check_alt_matchers(dev, limit=None):
         assert got == sorted(map(tuple, g[f"r{i}_ray_matches"].tolist())), (r, got[:5])
     assert worst <= 1e-9, worst
     return worst
+
+
+# ---------------------------------------------------------------------------------------------------
+_emu_binding = None
+
+
+def run_ik_cpu_restatement(probs, max_nfev=None):
+    """The SAME kernel sources (csrc/ik.cu, trf_warp.cuh, det_math.cuh) compiled for the CPU (tests/emu/libmvmc_emu.so, g++
+    -ffp-contract=off) and executed with the same operation order as on the GPU: the deterministic CPU restatement of
+    FK + forward-difference Jacobian + TRF that SURVEY.md 8c' (protocol item 3) asks for. Called through its own ctypes
+    binding with host arrays, next to whatever library the test tier has bound."""
+    global _emu_binding
+    import ctypes
+    from helpers import EMU_LIB
+    from multiview_motion_capture_b200 import _lib
+    if _emu_binding is None:
+        _emu_binding = _lib._bind(ctypes.CDLL(EMU_LIB))
+    lib = _emu_binding
+    M, V = len(probs), MAX_SEL
+    kps = np.zeros((M, V, 17, 3))
+    Ps = np.zeros((M, V, 3, 4))
+    nv = np.zeros(M, np.int32)
+    x0 = np.zeros((M, 68))
+    birth = np.zeros(M, np.uint8)
+    nfev = np.zeros(M, np.int32)
+    for m, p in enumerate(probs):
+        v = len(p["sel"])
+        kps[m, :v], Ps[m, :v], nv[m], x0[m], birth[m] = p["kps"], p["P"], v, p["x0"], int(p["birth"])
+        nfev[m] = (50 if p["birth"] else 5) if max_nfev is None else max_nfev
+    ws = np.zeros(64)
+    x, joints, info, cost = np.zeros((M, 68)), np.zeros((M, 18, 3)), np.zeros((M, 2, 4), np.int32), np.zeros((M, 2))
+    ptr = lambda a: a.ctypes.data
+    _lib.check(lib.mvmc_ik_solve(ptr(kps), ptr(Ps), ptr(nv), ptr(x0), ptr(birth), ptr(nfev), None, M, V, ptr(ws), ptr(x), ptr(joints),
+                                 ptr(info), ptr(cost), None), "emulator mvmc_ik_solve")
+    return x, joints, info, cost
+
+
+def check_ik_bitwise_vs_cpu_restatement(dev, name, frames):
+    """SURVEY.md 8c' protocol item 3(i): on the REAL (rank-deficient, chaotic) path - every update and birth the reference
+    solved on the given frames - the CUDA kernel against the CPU restatement with the same operation order. The kernel has
+    no compiler-chosen FMA contraction and its own sincos, so the bar is not 1e-3 rad but bitwise equality of parameters,
+    joints, costs and (nfev, njev, status)."""
+    probs = ik_problems(name, frames)
+    assert len(probs) > 0
+    got = run_ik(dev, probs)
+    ref = run_ik_cpu_restatement(probs)
+    n_birth = sum(int(p["birth"]) for p in probs)
+    worst = float(np.abs(got[0] - ref[0]).max())
+    for a, b, what in zip(got, ref, ("parameters", "joints", "info", "cost")):
+        assert np.array_equal(a, b), (name, what, float(np.abs(np.asarray(a, dtype=np.float64) - b).max()))
+    return len(probs), n_birth, worst

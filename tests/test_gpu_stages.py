@@ -175,3 +175,14 @@ def test_alternative_matchers(cuda):
     w = SC.check_alt_matchers(DEV)
     print(f"PARITY alternative matchers vs reference (Hungarian grouping across views at two thresholds, 3D ray association): "
           f"groups / matches identical on 9 frames incl. 8x16 and 8x32, max |ray cost diff| {w:.2e} m")
+
+
+def test_ik_bitwise_equal_to_the_cpu_restatement(cuda):
+    """I4, SURVEY.md 8c' protocol 3(i): CUDA == same-operation-order CPU restatement, bit for bit, on the real path."""
+    tot = 0
+    for name, frames in (("shelf", list(range(1, 40)) + [120, 121, 250]), ("synth_c8p6", [1, 2, 3, 4]), ("warm_c8p16", [3, 4])):
+        n, nb, worst = SC.check_ik_bitwise_vs_cpu_restatement(DEV, name, frames)
+        tot += n
+        print(f"PARITY IK real path, CUDA vs CPU restatement (same sources, same operation order): {name}: {n} solves ({nb} births) "
+              f"bit-identical (max |dx| {worst})")
+    assert tot > 150
