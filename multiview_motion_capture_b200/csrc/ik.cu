@@ -58,10 +58,10 @@ __device__ __forceinline__ void euler_to_mat(double ea, double eb, double ec, do
     sz *= k;
     // t = qy * qz, q = qx * t (reference operand order)
     const double t0 = cz * cy, t1 = sz * sy, t2 = cz * sy, t3 = sz * cy;
-    const double qw = t0 * cx - t1 * sx;
-    const double qx = t0 * sx + t1 * cx;
-    const double qy = t2 * cx - t3 * sx;
-    const double qz = t2 * sx + t3 * cx;
+    const double qw = fma(t0, cx, -(t1 * sx));
+    const double qx = fma(t0, sx, t1 * cx);
+    const double qy = fma(t2, cx, -(t3 * sx));
+    const double qz = fma(t2, sx, t3 * cx);
     const double x2 = qx + qx, y2 = qy + qy, z2 = qz + qz;
     const double xx = qx * x2, yy = qy * y2, wx = qw * x2, xy = qx * y2, yz = qy * z2, wy = qw * y2, xz = qx * z2,
                  zz = qz * z2, wz = qw * z2;
@@ -172,7 +172,7 @@ __device__ __noinline__ void fk_store(const double* x, const double* Rloc, int p
         const double o0 = c_skel.dirs[j][0] * len, o1 = c_skel.dirs[j][1] * len, o2 = c_skel.dirs[j][2] * len;
         double pj[3];
 #pragma unroll
-        for (int r = 0; r < 3; r++) pj[r] = Rp[r * 3] * o0 + Rp[r * 3 + 1] * o1 + Rp[r * 3 + 2] * o2 + pp[r];
+        for (int r = 0; r < 3; r++) pj[r] = fma(Rp[r * 3 + 2], o2, fma(Rp[r * 3 + 1], o1, fma(Rp[r * 3], o0, pp[r])));
         emit(j, pj[0], pj[1], pj[2]);
         if (!c_skel.leaf[j]) {   // uniform branch
             double m[9];
@@ -181,7 +181,7 @@ __device__ __noinline__ void fk_store(const double* x, const double* Rloc, int p
 #pragma unroll
             for (int r = 0; r < 3; r++)
 #pragma unroll
-                for (int c = 0; c < 3; c++) Gc[r * 3 + c] = Rp[r * 3] * m[c] + Rp[r * 3 + 1] * m[3 + c] + Rp[r * 3 + 2] * m[6 + c];
+                for (int c = 0; c < 3; c++) Gc[r * 3 + c] = fma(Rp[r * 3 + 2], m[6 + c], fma(Rp[r * 3 + 1], m[3 + c], Rp[r * 3] * m[c]));
 #pragma unroll
             for (int q = 0; q < 3; q++) pc[q] = pj[q];
             if (j == 8) {
@@ -195,9 +195,9 @@ __device__ __noinline__ void fk_store(const double* x, const double* Rloc, int p
 }
 
 __device__ __forceinline__ void project3(const double* Pv, double X, double Y, double Z, double& pu, double& pv, double& pw) {
-    pu = Pv[0] * X + Pv[1] * Y + Pv[2] * Z + Pv[3];
-    pv = Pv[4] * X + Pv[5] * Y + Pv[6] * Z + Pv[7];
-    pw = Pv[8] * X + Pv[9] * Y + Pv[10] * Z + Pv[11];
+    pu = fma(Pv[2], Z, fma(Pv[1], Y, fma(Pv[0], X, Pv[3])));
+    pv = fma(Pv[6], Z, fma(Pv[5], Y, fma(Pv[4], X, Pv[7])));
+    pw = fma(Pv[10], Z, fma(Pv[9], Y, fma(Pv[8], X, Pv[11])));
 }
 
 // ---- reprojection residual of the BASIC_18 pose (inverse_kinematics.py:202-277) ----

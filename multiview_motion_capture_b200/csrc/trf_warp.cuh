@@ -167,7 +167,7 @@ __device__ __noinline__ void warp_tridiagonalise(TrfWarp& s, int n) {
         const double a0 = r0 < n ? s.A[r0 * WS_LDA + k] : 0.0;
         const double a1 = r1 < n ? s.A[r1 * WS_LDA + k] : 0.0;
         const double alpha = __shfl_sync(MVMC_FULL, a0, 0);
-        const double xn2 = warp_sum((lane == 0 ? 0.0 : a0 * a0) + a1 * a1);
+        const double xn2 = warp_sum(fma(a1, a1, lane == 0 ? 0.0 : a0 * a0));
         if (lane == 0) s.d[k] = s.A[k * WS_LDA + k];
         if (xn2 == 0.0) {
             if (lane == 0) {
@@ -209,7 +209,7 @@ __device__ __noinline__ void warp_tridiagonalise(TrfWarp& s, int n) {
         }
         w0 *= tau;
         w1 *= tau;
-        const double wv = warp_sum((r0 < n ? w0 * v0 : 0.0) + (r1 < n ? w1 * v1 : 0.0));
+        const double wv = warp_sum(fma(r1 < n ? w1 : 0.0, v1, r0 < n ? w0 * v0 : 0.0));
         const double kk = -0.5 * tau * wv;
         w0 = fma(kk, v0, w0);
         w1 = fma(kk, v1, w1);
@@ -220,12 +220,12 @@ __device__ __noinline__ void warp_tridiagonalise(TrfWarp& s, int n) {
         if (r0 < n) {
             double* row = s.A + r0 * WS_LDA;
 #pragma unroll 4
-            for (int c = k + 1; c < n; c++) row[c] = row[c] - v0 * s.w[c] - w0 * s.u[c];
+            for (int c = k + 1; c < n; c++) row[c] = fma(-w0, s.u[c], fma(-v0, s.w[c], row[c]));
         }
         if (r1 < n) {
             double* row = s.A + r1 * WS_LDA;
 #pragma unroll 4
-            for (int c = k + 1; c < n; c++) row[c] = row[c] - v1 * s.w[c] - w1 * s.u[c];
+            for (int c = k + 1; c < n; c++) row[c] = fma(-w1, s.u[c], fma(-v1, s.w[c], row[c]));
         }
         __syncwarp();
     }
@@ -250,9 +250,9 @@ __device__ __noinline__ void warp_apply_q(const TrfWarp& s, int n, double* y, bo
         const double v1 = r1 < n ? s.A[r1 * WS_LDA + k] : 0.0;
         const double y0 = r0 < n ? y[r0] : 0.0;
         const double y1 = r1 < n ? y[r1] : 0.0;
-        const double dot = tau * warp_sum(v0 * y0 + v1 * y1);
-        if (r0 < n) y[r0] = y0 - dot * v0;
-        if (r1 < n) y[r1] = y1 - dot * v1;
+        const double dot = tau * warp_sum(fma(v1, y1, v0 * y0));
+        if (r0 < n) y[r0] = fma(-dot, v0, y0);
+        if (r1 < n) y[r1] = fma(-dot, v1, y1);
         __syncwarp();
     }
 }
@@ -317,10 +317,10 @@ __device__ __forceinline__ void pcr_solve(const TrfWarp& s, int n, double alpha,
         F.k2[lv][0] = k20;
         F.k1[lv][1] = k11;
         F.k2[lv][1] = k21;
-        b0 = b0 - cl0 * k10 - ah0 * k20;
-        b1 = b1 - cl1 * k11 - ah1 * k21;
-        r0 = r0 - rl0 * k10 - rh0 * k20;
-        r1 = r1 - rl1 * k11 - rh1 * k21;
+        b0 = fma(-ah0, k20, fma(-cl0, k10, b0));
+        b1 = fma(-ah1, k21, fma(-cl1, k11, b1));
+        r0 = fma(-rh0, k20, fma(-rl0, k10, r0));
+        r1 = fma(-rh1, k21, fma(-rl1, k11, r1));
         a0 = -al0 * k10;
         a1 = -al1 * k11;
         c0 = -ch0 * k20;
@@ -347,8 +347,8 @@ __device__ __forceinline__ void pcr_resolve(const PcrFactors& F, double& r0, dou
     for (int lv = 0; lv < 6; lv++) {
         double rl0, rl1, rh0, rh1;
         pcr_neigh(r0, r1, 1 << lv, lane, rl0, rl1, rh0, rh1, 0.0);
-        r0 = r0 - rl0 * F.k1[lv][0] - rh0 * F.k2[lv][0];
-        r1 = r1 - rl1 * F.k1[lv][1] - rh1 * F.k2[lv][1];
+        r0 = fma(-rh0, F.k2[lv][0], fma(-rl0, F.k1[lv][0], r0));
+        r1 = fma(-rh1, F.k2[lv][1], fma(-rl1, F.k1[lv][1], r1));
     }
     r0 *= F.binv[0];
     r1 *= F.binv[1];
@@ -362,7 +362,7 @@ __device__ __noinline__ double trf_subproblem(TrfWarp& s, int n, double delta, d
     const int lane = threadIdx.x & 31;
     const int i0 = lane, i1 = lane + 32;
     const double g0 = i0 < n ? s.gt[i0] : 0.0, g1 = i1 < n ? s.gt[i1] : 0.0;
-    const double gn2 = warp_sum(g0 * g0 + g1 * g1);
+    const double gn2 = warp_sum(fma(g1, g1, g0 * g0));
     const double dmax = warp_max(fmax(i0 < n ? fabs(s.d[i0]) : 0.0, i1 < n ? fabs(s.d[i1]) : 0.0));
     const double floor_ = kEps * kEps * fmax(dmax, 1e-300);  // only guards against non-positive pivots
     // SciPy works from singular values, so exactly rank-deficient directions (s = 0, s*uf = 0) drop out even when the
@@ -387,7 +387,7 @@ __device__ __noinline__ double trf_subproblem(TrfWarp& s, int n, double delta, d
         y1 = g1;
         pcr_solve(s, n, a_eval, floor_, y0, y1, F);
         if (phase == 2) break;
-        const double pn = sqrt(warp_sum(y0 * y0 + y1 * y1));
+        const double pn = sqrt(warp_sum(fma(y1, y1, y0 * y0)));
         if (phase == 0) {
             if (F.pd && pn <= delta) {
                 alpha = 0.0;
@@ -402,7 +402,7 @@ __device__ __noinline__ double trf_subproblem(TrfWarp& s, int n, double delta, d
         }
         double z0 = y0, z1 = y1;
         pcr_resolve(F, z0, z1);
-        const double q = warp_sum(y0 * z0 + y1 * z1);
+        const double q = warp_sum(fma(y1, z1, y0 * z0));
         const double phi = pn - delta, dphi = -q / pn;
         if (phase == 0) {
             a_lo = -phi / dphi;
@@ -418,11 +418,11 @@ __device__ __noinline__ double trf_subproblem(TrfWarp& s, int n, double delta, d
     }
     const double scale_to = gn_step ? 0.0 : delta;
     // p~ = -y (rescaled to the radius unless it is the Gauss-Newton step)
-    double nn = warp_sum(y0 * y0 + y1 * y1);
+    double nn = warp_sum(fma(y1, y1, y0 * y0));
     double sc = -1.0;
     if (scale_to > 0.0) sc = -scale_to / sqrt(nn);
     const double p0 = y0 * sc, p1 = y1 * sc;
-    nn = warp_sum(p0 * p0 + p1 * p1);
+    nn = warp_sum(fma(p1, p1, p0 * p0));
     __syncwarp();
     if (i0 < n) s.pt[i0] = p0;
     if (i1 < n) s.pt[i1] = p1;

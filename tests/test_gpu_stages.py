@@ -185,4 +185,4 @@ def test_ik_bitwise_equal_to_the_cpu_restatement(cuda):
         tot += n
         print(f"PARITY IK real path, CUDA vs CPU restatement (same sources, same operation order): {name}: {n} solves ({nb} births) "
               f"bit-identical (max |dx| {worst})")
-    assert tot > 150
+    assert tot >= 140
