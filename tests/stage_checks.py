@@ -385,9 +385,10 @@ def check_ik_targets(dev, limit=None):
         # (a 50-evaluation birth converges - status 2 - after a few evaluations more or less than SciPy; what it converges
         #  to is compared below. A 5-evaluation update spends its whole budget: nfev and status identical.)
         for got, ref_m in ((st1[2][q, 0], meta[0]), (st2[2][q, 1], meta[1])):
-            assert got[2] == ref_m[2], (i, got, ref_m)
-            if not birth:
-                assert got[0] == ref_m[0], (i, got, ref_m)
+            if birth:     # converged like the reference (SciPy status 1..4: gtol / ftol / xtol; which test fires first can differ)
+                assert got[2] > 0 and ref_m[2] > 0, (i, got, ref_m)
+            else:
+                assert got[2] == ref_m[2] and got[0] == ref_m[0], (i, got, ref_m)
         assert st1[2][q, 1, 0] == 0 and st2[2][q, 0, 0] == 0                   # the other stage did not run
         assert np.array_equal(st1[0][q, 57:], x0[q, 57:])                        # solve_pose leaves the bone lengths alone
         assert abs(st1[3][q, 0] - cost[0]) <= (1e-6 if birth else 0.5) * cost[0] + 1e-12, (i, st1[3][q, 0], cost[0])
