@@ -308,11 +308,13 @@ __device__ __forceinline__ void pcr_solve(const TrfWarp& s, int n, double alpha,
             b1 = floor_;
         }
         double bl0, bl1, bh0, bh1, al0, al1, ah0, ah1, cl0, cl1, ch0, ch1, rl0, rl1, rh0, rh1;
-        pcr_neigh(b0, b1, st, lane, bl0, bl1, bh0, bh1, 1.0);
+        // every row inverts its own diagonal once and hands the reciprocal to its neighbours (two divisions per level and
+        // lane instead of four; a double-precision division is ~25 instructions with a slow path)
+        pcr_neigh(1.0 / b0, 1.0 / b1, st, lane, bl0, bl1, bh0, bh1, 1.0);
         pcr_neigh(a0, a1, st, lane, al0, al1, ah0, ah1, 0.0);
         pcr_neigh(c0, c1, st, lane, cl0, cl1, ch0, ch1, 0.0);
         pcr_neigh(r0, r1, st, lane, rl0, rl1, rh0, rh1, 0.0);
-        const double k10 = a0 / bl0, k20 = c0 / bh0, k11 = a1 / bl1, k21 = c1 / bh1;
+        const double k10 = a0 * bl0, k20 = c0 * bh0, k11 = a1 * bl1, k21 = c1 * bh1;
         F.k1[lv][0] = k10;
         F.k2[lv][0] = k20;
         F.k1[lv][1] = k11;
