@@ -264,7 +264,7 @@ struct IkRes {
 #pragma unroll
         for (int e = 0; e < 12; e++) Pv[e] = P[v * 12 + e];
         for (int c = lane; c < ncol; c += 32) {
-            const double rdx = 1.0 / s.dx[c];
+            const double rdx = s.tau[c];   // 1 / dx, formed once per Jacobian
 #pragma unroll
             for (int qq = 0; qq < 4; qq++) {
                 const int q = q0 + qq;
@@ -325,7 +325,7 @@ struct Ik3dRes {
         const int lane = threadIdx.x & 31;
         const double* S = s.A;
         for (int c = lane; c < ncol; c += 32) {
-            const double rdx = 1.0 / s.dx[c];
+            const double rdx = s.tau[c];   // 1 / dx, formed once per Jacobian
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 const int row = 8 * ch + r, q = row / 3, cc = row % 3;
@@ -379,25 +379,36 @@ struct TriRes {
     }
 };
 
-// ---- DLT: null vector of the (2V x 4) system by one-sided Jacobi (single thread, tiny) ----
-__device__ void dlt_point(const double* P /*[V][12]*/, const double* xy /*[V][2]*/, const int* sel, int nsel, double* out3) {
-    double a[2 * MVMC_MAX_SEL][4];
+// ---- DLT: null vector of the (2V x 4) system by one-sided Jacobi, one thread per joint ----
+// mv_math_util.py:215-240 (rows x P[2] - P[0], y P[2] - P[1] of every used view, smallest right singular vector, divide by
+// w). View v owns rows 2v, 2v+1 of a fixed-size system (zero rows for views that are not used: they add exact zeros to every
+// sum, so the result is that of the compacted system) and every loop is unrolled: the whole system lives in registers
+// (the first version indexed local arrays by run-time row numbers and waited on local-memory loads 80 % of the time).
+template <int VM>
+__device__ __forceinline__ void dlt_point(const double* P /*[V][12]*/, const double* obs /*[V][K][3]*/, int V, int K, int k, unsigned use,
+                                          double* out3) {
+    double a[2 * VM][4];
     double v[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
-    const int rows = 2 * nsel;
-    for (int q = 0; q < nsel; q++) {
-        const double* Pv = P + sel[q] * 12;
-        const double px = xy[sel[q] * 2], py = xy[sel[q] * 2 + 1];
+#pragma unroll
+    for (int q = 0; q < VM; q++) {
+        const bool on = q < V && ((use >> q) & 1u);
+        const double* Pv = P + (on ? q : 0) * 12;
+        const double px = on ? obs[(q * K + k) * 3] : 0.0, py = on ? obs[(q * K + k) * 3 + 1] : 0.0;
+#pragma unroll
         for (int c = 0; c < 4; c++) {
-            a[2 * q][c] = px * Pv[8 + c] - Pv[c];
-            a[2 * q + 1][c] = py * Pv[8 + c] - Pv[4 + c];
+            a[2 * q][c] = on ? px * Pv[8 + c] - Pv[c] : 0.0;
+            a[2 * q + 1][c] = on ? py * Pv[8 + c] - Pv[4 + c] : 0.0;
         }
     }
     for (int sweep = 0; sweep < 30; sweep++) {
         bool rotated = false;
+#pragma unroll
         for (int p = 0; p < 3; p++)
+#pragma unroll
             for (int q = p + 1; q < 4; q++) {
                 double app = 0, aqq = 0, apq = 0;
-                for (int r = 0; r < rows; r++) {
+#pragma unroll
+                for (int r = 0; r < 2 * VM; r++) {
                     app += a[r][p] * a[r][p];
                     aqq += a[r][q] * a[r][q];
                     apq += a[r][p] * a[r][q];
@@ -407,11 +418,13 @@ __device__ void dlt_point(const double* P /*[V][12]*/, const double* xy /*[V][2]
                 const double tau = (aqq - app) / (2.0 * apq);
                 const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
                 const double c = 1.0 / sqrt(1.0 + t * t), sn = t * c;
-                for (int r = 0; r < rows; r++) {
+#pragma unroll
+                for (int r = 0; r < 2 * VM; r++) {
                     const double ap = a[r][p], aq = a[r][q];
                     a[r][p] = c * ap - sn * aq;
                     a[r][q] = sn * ap + c * aq;
                 }
+#pragma unroll
                 for (int r = 0; r < 4; r++) {
                     const double vp = v[r][p], vq = v[r][q];
                     v[r][p] = c * vp - sn * vq;
@@ -420,38 +433,44 @@ __device__ void dlt_point(const double* P /*[V][12]*/, const double* xy /*[V][2]
             }
         if (!rotated) break;
     }
-    int best = 0;
-    double bn = INFINITY;
+    double bn = INFINITY, b0 = 0, b1 = 0, b2 = 0, b3 = 1;
+#pragma unroll
     for (int c = 0; c < 4; c++) {
         double nn = 0;
-        for (int r = 0; r < rows; r++) nn += a[r][c] * a[r][c];
+#pragma unroll
+        for (int r = 0; r < 2 * VM; r++) nn += a[r][c] * a[r][c];
         if (nn < bn) {
             bn = nn;
-            best = c;
+            b0 = v[0][c];
+            b1 = v[1][c];
+            b2 = v[2][c];
+            b3 = v[3][c];
         }
     }
-    out3[0] = v[0][best] / v[3][best];
-    out3[1] = v[1][best] / v[3][best];
-    out3[2] = v[2][best] / v[3][best];
+    out3[0] = b0 / b3;
+    out3[1] = b1 / b3;
+    out3[2] = b2 / b3;
 }
 
-// obs [V][K][3] -> out [K][4]; one thread per joint. mv_math_util.py:152-186
-__device__ void triangulate_joint(const double* obs, const double* P, int V, int K, int k, double min_score, double* out4) {
-    int sel[MVMC_MAX_SEL];
-    double xy[MVMC_MAX_SEL * 2];
+// obs [V][K][3] -> out [K][4]; one thread per joint. mv_math_util.py:152-186: views with score >= min_score, all views if
+// fewer than two qualify; the fourth output is the mean score of the views used.
+template <int VM>
+__device__ __forceinline__ void triangulate_joint(const double* obs, const double* P, int V, int K, int k, double min_score, double* out4) {
+    unsigned use = 0;
     int nsel = 0;
-    for (int v = 0; v < V; v++) {
-        xy[2 * v] = obs[(v * K + k) * 3];
-        xy[2 * v + 1] = obs[(v * K + k) * 3 + 1];
-        if (obs[(v * K + k) * 3 + 2] >= min_score) sel[nsel++] = v;
-    }
+    for (int v = 0; v < V; v++)
+        if (obs[(v * K + k) * 3 + 2] >= min_score) {
+            use |= 1u << v;
+            nsel++;
+        }
     if (nsel < 2) {
         nsel = V;
-        for (int v = 0; v < V; v++) sel[v] = v;
+        use = V >= 32 ? 0xffffffffu : ((1u << V) - 1u);
     }
     double sc = 0.0;
-    for (int q = 0; q < nsel; q++) sc += obs[(sel[q] * K + k) * 3 + 2];
-    dlt_point(P, xy, sel, nsel, out4);
+    for (int v = 0; v < V; v++)
+        if ((use >> v) & 1u) sc += obs[(v * K + k) * 3 + 2];
+    dlt_point<VM>(P, obs, V, K, k, use, out4);
     out4[3] = sc / nsel;
 }
 
@@ -492,7 +511,7 @@ template <int VMAX>
 __device__ void warp_triangulate(IkWarpSh<VMAX>& sh, const double* obs /*[nv][K][3] shared*/, int nv, int K, double min_score,
                                  int refine_nfev) {
     const int lane = threadIdx.x & 31;
-    if (lane < K) triangulate_joint(obs, sh.P, nv, K, lane, min_score, sh.p3 + lane * 4);
+    if (lane < K) triangulate_joint<VMAX>(obs, sh.P, nv, K, lane, min_score, sh.p3 + lane * 4);
     __syncwarp();
     if (refine_nfev <= 0) return;
     for (int e = lane; e < MVMC_N_PARAM; e += 32) sh.t.x[e] = 0.0;
@@ -901,6 +920,13 @@ extern "C" int mvmc_triangulate(const double* obs, const double* Psel, const int
                                 double min_score, int refine_nfev, double* out, void* stream) {
     if (!obs || !Psel || !n_views || !out) return MVMC_ERR_INVALID;
     if (M <= 0 || V < 1 || V > MVMC_MAX_SEL || K < 1 || K > 18 || refine_nfev < 0) return MVMC_ERR_INVALID;
+    if (V <= 8) {   // (up to 8 views: the 16 x 4 system of a joint fits the register file without spills, 3 CTAs more per SM)
+        MVMC_CUDA_OK(cudaFuncSetAttribute(k_triangulate<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IkWarpSh<8>)));
+        MVMC_LAUNCH(k_triangulate<8>, dim3(M < 148 * 6 ? M : 148 * 6), dim3(32), sizeof(IkWarpSh<8>), stream, obs, Psel, n_views, M, V, K,
+                    min_score, refine_nfev, out);
+        MVMC_CHECK_LAUNCH("k_triangulate");
+        return MVMC_OK;
+    }
     MVMC_CUDA_OK(cudaFuncSetAttribute(k_triangulate<MVMC_MAX_SEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(IkWarpSh<MVMC_MAX_SEL>)));
     MVMC_LAUNCH(k_triangulate<MVMC_MAX_SEL>, dim3(ik_grid(M)), dim3(32), sizeof(IkWarpSh<MVMC_MAX_SEL>), stream, obs, Psel,

@@ -91,6 +91,7 @@ __device__ __noinline__ void trf_jacobian(TrfWarp& s, Res& res, int ncol, const 
         const double xi = s.x[s.act[c]];
         const double h = kSqrtEps * (xi >= 0.0 ? 1.0 : -1.0) * fmax(1.0, fabs(xi));
         s.dx[c] = DSUB(xi + h, xi);
+        s.tau[c] = 1.0 / s.dx[c];   // (tau is free until the tridiagonalisation: the residuals' fd_chunk multiply by it)
         s.w[c] = xi + h;    // perturbed value of the column's parameter
     }
     __syncwarp();
