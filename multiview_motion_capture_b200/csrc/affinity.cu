@@ -185,8 +185,6 @@ __global__ void k_fundamental_krt(const double* __restrict__ K, const double* __
 // ------------------------------------------------------------------------------------------------
 #define AFF_TILE 16
 #define AFF_ITEM 54  // 18 joints x 3 doubles (2D poses use the first 51)
-#define AFF_NV 3     // distinct views per tile side the epiline cache has slots for
-#define AFF_LINE_BYTES (2 * AFF_TILE * AFF_NV * MVMC_N_COCO * 4 * 8)
 
 __device__ __forceinline__ void line_from(const double* f, bool transpose, double x, double y, double& a, double& b,
                                           double& c) {
@@ -219,25 +217,6 @@ __device__ double epipolar_error(const double* f, const double* ki, const double
         const double d1 = fabs(a * x2 + b * y2 + c) / sqrt(a * a + b * b);
         line_from(f, true, x2, y2, a, b, c);
         const double d2 = fabs(a * x1 + b * y1 + c) / sqrt(a * a + b * b);
-        total = total + 0.5 * (d1 + d2);
-        cnt++;
-    }
-    return cnt ? total / cnt : NAN;
-}
-
-// the same from cached normalised lines: L1[q] = line of ki's joint q in kj's view, L2[q] = line of kj's joint q in ki's view,
-// each (a, b, c, sqrt(a^2 + b^2))
-__device__ double epipolar_error_cached(const double* L1, const double* L2, const double* ki, const double* kj) {
-    double total = 0.0;
-    int cnt = 0;
-    for (int q = 0; q < MVMC_N_COCO; q++) {
-        const double s = ki[3 * q + 2] * kj[3 * q + 2];
-        if (!(s > 0.1)) continue;
-        const double x1 = ki[3 * q], y1 = ki[3 * q + 1], x2 = kj[3 * q], y2 = kj[3 * q + 1];
-        const double* l1 = L1 + 4 * q;
-        const double* l2 = L2 + 4 * q;
-        const double d1 = fabs(l1[0] * x2 + l1[1] * y2 + l1[2]) / l1[3];
-        const double d2 = fabs(l2[0] * x1 + l2[1] * y1 + l2[2]) / l2[3];
         total = total + 0.5 * (d1 + d2);
         cnt++;
     }
@@ -288,7 +267,6 @@ __global__ void __launch_bounds__(AFF_TILE* AFF_TILE)
     if (i0 >= n || j0 >= n) return;
     __shared__ double s_item[2 * AFF_TILE][AFF_ITEM];
     __shared__ int s_view[2 * AFF_TILE], s_pose[2 * AFF_TILE];
-    __shared__ int s_vlist[2][AFF_NV], s_nv[2];
     const int tid = threadIdx.y * AFF_TILE + threadIdx.x;
     const int T = min(n_trk[b], Tmax);
     // stage: items 0..15 = rows i0.., 16..31 = cols j0.. - every thread brings a few elements of several items and all of
@@ -323,54 +301,6 @@ __global__ void __launch_bounds__(AFF_TILE* AFF_TILE)
         }
     }
     __syncthreads();
-    // ---- normalised-epiline cache (float64 path) ----
-    // The epiline of joint q of pose i in view vj, l = normalise(F[vi][vj] x_i(q)), depends on (pose i, view vj) only, yet
-    // every entry of the tile used to recompute it (per joint: 4 square roots + 4 divisions; with the cache 2 divisions).
-    // A 16-wide window of the index layout spans few views (poses are grouped by view): every distinct view of the rows /
-    // of the columns gets a slot (at most AFF_NV per side, else the tile computes its entries directly, as before), and
-    // the tile's threads first fill line[side][pose][view slot][joint] = (a, b, c, sqrt(a^2 + b^2)).
-    MVMC_DYN_SMEM(double, s_line);    // [2][AFF_TILE][AFF_NV][17][4]
-    const bool f64path = T > 0 || force_f64;
-    if (f64path) {
-        if (tid < 2) {          // distinct 2D views of the rows (tid 0) / of the columns (tid 1), in order of appearance
-            int nv = 0;
-            bool over = false;
-            for (int t = 0; t < AFF_TILE; t++) {
-                const int v = s_view[tid * AFF_TILE + t];
-                if (v < 0) continue;
-                bool seen = false;
-                for (int u = 0; u < nv; u++) seen = seen || s_vlist[tid][u] == v;
-                if (!seen) {
-                    if (nv < AFF_NV) s_vlist[tid][nv++] = v;
-                    else over = true;
-                }
-            }
-            s_nv[tid] = over ? -1 : nv;
-        }
-        __syncthreads();
-        if (s_nv[0] >= 0 && s_nv[1] >= 0) {
-            // side 0: row poses towards the column views (F[vi][vu] x); side 1: column poses towards the row views (F[vu][vj]^T x)
-            const int per_side = AFF_TILE * AFF_NV * MVMC_N_COCO;
-            for (int e = tid; e < 2 * per_side; e += AFF_TILE * AFF_TILE) {
-                const int side = e / per_side, r = e % per_side;
-                const int t = r / (AFF_NV * MVMC_N_COCO), u = (r / MVMC_N_COCO) % AFF_NV, q = r % MVMC_N_COCO;
-                const int vp = s_view[side * AFF_TILE + t];
-                if (vp < 0 || u >= s_nv[1 - side]) continue;
-                const int vo = s_vlist[1 - side][u];
-                if (vo == vp) continue;
-                const double* kp = s_item[side * AFF_TILE + t];
-                const double* f = side == 0 ? F + ((size_t)(b * C + vp) * C + vo) * 9 : F + ((size_t)(b * C + vo) * C + vp) * 9;
-                double la, lb, lc;
-                line_from(f, side == 1, kp[3 * q], kp[3 * q + 1], la, lb, lc);
-                double* dstl = s_line + ((size_t)((side * AFF_TILE + t) * AFF_NV + u) * MVMC_N_COCO + q) * 4;
-                dstl[0] = la;
-                dstl[1] = lb;
-                dstl[2] = lc;
-                dstl[3] = sqrt(la * la + lb * lb);
-            }
-        }
-        __syncthreads();
-    }
     const int i = i0 + threadIdx.y, j = j0 + threadIdx.x;
     if (i >= n || j >= n) return;
     const int vi = s_view[threadIdx.y], vj = s_view[AFF_TILE + threadIdx.x];
@@ -380,20 +310,7 @@ __global__ void __launch_bounds__(AFF_TILE* AFF_TILE)
     if (T > 0 || force_f64) {
         if (i == j) d = 0.0;
         else if (vi >= 0 && vi == vj) d = NAN;
-        else if (vi >= 0 && vj >= 0) {
-            if (s_nv[0] >= 0 && s_nv[1] >= 0) {
-                int ui = 0, uj = 0;     // slots of vi among the row views, of vj among the column views
-                for (int u = 0; u < AFF_NV; u++) {
-                    if (u < s_nv[0] && s_vlist[0][u] == vi) ui = u;
-                    if (u < s_nv[1] && s_vlist[1][u] == vj) uj = u;
-                }
-                const double* L1 = s_line + (size_t)((threadIdx.y * AFF_NV + uj) * MVMC_N_COCO) * 4;                  // row pose -> view vj
-                const double* L2 = s_line + (size_t)(((AFF_TILE + threadIdx.x) * AFF_NV + ui) * MVMC_N_COCO) * 4;     // column pose -> view vi
-                d = epipolar_error_cached(L1, L2, ki, kj);
-            } else {
-                d = epipolar_error(F + ((size_t)(b * C + vi) * C + vj) * 9, ki, kj);
-            }
-        }
+        else if (vi >= 0 && vj >= 0) d = epipolar_error(F + ((size_t)(b * C + vi) * C + vj) * 9, ki, kj);
         else if (vi >= 0) d = reprojection_error(P + (size_t)(b * C + vi) * 12, kj, ki);
         else if (vj >= 0) d = reprojection_error(P + (size_t)(b * C + vj) * 12, ki, kj);
         else d = NAN;
@@ -628,8 +545,7 @@ extern "C" int mvmc_affinity(const double* kps, const double* P, const double* F
         return MVMC_ERR_INVALID;
     const int N = Tmax + C * Pmax;
     const int tiles = (N + AFF_TILE - 1) / AFF_TILE;
-    MVMC_CUDA_OK(cudaFuncSetAttribute(k_affinity, cudaFuncAttributeMaxDynamicSharedMemorySize, AFF_LINE_BYTES));
-    MVMC_LAUNCH(k_affinity, dim3(tiles, tiles, B), dim3(AFF_TILE, AFF_TILE), AFF_LINE_BYTES, stream, kps, P, F, F32, trk_joints, n_trk,
+    MVMC_LAUNCH(k_affinity, dim3(tiles, tiles, B), dim3(AFF_TILE, AFF_TILE), 0, stream, kps, P, F, F32, trk_joints, n_trk,
                 dim_groups, idx_view, idx_pose, C, Pmax, Tmax, 0, dst);
     MVMC_CHECK_LAUNCH("k_affinity");
     MVMC_LAUNCH(k_simfill, dim3(B), dim3(256), 0, stream, n_trk, dim_groups, C, N, dst, sim);
@@ -647,9 +563,8 @@ extern "C" int mvmc_distances(const double* kps, const double* P, const double* 
         return MVMC_ERR_INVALID;
     const int N = Tmax + C * Pmax;
     const int tiles = (N + AFF_TILE - 1) / AFF_TILE;
-    MVMC_CUDA_OK(cudaFuncSetAttribute(k_affinity, cudaFuncAttributeMaxDynamicSharedMemorySize, AFF_LINE_BYTES));
-    MVMC_LAUNCH(k_affinity, dim3(tiles, tiles, B), dim3(AFF_TILE, AFF_TILE), AFF_LINE_BYTES, stream, kps, P, F, (const float*)nullptr,
-                trk_joints, n_trk, dim_groups, idx_view, idx_pose, C, Pmax, Tmax, 1, dst);
+    MVMC_LAUNCH(k_affinity, dim3(tiles, tiles, B), dim3(AFF_TILE, AFF_TILE), 0, stream, kps, P, F, (const float*)nullptr, trk_joints,
+                n_trk, dim_groups, idx_view, idx_pose, C, Pmax, Tmax, 1, dst);
     MVMC_CHECK_LAUNCH("k_affinity");
     return MVMC_OK;
 }
