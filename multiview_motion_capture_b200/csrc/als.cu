@@ -1245,7 +1245,7 @@ int AL_LAUNCHER(const double* sim, const int* dim_groups, int n_groups, const in
 }
 
 #ifndef AL_VARIANT
-// Tile shape by problem size: rmax <= 32 (scenes of up to 16 people per view: n ~ 130, r = 32) runs the build with 48 x 48
+// Tile shape by problem size: N <= 192 (scenes of up to 16 people per view: n ~ 130, r = 32) runs the build with 48 x 48
 // CTA tiles and 4-warp CTAs (als.cu compiled with -DAL_VARIANT=small -DAL_FM_=3 -DAL_THREADS_=128) - 64 x 96 tiles leave most
 // of their fragments on padding there (n = 131 is two 64-row tiles plus 3 rows). Same arithmetic per element; the two
 // builds differ in which rows a CTA's warps own, never in a summation order along k.
@@ -1260,7 +1260,8 @@ extern "C" int mvmc_als_force_variant(int v) {
 int mvmc_match_als_ordered(const double* sim, const int* dim_groups, int n_groups, const int* f32_first_iter,
                            const double* rand_stream, const int* order, int B, int N, int rmax, void* workspace, uint32_t* xbin,
                            int* n_iter, void* stream) {
-    const bool small = g_als_force_variant < 0 ? rmax <= 32 : g_als_force_variant == 1;
+    // (by problem size: N = max_tracks + views x max_poses <= 192 covers scenes of up to 16 people per view, n ~ 130, r = 32)
+    const bool small = g_als_force_variant < 0 ? N <= 192 : g_als_force_variant == 1;
     if (small)
         return mvmc_match_als_ordered_small(sim, dim_groups, n_groups, f32_first_iter, rand_stream, order, B, N, rmax, workspace,
                                             xbin, n_iter, stream);
