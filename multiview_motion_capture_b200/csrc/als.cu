@@ -1260,8 +1260,11 @@ extern "C" int mvmc_als_force_variant(int v) {
 int mvmc_match_als_ordered(const double* sim, const int* dim_groups, int n_groups, const int* f32_first_iter,
                            const double* rand_stream, const int* order, int B, int N, int rmax, void* workspace, uint32_t* xbin,
                            int* n_iter, void* stream) {
-    // (by problem size: N = max_tracks + views x max_poses <= 192 covers scenes of up to 16 people per view, n ~ 130, r = 32)
-    const bool small = g_als_force_variant < 0 ? N <= 192 : g_als_force_variant == 1;
+    // By problem size (N = max_tracks + views x max_poses <= 192 covers scenes of up to 16 people per view, n ~ 130, r = 32) and
+    // by batch size: the small build's 4-warp CTAs finish MORE clips per second once they queue for SMs (4 per SM, 592
+    // resident) but each clip takes longer than under an 8-warp CTA, so a launch that fits in one wave (strong scaling: 170
+    // clips per group at 8 GPUs, where a frame takes as long as its slowest clip) keeps the big build.
+    const bool small = g_als_force_variant < 0 ? (N <= 192 && B > 592) : g_als_force_variant == 1;
     if (small)
         return mvmc_match_als_ordered_small(sim, dim_groups, n_groups, f32_first_iter, rand_stream, order, B, N, rmax, workspace,
                                             xbin, n_iter, stream);

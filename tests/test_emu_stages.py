@@ -81,3 +81,13 @@ def test_linear_sum_assignment(emu):
 def test_alternative_matchers(emu):
     """SURVEY.md 8f-3 through the emulator on the Shelf records."""
     SC.check_alt_matchers(DEV, limit=6)
+
+
+def test_als_tile_builds_agree(emu):
+    """Both tile builds of k_als through the emulator (forced): the reference's X_bin and stopping iteration."""
+    try:
+        for v in (1, 0):
+            emu.mvmc_als_force_variant(v)
+            assert SC.check_als(DEV, "shelf", [2, 9], N=64, rmax=16) == 2
+    finally:
+        emu.mvmc_als_force_variant(-1)

@@ -186,3 +186,20 @@ def test_ik_bitwise_equal_to_the_cpu_restatement(cuda):
         print(f"PARITY IK real path, CUDA vs CPU restatement (same sources, same operation order): {name}: {n} solves ({nb} births) "
               f"bit-identical (max |dx| {worst})")
     assert tot >= 140
+
+
+def test_als_tile_builds_agree(cuda):
+    """The two tile builds of k_als (64x96 / 8 warps and 48x48 / 4 warps; the dispatcher picks by problem and batch size):
+    X_bin and stopping iteration of the reference with either, on Shelf, 8 x 12 and 8 x 16 frames."""
+    from multiview_motion_capture_b200 import _lib
+    lib = _lib.get_lib()
+    try:
+        for v in (1, 0):
+            lib.mvmc_als_force_variant(v)
+            assert SC.check_als(DEV, "shelf", list(range(1, 301, 13)), N=64, rmax=16) == 24
+            for name, Pmax, Tmax in (("warm_c8p12", 12, 16), ("warm_c8p16", 16, 24)):
+                fr = _frames(name)
+                N = -(-(Tmax + 8 * Pmax) // 32) * 32
+                assert SC.check_als(DEV, name, fr, N=N, rmax=2 * max(Pmax, Tmax)) == len(fr)
+    finally:
+        lib.mvmc_als_force_variant(-1)
