@@ -1,6 +1,6 @@
 # Round-2 evidence run (one B200): bench at HEAD, reference arm, launch list, ncu --set full of the top kernels, memcheck.
 set -x
-T=r02
+T=${1:-r02}
 timeout 900 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err
 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --als-phases > /dev/null 2> gpurun_out/${T}_k_als_phases.txt
