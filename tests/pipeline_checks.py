@@ -178,3 +178,74 @@ def run_side_by_side_with_oracle(dev, n_views, n_people, n_clips, n_frames, seed
             st["iters"].append(a.n_iter)
         cb.close()
     return st
+
+
+def check_edge_cases(dev):
+    """Edge cases of the per-frame path against the oracle's tracker on the same inputs (a 4-camera, 3-person golden scene,
+    tracks seeded from the reference's table): an empty frame (no pose in any view: every track is marked missed and dies,
+    max_age = 0), a frame after it (no tracks left: the float32 no-track path, births with fresh ids), a frame with poses
+    in ONE view only (nothing can be matched by two views: no update, no birth), a ragged frame (one view empty, one view
+    with a single pose), and poses that fail the filter (all-zero scores). Compared: X_bin, ALS iterations, alive ids,
+    lifecycle counters, died ids, updated ids."""
+    from multiview_motion_capture_b200.clips import ClipBatch
+    inp, g = golden("synth_c4p3")
+    kps_all = o.body25_to_coco(inp["kps25"])
+    C, Pmax, Tmax = kps_all.shape[1], 4, 8
+    cb = ClipBatch(1, C, Pmax, max_tracks=Tmax, max_new=4, device=dev)
+    cb.set_calib(inp["K"][None], inp["RT"][None])
+    tab = GoldenTable(g)
+    trk = o.Tracker(o.projections(inp["K"], inp["RT"]), inp["K"], inp["RT"])
+    f0 = 3
+    pk = tab.packed(f0, 1, Tmax)
+    cb.set_tracks(**pk)
+    for i in range(int(pk["n_trk"][0])):
+        prm = o.PoseParam.unpack(pk["param"][0, i].copy())
+        L = int(pk["length"][0, i])
+        trk.tracks.append(o.Track(int(pk["ids"][0, i]), list(range(f0 - L, f0)), [prm] * L, [pk["joints"][0, i].reshape(18, 3).copy()] * L,
+                                  [[]] * L, state=int(pk["state"][0, i]), hits=int(pk["hits"][0, i]),
+                                  time_since_update=int(pk["tsu"][0, i])))
+    trk.next_id = int(pk["next_id"][0])
+
+    def frame(kind, f):
+        k = pad_poses(kps_all[f], Pmax).copy()
+        n = inp["n_pose"][f].copy().astype(np.int32)
+        if kind == "empty":
+            n[:] = 0
+        elif kind == "one_view":
+            n[1:] = 0
+        elif kind == "ragged":
+            n[0] = 0
+            n[1] = 1
+        elif kind == "filtered":
+            k[:, :, :, 2] = 0.0          # every pose fails filter_bad_pose (no keypoint above the score threshold)
+        return k, n
+
+    seen = []
+    for step, (kind, f) in enumerate([("normal", 3), ("empty", 4), ("normal", 5), ("one_view", 6), ("ragged", 7), ("filtered", 8),
+                                      ("normal", 8)]):
+        k, n = frame(kind, f)
+        fi = 100 + step
+        ids_before = [t.track_id for t in trk.tracks]
+        a = trk.step(fi, k, n)
+        rec = cb.step(k[None], n[None], fi)[0].copy()
+        _, _, xb, dg = cb.read_matrices(0)
+        tag = (kind, f)
+        assert xb.shape == a.x_bin.shape and np.array_equal(xb, a.x_bin), tag + ("X_bin",)
+        if a.x_bin.size:
+            assert int(rec["als_iters"]) == a.n_iter, tag + (int(rec["als_iters"]), a.n_iter)
+        na = int(rec["n_alive"])
+        tr = rec["tracks"][:na]
+        assert tr["track_id"].tolist() == [t.track_id for t in trk.tracks], tag + (tr["track_id"].tolist(), [t.track_id for t in trk.tracks])
+        st = np.stack([tr["state"], tr["hits"], tr["time_since_update"], tr["length"]], 1).reshape(-1, 4)
+        assert np.array_equal(st, np.array([[t.state, t.hits, t.time_since_update, len(t)] for t in trk.tracks]).reshape(-1, 4)), tag
+        died = sorted(set(ids_before) - {t.track_id for t in trk.tracks})
+        assert sorted(rec["died_ids"][:rec["n_died"]].tolist()) == died, tag
+        assert tr[tr["updated"] > 0]["track_id"].tolist() == [t.track_id for t in trk.tracks if t.frame_idxs[-1] == fi], tag
+        assert rec["error"] == 0
+        seen.append((kind, na, len(died)))
+    cb.close()
+    kinds = dict((k, (na, nd)) for k, na, nd in seen)
+    assert kinds["empty"][0] == 0 and kinds["empty"][1] > 0          # everything died on the empty frame
+    # (a one-view match is not solved but still counts as "matched": the track is not marked missed - the reference's quirk,
+    #  src/motion_capture.py:925-934 - so nothing has to die on the single-view frame)
+    return seen

@@ -91,3 +91,9 @@ def test_als_tile_builds_agree(emu):
             assert SC.check_als(DEV, "shelf", [2, 9], N=64, rmax=16) == 2
     finally:
         emu.mvmc_als_force_variant(-1)
+
+
+def test_edge_cases_against_the_oracle(emu):
+    """Empty / single-view / ragged / all-filtered frames and the return to the no-track path after every track died."""
+    from pipeline_checks import check_edge_cases
+    print(check_edge_cases(DEV))

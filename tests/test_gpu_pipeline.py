@@ -170,3 +170,9 @@ def test_clip_streams_equal_clip_batch(cuda):
     """Groups of clips on their own CUDA streams (ClipStreams, mvmc_clips_step_host_async): byte-identical records."""
     from pipeline_checks import check_clip_streams_equal_clip_batch
     check_clip_streams_equal_clip_batch(DEV, name="synth_c8p6", Pmax=8, Tmax=16, max_new=8, frames=(2, 3, 4), B=5, groups=3)
+
+
+def test_edge_cases_against_the_oracle(cuda):
+    """Empty / single-view / ragged / all-filtered frames and the return to the no-track path after every track died."""
+    from pipeline_checks import check_edge_cases
+    print("edge cases (kind, alive after, died):", check_edge_cases(DEV))
