@@ -39,7 +39,9 @@ extern "C" {
 #define MVMC_N_COCO 17
 #define MVMC_N_B18 18
 #define MVMC_N_PARAM 68
-#define MVMC_MAX_SEL 16         /* 2D poses that can feed one IK solve (no-track frames may group >1 pose per view) */
+#define MVMC_MAX_SEL 16         /* 2D poses per IK solve on the fast path (tracked frames use at most one per view) */
+#define MVMC_MAX_GROUP 256      /* 2D poses a no-track group can hold: births from more than MVMC_MAX_SEL poses take the slow path */
+#define MVMC_MAX_BIG 8          /* such groups per clip and frame */
 
 int mvmc_version(void);
 const char* mvmc_error_string(int code);
@@ -110,6 +112,15 @@ int mvmc_assign_listed(const uint32_t* xbin, const int* dim_groups, const int* i
                        int* new_n, int* new_nsel, int* new_sel, int* counts, int* err, int* new_seq, int* singles,
                        void* stream);
 
+/* The same with the overflow lists of the many-pose groups (no-track frames of crowded scenes): a 2D-only group of more than
+ * MVMC_MAX_SEL poses keeps ALL its poses (up to MVMC_MAX_GROUP) in big_sel [B,MVMC_MAX_BIG,MVMC_MAX_GROUP,2], its size in
+ * big_nsel [B,MVMC_MAX_BIG] AND in new_nsel of its birth slot big_slot [B,MVMC_MAX_BIG]; big_n [B] such groups. Only a
+ * group beyond those capacities is still cut to MVMC_MAX_SEL poses and counted in counts[2]. All four or none may be NULL. */
+int mvmc_assign_groups(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose,
+                       const int* n_trk, int B, int C, int N, int Tmax, int max_new, int* trk_nsel, int* trk_sel,
+                       int* new_n, int* new_nsel, int* new_sel, int* counts, int* err, int* new_seq, int* singles,
+                       int* big_n, int* big_nsel, int* big_sel, int* big_slot, void* stream);
+
 /* A6, first half alone — mv_association.py:99-121 transform_closure (what match_als returns as `match_mat`).
  * xbin [B,N,(N+31)/32] as written by mvmc_match_als, n [B] live size of each instance ->
  * match_mat [B,N,N] bytes (leading n x n block written): match[j][i] = 1 iff i is a leader and j belongs to it. */
@@ -176,6 +187,17 @@ int mvmc_ik_solve(const double* kps2d, const double* Psel, const int* n_views, c
                   const uint8_t* birth, const int* max_nfev, const uint8_t* free_mask, int M, int V,
                   void* workspace, double* x_out, double* joints, int* info, double* cost, void* stream);
 
+/* Births from many poses — motion_capture.py:618-624, 942-958: a no-track frame of a crowded scene groups dozens of 2D poses
+ * (several per view) and the reference builds the new track from ALL of them. kps [B,C,Pmax,17,3], P [B,C,3,4]; per clip
+ * big_n [B] groups, big_nsel [B,G] their sizes (<= MVMC_MAX_GROUP), big_sel [B,G,MVMC_MAX_GROUP,2] (view, pose id),
+ * big_slot [B,G]; the solve of group (b, g) is written to row b*S + slot0 + big_slot[b][g] of x_out [.,68], joints [.,18,3],
+ * info [.,2,4], cost [.,2]. Triangulation (+ 2-evaluation refine) and the two max_nfev-evaluation TRF stages of
+ * PoseSolver.solve, with no cap on the number of observations. workspace: mvmc_ik_birth_big_workspace_bytes(). */
+size_t mvmc_ik_birth_big_workspace_bytes(void);
+int mvmc_ik_birth_big(const double* kps, const double* P, const int* big_n, const int* big_nsel, const int* big_sel,
+                      const int* big_slot, int B, int C, int Pmax, int G, int S, int slot0, int max_nfev, void* workspace,
+                      double* x_out, double* joints, int* info, double* cost, void* stream);
+
 /* SURVEY.md 8f-4 — inverse_kinematics.py:280-336 solve_pose / solve_pose_bone_lens, the 3D-target variants behind
  * PoseSolver's `use_only_reproj = False` (:402-415): residual = (FK joint - triangulated point) * point score over the 16
  * IK joints. target [M,16,4] = (x, y, z, score) gathered at the IK joints (BASIC_18 idx 1..7, 9..17 <- 18-point observation
@@ -228,7 +250,8 @@ typedef struct mvmc_track_out {
     int32_t time_since_update;
     int32_t length;                   /* frames in which the track was solved */
     int32_t updated;                  /* 1 = solved this frame (update or birth), 2 = born this frame */
-    int32_t n_sel;                    /* (view, pose) pairs used this frame */
+    int32_t n_sel;                    /* (view, pose) pairs used this frame; a birth from a many-pose group may report more than
+                                         MVMC_MAX_SEL: sel then holds the first ones, mvmc_clips_read_big_groups_host all */
     int32_t sel[MVMC_MAX_SEL][2];
     int32_t nfev[2], njev[2], status[2];
     int32_t pad_;
@@ -246,7 +269,8 @@ typedef struct mvmc_step_out {
     int32_t als_iters;
     int32_t n_dup_view;
     int32_t error;                    /* 0 or MVMC_ERR_CAPACITY */
-    int32_t n_truncated;              /* groups cut to their first MVMC_MAX_SEL poses (see mvmc_assign) */
+    int32_t n_truncated;              /* groups cut to their first MVMC_MAX_SEL poses: only groups beyond the overflow capacities
+                                         (MVMC_MAX_BIG groups of MVMC_MAX_GROUP poses per clip and frame), see mvmc_assign_groups */
     mvmc_track_out tracks[MVMC_MAX_TRACKS];
 } mvmc_step_out;
 
@@ -293,6 +317,11 @@ int mvmc_clips_step_body25_host(mvmc_clips* h, const double* kps25_host, const i
 int mvmc_clips_set_tracks_host(mvmc_clips* h, const int* n_trk, const int* ids, const int* state,
                                const int* hits, const int* tsu, const int* length, const double* param,
                                const double* joints, const int* next_id, void* stream);
+
+/* The many-pose birth groups of clip b in the last step (HOST pointers): *n groups, nsel [MVMC_MAX_BIG] sizes,
+ * slot [MVMC_MAX_BIG] = index among the clip's births of that step (the k-th track with updated == 2 of its record),
+ * sel [MVMC_MAX_BIG, MVMC_MAX_GROUP, 2] (view, pose id). */
+int mvmc_clips_read_big_groups_host(mvmc_clips* h, int b, int* n, int* nsel, int* slot, int* sel, void* stream);
 
 /* Debug/parity read-back of the last step's association matrices of clip b (HOST pointers, sized n*n
  * with n = n_total of that clip; xbin as bytes). Requires keep_matrices=1. */

@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmvmc.so")
 
 MAX_VIEWS, MAX_POSES, MAX_TRACKS, N_COCO, N_B18, N_PARAM, MAX_SEL = 8, 32, 64, 17, 18, 68, 16
+MAX_GROUP, MAX_BIG = 256, 8
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 
 
@@ -51,12 +52,15 @@ _SIGNATURES = {
     "mvmc_match_views_workspace_bytes": (c_size_t, [c_int]),
     "mvmc_match_views_hungarian": (c_int, [_P, _P, c_int, c_int, c_int, c_double, _P, _P, _P, _P, _P]),
     "mvmc_tracklet_pose_association": (c_int, [_P] * 6 + [c_int] * 4 + [c_double, _P, _P, _P, _P]),
+    "mvmc_assign_groups": (c_int, [_P] * 5 + [c_int] * 5 + [_P] * 13 + [_P]),
     "mvmc_transform_closure": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "mvmc_triangulate": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_double, c_int, _P, _P]),
     "mvmc_fk": (c_int, [_P, c_int, _P, _P]),
     "mvmc_fk_chain": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P]),
     "mvmc_ik_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mvmc_ik_solve": (c_int, [_P] * 7 + [c_int, c_int] + [_P] * 6),
+    "mvmc_ik_birth_big_workspace_bytes": (c_size_t, []),
+    "mvmc_ik_birth_big": (c_int, [_P] * 6 + [c_int] * 7 + [_P] * 5 + [_P]),
     "mvmc_ik_solve_targets": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
     "mvmc_default_config": (None, [POINTER(Config)]),
     "mvmc_clips_create": (c_int, [POINTER(Config), POINTER(c_void_p)]),
@@ -75,6 +79,7 @@ _SIGNATURES = {
     "mvmc_ingest_body25": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "mvmc_clips_step_body25_host": (c_int, [c_void_p, _P, _P, c_int, _P, _P]),
     "mvmc_clips_set_tracks_host": (c_int, [c_void_p] + [_P] * 9 + [_P]),
+    "mvmc_clips_read_big_groups_host": (c_int, [c_void_p, c_int, _P, _P, _P, _P, _P]),
     "mvmc_clips_read_matrices_host": (c_int, [c_void_p, c_int, _P, _P, _P, _P, _P, _P]),
     "mvmc_clips_stats_host": (c_int, [c_void_p, _P, c_int, _P]),
     "mvmc_clips_profile": (c_int, [c_void_p, c_int, _P, _P, _P]),

@@ -175,6 +175,18 @@ class ClipBatch:
               "mvmc_clips_profile")
         return dict(zip(self.STAGE_NAMES, out.tolist())), n.value
 
+    def read_big_groups(self, b=0):
+        """The many-pose birth groups of clip b in the last step: {birth index k: [(view, pose id), ...]} (groups of more than
+        MVMC_MAX_SEL poses; k = position among the tracks born in that step)."""
+        from ._lib import MAX_BIG, MAX_GROUP
+        n = ctypes.c_int(0)
+        nsel = np.zeros(MAX_BIG, np.int32)
+        slot = np.zeros(MAX_BIG, np.int32)
+        sel = np.zeros((MAX_BIG, MAX_GROUP, 2), np.int32)
+        check(self.lib.mvmc_clips_read_big_groups_host(self._h, int(b), ctypes.addressof(n), ptr(nsel), ptr(slot), ptr(sel), self._stream()),
+              "mvmc_clips_read_big_groups_host")
+        return {int(slot[g]): [tuple(x) for x in sel[g, :nsel[g]].tolist()] for g in range(n.value)}
+
     def read_matrices(self, b=0):
         """(dst, sim, xbin, dim_groups) of clip b from the last step."""
         N = self.Tmax + self.C * self.Pmax

@@ -15,7 +15,8 @@ __global__ void __launch_bounds__(32)
              const int* __restrict__ idx_pose, const int* __restrict__ n_trk, int C, int N, int Tmax, int max_new,
              int* __restrict__ trk_nsel, int* __restrict__ trk_sel, int* __restrict__ new_n, int* __restrict__ new_nsel,
              int* __restrict__ new_sel, int* __restrict__ counts, int* __restrict__ err, int* __restrict__ new_seq,
-             int* __restrict__ singles) {
+             int* __restrict__ singles, int* __restrict__ big_n, int* __restrict__ big_nsel, int* __restrict__ big_sel,
+             int* __restrict__ big_slot) {
     const int b = blockIdx.x, lane = threadIdx.x;
     const int NW = (N + 31) / 32;
     const int n = dim_groups[b * (C + 2) + C + 1];
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(32)
     uint32_t vis = 0;       // this lane's word of `vis`
     uint32_t assigned = 0;  // this lane's word of "row already attached to a kept column"
     int n_new = 0, dup = 0, error = 0, n_single = 0, n_trunc = 0, seq = 0;   // seq: position among the 2D-only groups
+    int n_big = 0;                                                          // groups of more than MVMC_MAX_SEL poses so far
     const bool has_trk = T > 0;
     for (int i = 0; i < n; i++) {
         const uint32_t vw = __shfl_sync(MVMC_FULL, vis, i >> 5);
@@ -79,9 +81,12 @@ __global__ void __launch_bounds__(32)
                         break;
                     }
             int sel[MVMC_MAX_SEL][2];
-            int nsel = 0;
+            int nsel = 0, ntot = 0;   // poses stored in `sel` / poses of the group
             uint32_t seen_views = 0;
             bool over = false;
+            // a no-track group may hold many poses per view: all of them go to the overflow list as well (kept if > MVMC_MAX_SEL)
+            int* bs = (!has_trk && big_sel && n_big < MVMC_MAX_BIG) ? big_sel + ((size_t)b * MVMC_MAX_BIG + n_big) * MVMC_MAX_GROUP * 2
+                                                                     : nullptr;
             for (int q = 0; q < base; q++) {
                 const int g = s_members[q];
                 if (has_trk && g < T) continue;
@@ -97,10 +102,17 @@ __global__ void __launch_bounds__(32)
                     sel[nsel][0] = v;
                     sel[nsel][1] = ip[g];
                     nsel++;
-                } else {
-                    over = true;  // keep the first MVMC_MAX_SEL poses (include/mvmc.h: n_truncated)
                 }
+                if (bs && ntot < MVMC_MAX_GROUP) {
+                    bs[2 * ntot] = v;
+                    bs[2 * ntot + 1] = ip[g];
+                }
+                ntot++;
             }
+            // more poses than the fast path stages: solved from all of them by the many-pose birth solver if an overflow slot
+            // is free (and the group fits MVMC_MAX_GROUP), else cut to the first MVMC_MAX_SEL and counted (n_truncated)
+            const bool big = ntot > MVMC_MAX_SEL && bs != nullptr && ntot <= MVMC_MAX_GROUP && t_idx < 0 && n_new < max_new;
+            over = ntot > MVMC_MAX_SEL && !big;
             if (over) n_trunc++;
             if (nsel > 0) {
                 if (t_idx >= 0) {
@@ -122,7 +134,12 @@ __global__ void __launch_bounds__(32)
                 } else if (n_new < max_new) {
                     if (new_seq) new_seq[(size_t)b * max_new + n_new] = seq;
                     seq++;
-                    nn_[n_new] = nsel;
+                    nn_[n_new] = big ? ntot : nsel;   // (> MVMC_MAX_SEL: the list is in big_sel, new_sel holds its first poses)
+                    if (big) {
+                        big_nsel[b * MVMC_MAX_BIG + n_big] = ntot;
+                        big_slot[b * MVMC_MAX_BIG + n_big] = n_new;
+                        n_big++;
+                    }
                     for (int q = 0; q < nsel; q++) {
                         ns[(n_new * MVMC_MAX_SEL + q) * 2] = sel[q][0];
                         ns[(n_new * MVMC_MAX_SEL + q) * 2 + 1] = sel[q][1];
@@ -141,6 +158,7 @@ __global__ void __launch_bounds__(32)
         counts[4 * b + 1] = n_single;
         counts[4 * b + 2] = n_trunc;
         err[b] = error;
+        if (big_n) big_n[b] = n_big;
     }
 }
 
@@ -186,10 +204,13 @@ extern "C" int mvmc_transform_closure(const uint32_t* xbin, const int* n, int B,
     return MVMC_OK;
 }
 
-extern "C" int mvmc_assign_listed(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose,
+extern "C" int mvmc_assign_groups(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose,
                                   const int* n_trk, int B, int C, int N, int Tmax, int max_new, int* trk_nsel, int* trk_sel,
                                   int* new_n, int* new_nsel, int* new_sel, int* counts, int* err, int* new_seq, int* singles,
-                                  void* stream) {
+                                  int* big_n, int* big_nsel, int* big_sel, int* big_slot, void* stream) {
+    if ((big_n != nullptr) != (big_sel != nullptr) || (big_n != nullptr) != (big_nsel != nullptr) ||
+        (big_n != nullptr) != (big_slot != nullptr))
+        return MVMC_ERR_INVALID;
     if (!xbin || !dim_groups || !idx_view || !idx_pose || !n_trk || !trk_nsel || !trk_sel || !new_n || !new_nsel ||
         !new_sel || !counts || !err)
         return MVMC_ERR_INVALID;
@@ -197,9 +218,17 @@ extern "C" int mvmc_assign_listed(const uint32_t* xbin, const int* dim_groups, c
         Tmax > MVMC_MAX_TRACKS || max_new <= 0)
         return MVMC_ERR_INVALID;   // (k_assign lists a group's members in shared memory sized for the largest layout)
     MVMC_LAUNCH(k_assign, dim3(B), dim3(32), 0, stream, xbin, dim_groups, idx_view, idx_pose, n_trk, C, N, Tmax, max_new,
-                trk_nsel, trk_sel, new_n, new_nsel, new_sel, counts, err, new_seq, singles);
+                trk_nsel, trk_sel, new_n, new_nsel, new_sel, counts, err, new_seq, singles, big_n, big_nsel, big_sel, big_slot);
     MVMC_CHECK_LAUNCH("k_assign");
     return MVMC_OK;
+}
+
+extern "C" int mvmc_assign_listed(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose,
+                                  const int* n_trk, int B, int C, int N, int Tmax, int max_new, int* trk_nsel, int* trk_sel,
+                                  int* new_n, int* new_nsel, int* new_sel, int* counts, int* err, int* new_seq, int* singles,
+                                  void* stream) {
+    return mvmc_assign_groups(xbin, dim_groups, idx_view, idx_pose, n_trk, B, C, N, Tmax, max_new, trk_nsel, trk_sel, new_n,
+                              new_nsel, new_sel, counts, err, new_seq, singles, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int mvmc_assign(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose,

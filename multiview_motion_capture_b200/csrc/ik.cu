@@ -203,6 +203,7 @@ __device__ __forceinline__ void project3(const double* Pv, double X, double Y, d
 // ---- reprojection residual of the BASIC_18 pose (inverse_kinematics.py:202-277) ----
 // rows: (view v, observed joint q, {u, v}) -> (v*16 + q)*2 + {0,1};  a chunk = 4 joints of one view (8 rows)
 struct IkRes {
+    static constexpr bool kGlobalF = false;
     const double* obs;   // [V][16][3] gathered at c_ik_obs_idx (shared)
     const double* P;     // [V][12] (shared)
     double* posb;        // [16][3] scratch (shared)
@@ -285,6 +286,7 @@ struct IkRes {
 // ---- 3D-target residual (inverse_kinematics.py:280-336 solve_pose / solve_pose_bone_lens): FK joints against triangulated
 // points, rows (observed joint q, coordinate c) -> 3 q + c, weighted by the point's score; 48 rows = 6 chunks of 8 ----
 struct Ik3dRes {
+    static constexpr bool kGlobalF = false;
     const double* tgt;   // [16][4] (x, y, z, score), gathered at the IK joints (shared)
     double* posb;        // [16][3] scratch (shared)
     double* Rloc;        // [18][9] (shared)
@@ -339,6 +341,7 @@ struct Ik3dRes {
 // ---- triangulation refine residual (mv_math_util.py:190-202): rows (view v, point k) -> v*K + k ----
 // a chunk = a third of the points of one view (K <= 18: at most 6 rows)
 struct TriRes {
+    static constexpr bool kGlobalF = false;
     const double* obs;  // [V][K][3] (shared)
     const double* P;    // [V][12]
     int V, K;
@@ -553,6 +556,284 @@ __device__ int ik_columns(TrfWarp& t, const uint8_t* free_mask, int npar, int& n
     }
     __syncwarp();
     return ncol;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Births from MANY poses. A no-track frame of a crowded scene makes the reference's float32 affinity merge dozens of 2D
+// poses (several per view, of several people) into one group, and it then builds the new track from ALL of them
+// (motion_capture.py:618-624, 942-958: cam_poses_2d = every grouped pose, one "view" each). Groups of up to MVMC_MAX_SEL
+// poses go through k_ik_solve's shared-memory staging; larger ones (up to MVMC_MAX_GROUP) are solved here, one warp per
+// group, with the observations, the residual vectors and the DLT systems in a global scratch slot owned by the CTA: same
+// triangulation (+ 2-evaluation refine), same two 50-evaluation TRF stages, no cap on the number of "views".
+// ------------------------------------------------------------------------------------------------
+struct BigScratch {
+    double f[32 * MVMC_MAX_GROUP], fn[32 * MVMC_MAX_GROUP];
+    double obs18[MVMC_MAX_GROUP * 18 * 3];
+    double dlt[18][2 * MVMC_MAX_GROUP][4];
+};
+struct IkResBig {
+    static constexpr bool kGlobalF = true;
+    const double* obs18;  // [V][18][3] (global scratch): COCO + mid spine
+    const int* vof;       // [V] camera of every pose (shared)
+    const double* P;      // [C][12] (shared)
+    double* posb;
+    double* Rloc;
+    int V;
+    __device__ int m() const { return V * MVMC_N_IKJ * 2; }
+    __device__ int n_chunks() const { return 4 * V; }
+    __device__ int chunk_rows(int) const { return 8; }
+    __device__ int chunk_row0(int c) const { return 8 * c; }
+    __device__ __noinline__ void eval(const double* x, double* f) {
+        const int lane = threadIdx.x & 31;
+        local_rots(x, Rloc);
+        fk_store(x, Rloc, -1, 0.0, posb, 1, true, lane == 0);
+        __syncwarp();
+        for (int it = lane; it < V * MVMC_N_IKJ; it += 32) {
+            const int v = it >> 4, q = it & 15;
+            const double* o = obs18 + (v * 18 + c_ik_obs_idx[q]) * 3;
+            double pu, pv, pw;
+            project3(P + vof[v] * 12, posb[q * 3], posb[q * 3 + 1], posb[q * 3 + 2], pu, pv, pw);
+            const double inv = 1.0 / (1e-5 + pw);
+            f[2 * it] = DMUL(DSUB(DMUL(pu, inv), o[0]), o[2]);
+            f[2 * it + 1] = DMUL(DSUB(DMUL(pv, inv), o[1]), o[2]);
+        }
+        __syncwarp();
+    }
+    __device__ void fd_prepare(TrfWarp& s, int ncol) {
+        const int lane = threadIdx.x & 31;
+        double* S = s.A;
+        local_rots(s.x, Rloc);
+        for (int c0 = 0; c0 < ncol; c0 += 32) {
+            const int c = c0 + lane;
+            const bool on = c < ncol;
+            fk_store(s.x, Rloc, on ? s.act[c] : -1, on ? s.w[c] : 0.0, S + c, WS_NC, true, on);
+        }
+    }
+    __device__ __forceinline__ void fd_chunk(TrfWarp& s, int ncol, int ch, const double* f) {
+        const int lane = threadIdx.x & 31;
+        const int v = ch >> 2, q0 = (ch & 3) * 4;
+        const double* S = s.A;
+        double Pv[12];
+#pragma unroll
+        for (int e = 0; e < 12; e++) Pv[e] = P[vof[v] * 12 + e];
+        for (int c = lane; c < ncol; c += 32) {
+            const double rdx = s.tau[c];
+#pragma unroll
+            for (int qq = 0; qq < 4; qq++) {
+                const int q = q0 + qq;
+                const double* o = obs18 + (v * 18 + c_ik_obs_idx[q]) * 3;
+                double pu, pv, pw;
+                project3(Pv, S[(q * 3) * WS_NC + c], S[(q * 3 + 1) * WS_NC + c], S[(q * 3 + 2) * WS_NC + c], pu, pv, pw);
+                const double inv = 1.0 / (1e-5 + pw);
+                const double ru = DMUL(DSUB(DMUL(pu, inv), o[0]), o[2]);
+                const double rv = DMUL(DSUB(DMUL(pv, inv), o[1]), o[2]);
+                const int row = (v * MVMC_N_IKJ + q) * 2;
+                s.Jc[(2 * qq) * WS_LDJ + c] = DMUL(DSUB(ru, f[row]), rdx);
+                s.Jc[(2 * qq + 1) * WS_LDJ + c] = DMUL(DSUB(rv, f[row + 1]), rdx);
+            }
+        }
+    }
+};
+struct TriResBig {
+    static constexpr bool kGlobalF = true;
+    const double* obs;  // [V][18][3] (global)
+    const int* vof;
+    const double* P;
+    int V;
+    static constexpr int K = 18;
+    __device__ int m() const { return V * K; }
+    __device__ int n_chunks() const { return 3 * V; }
+    __device__ int chunk_rows(int) const { return 6; }
+    __device__ int chunk_row0(int c) const { return (c / 3) * K + 6 * (c % 3); }
+    __device__ double one(const double* Pv, const double* o, double X, double Y, double Z) const {
+        double pu, pv, pw;
+        project3(Pv, X, Y, Z, pu, pv, pw);
+        const double den = pw + 1e-6;
+        const double du = DSUB(DDIV(pu, den), o[0]), dv = DSUB(DDIV(pv, den), o[1]);
+        return DMUL(sqrt(DMUL(du, du) + DMUL(dv, dv)), o[2]);
+    }
+    __device__ void eval(const double* x, double* f) {
+        const int lane = threadIdx.x & 31;
+        for (int it = lane; it < V * K; it += 32) {
+            const int v = it / K, k = it % K;
+            f[it] = one(P + vof[v] * 12, obs + it * 3, x[3 * k], x[3 * k + 1], x[3 * k + 2]);
+        }
+        __syncwarp();
+    }
+    __device__ void fd_prepare(TrfWarp&, int) {}
+    __device__ void fd_chunk(TrfWarp& s, int ncol, int ch, const double* f) {
+        const int lane = threadIdx.x & 31;
+        const int v = ch / 3, k0 = 6 * (ch % 3), k1 = k0 + 6;
+        for (int c = lane; c < ncol; c += 32) {
+            const int prm = s.act[c], k = prm / 3, comp = prm % 3;
+            for (int r = 0; r < 6; r++) s.Jc[r * WS_LDJ + c] = 0.0;
+            if (k < k0 || k >= k1) continue;
+            double X[3] = {s.x[3 * k], s.x[3 * k + 1], s.x[3 * k + 2]};
+            X[comp] = s.w[c];
+            const double r = one(P + vof[v] * 12, obs + (v * K + k) * 3, X[0], X[1], X[2]);
+            s.Jc[(k - k0) * WS_LDJ + c] = DDIV(DSUB(r, f[v * K + k]), s.dx[c]);
+        }
+    }
+};
+
+// DLT of one joint from any number of views: the (2 nsel x 4) system in a global scratch block (one-sided Jacobi, the
+// arithmetic of dlt_point on the compacted rows)
+__device__ void dlt_point_dyn(double (*a)[4], int rows, double* out3) {
+    double v[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    for (int sweep = 0; sweep < 30; sweep++) {
+        bool rotated = false;
+        for (int p = 0; p < 3; p++)
+            for (int q = p + 1; q < 4; q++) {
+                double app = 0, aqq = 0, apq = 0;
+                for (int r = 0; r < rows; r++) {
+                    app += a[r][p] * a[r][p];
+                    aqq += a[r][q] * a[r][q];
+                    apq += a[r][p] * a[r][q];
+                }
+                if (apq == 0.0 || fabs(apq) <= kEps * sqrt(app * aqq)) continue;
+                rotated = true;
+                const double tau = (aqq - app) / (2.0 * apq);
+                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                const double c = 1.0 / sqrt(1.0 + t * t), sn = t * c;
+                for (int r = 0; r < rows; r++) {
+                    const double ap = a[r][p], aq = a[r][q];
+                    a[r][p] = c * ap - sn * aq;
+                    a[r][q] = sn * ap + c * aq;
+                }
+                for (int r = 0; r < 4; r++) {
+                    const double vp = v[r][p], vq = v[r][q];
+                    v[r][p] = c * vp - sn * vq;
+                    v[r][q] = sn * vp + c * vq;
+                }
+            }
+        if (!rotated) break;
+    }
+    int best = 0;
+    double bn = INFINITY;
+    for (int c = 0; c < 4; c++) {
+        double nn = 0;
+        for (int r = 0; r < rows; r++) nn += a[r][c] * a[r][c];
+        if (nn < bn) {
+            bn = nn;
+            best = c;
+        }
+    }
+    out3[0] = v[0][best] / v[3][best];
+    out3[1] = v[1][best] / v[3][best];
+    out3[2] = v[2][best] / v[3][best];
+}
+
+struct BigSh {
+    TrfWarp t;
+    double P[MVMC_MAX_VIEWS * 12];
+    double p3[18 * 4];
+    double posb[MVMC_N_IKJ * 3];
+    double Rloc[MVMC_N_B18 * 9];
+    int vof[MVMC_MAX_GROUP];
+};
+
+// items: (clip b, big group g) for g < big_n[b]; the group's (view, pose id) list is big_sel[b][g][0..nsel); the result goes
+// to work slot b * S + slot0 + big_slot[b][g]. Persistent CTAs (one warp, one scratch slot each) scan the items.
+__global__ void __launch_bounds__(32)
+    k_ik_birth_big(const double* __restrict__ kps, const double* __restrict__ Pm, const int* __restrict__ big_n,
+                   const int* __restrict__ big_nsel, const int* __restrict__ big_sel, const int* __restrict__ big_slot, int B, int C,
+                   int Pmax, int G, int S, int slot0, int nfev_cap, BigScratch* __restrict__ scratch, int* __restrict__ counter,
+                   double* __restrict__ x_out, double* __restrict__ joints, int* __restrict__ info, double* __restrict__ cost_out) {
+    MVMC_DYN_SMEM(BigSh, shp);
+    BigSh& sh = *shp;
+    BigScratch& sc = scratch[blockIdx.x];
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(counter, 1);
+        item = __shfl_sync(MVMC_FULL, item, 0);
+        if (item >= B * G) break;
+        const int b = item / G, g = item % G;
+        if (g >= big_n[b]) continue;
+        const int nv = min(big_nsel[b * G + g], MVMC_MAX_GROUP);
+        const int* sel = big_sel + ((size_t)b * G + g) * MVMC_MAX_GROUP * 2;
+        const size_t mI = (size_t)b * S + slot0 + big_slot[b * G + g];
+        __syncwarp();
+        for (int e = lane; e < C * 12; e += 32) sh.P[e] = Pm[(size_t)b * C * 12 + e];
+        for (int v = lane; v < nv; v += 32) sh.vof[v] = sel[2 * v];
+        for (int e = lane; e < nv * MVMC_N_COCO * 3; e += 32) {
+            const int v = e / (MVMC_N_COCO * 3), q = e % (MVMC_N_COCO * 3);
+            sc.obs18[v * 54 + q] = kps[((size_t)(b * C + sel[2 * v]) * Pmax + sel[2 * v + 1]) * (MVMC_N_COCO * 3) + q];
+        }
+        __syncwarp();
+        for (int v = lane; v < nv; v += 32) mid_spine(sc.obs18 + v * 54, sc.obs18 + v * 54 + 51);
+        __syncwarp();
+        // triangulate the 18 points (score >= 0.01, all views if fewer than two qualify), mv_math_util.py:152-186
+        if (lane < 18) {
+            const int k = lane;
+            int nsel = 0;
+            for (int v = 0; v < nv; v++) nsel += sc.obs18[(v * 18 + k) * 3 + 2] >= 0.01 ? 1 : 0;
+            const bool all = nsel < 2;
+            double (*a)[4] = sc.dlt[k];
+            int rows = 0;
+            double ssum = 0.0;
+            for (int v = 0; v < nv; v++) {
+                const double* o = sc.obs18 + (v * 18 + k) * 3;
+                if (!(all || o[2] >= 0.01)) continue;
+                const double* Pv = sh.P + sh.vof[v] * 12;
+                for (int c = 0; c < 4; c++) {
+                    a[rows][c] = o[0] * Pv[8 + c] - Pv[c];
+                    a[rows + 1][c] = o[1] * Pv[8 + c] - Pv[4 + c];
+                }
+                rows += 2;
+                ssum += o[2];
+            }
+            dlt_point_dyn(a, rows, sh.p3 + k * 4);
+            sh.p3[k * 4 + 3] = ssum / (rows / 2);
+        }
+        __syncwarp();
+        {   // 2-evaluation refine of the 54 coordinates (mv_math_util.py:188-210)
+            for (int e = lane; e < MVMC_N_PARAM; e += 32) sh.t.x[e] = 0.0;
+            __syncwarp();
+            for (int e = lane; e < 54; e += 32) {
+                sh.t.x[e] = sh.p3[(e / 3) * 4 + (e % 3)];
+                sh.t.act[e] = e;
+            }
+            __syncwarp();
+            TriResBig tr{sc.obs18, sh.vof, sh.P, nv};
+            trf_solve_warp(sh.t, tr, 54, 54, 0.0, false, 2, sc.f, sc.fn);
+            __syncwarp();
+            for (int e = lane; e < 54; e += 32) sh.p3[(e / 3) * 4 + (e % 3)] = sh.t.x[e];
+            __syncwarp();
+        }
+        if (lane == 0) {
+            for (int c = 0; c < 3; c++) sh.t.x[c] = 0.5 * (sh.p3[kCocoLHip * 4 + c] + sh.p3[kCocoRHip * 4 + c]);
+            for (int e = 3; e < 57; e++) sh.t.x[e] = 0.0;
+            for (int e = 0; e < 11; e++) sh.t.x[57 + e] = c_skel.ref_side_lens[e];
+        }
+        __syncwarp();
+        IkResBig res{sc.obs18, sh.vof, sh.P, sh.posb, sh.Rloc, nv};
+        TrfResult r[2];
+        int ncols[2];
+#pragma unroll 1
+        for (int stage = 0; stage < 2; stage++) {
+            int n_opt;
+            double x2_dead;
+            bool has_dead;
+            const int ncol = ik_columns(sh.t, nullptr, stage == 0 ? 57 : MVMC_N_PARAM, n_opt, x2_dead, has_dead);
+            ncols[stage] = n_opt;
+            r[stage] = trf_solve_warp(sh.t, res, ncol, n_opt, x2_dead, has_dead, nfev_cap, sc.f, sc.fn);
+            __syncwarp();
+        }
+        for (int e = lane; e < MVMC_N_PARAM; e += 32) x_out[mI * MVMC_N_PARAM + e] = sh.t.x[e];
+        local_rots(sh.t.x, sh.Rloc);
+        fk_store(sh.t.x, sh.Rloc, -1, 0.0, joints + mI * MVMC_N_B18 * 3, 1, false, lane == 0);
+        if (lane == 0) {
+            for (int q = 0; q < 2; q++) {
+                info[mI * 8 + 4 * q] = r[q].nfev;
+                info[mI * 8 + 4 * q + 1] = r[q].njev;
+                info[mI * 8 + 4 * q + 2] = r[q].status;
+                info[mI * 8 + 4 * q + 3] = ncols[q];
+                cost_out[mI * 2 + q] = r[q].cost;
+            }
+        }
+        __syncwarp();
+    }
 }
 
 template <int VMAX, bool WITH_BIRTH>
@@ -901,6 +1182,31 @@ extern "C" int mvmc_ik_solve(const double* kps2d, const double* Psel, const int*
     if (M <= 0 || V < 2 || V > MVMC_MAX_SEL) return MVMC_ERR_INVALID;
     return mvmc_ik_launch(kps2d, Psel, n_views, x0, birth, max_nfev, free_mask, M, M, M, 0, V, V, (int*)workspace, x_out,
                           joints, info, cost, stream);
+}
+
+constexpr int IK_BIG_CTAS = 148;
+extern "C" size_t mvmc_ik_birth_big_workspace_bytes(void) { return 256 + (size_t)IK_BIG_CTAS * sizeof(BigScratch); }
+
+// Births from groups of more than MVMC_MAX_SEL poses (see k_ik_birth_big). kps [B,C,Pmax,17,3], P [B,C,3,4]; big_n [B],
+// big_nsel [B,G], big_sel [B,G,MVMC_MAX_GROUP,2] (view, pose id), big_slot [B,G]; outputs at work slot b*S + slot0 +
+// big_slot[b][g] of x_out [.,68], joints [.,18,3], info [.,2,4], cost [.,2]. workspace: mvmc_ik_birth_big_workspace_bytes().
+extern "C" int mvmc_ik_birth_big(const double* kps, const double* P, const int* big_n, const int* big_nsel, const int* big_sel,
+                                 const int* big_slot, int B, int C, int Pmax, int G, int S, int slot0, int max_nfev, void* workspace,
+                                 double* x_out, double* joints, int* info, double* cost, void* stream) {
+    if (!kps || !P || !big_n || !big_nsel || !big_sel || !big_slot || !workspace || !x_out || !joints || !info || !cost)
+        return MVMC_ERR_INVALID;
+    if (B <= 0 || C <= 0 || C > MVMC_MAX_VIEWS || Pmax <= 0 || G <= 0 || S <= 0 || slot0 < 0 || max_nfev < 1) return MVMC_ERR_INVALID;
+    int rc = ensure_skeleton();
+    if (rc) return rc;
+    int* counter = (int*)workspace;
+    BigScratch* scratch = (BigScratch*)((char*)workspace + 256);
+    MVMC_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
+    MVMC_CUDA_OK(cudaFuncSetAttribute(k_ik_birth_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSh)));
+    const int grid = B * G < IK_BIG_CTAS ? B * G : IK_BIG_CTAS;
+    MVMC_LAUNCH(k_ik_birth_big, dim3(grid), dim3(32), sizeof(BigSh), stream, kps, P, big_n, big_nsel, big_sel, big_slot, B, C, Pmax, G,
+                S, slot0, max_nfev, scratch, counter, x_out, joints, info, cost);
+    MVMC_CHECK_LAUNCH("k_ik_birth_big");
+    return MVMC_OK;
 }
 
 extern "C" int mvmc_ik_solve_targets(const double* target, const double* x0, const int* max_nfev, int stages, int M,

@@ -17,6 +17,14 @@ int mvmc_als_order(const int* prev_iter, int B, int* order, void* stream);
 int mvmc_match_als_ordered(const double* sim, const int* dim_groups, int n_groups, const int* f32_first_iter,
                            const double* rand_stream, const int* order, int B, int N, int rmax, void* workspace, uint32_t* xbin,
                            int* n_iter, void* stream);
+int mvmc_assign_groups(const uint32_t* xbin, const int* dim_groups, const int* idx_view, const int* idx_pose, const int* n_trk, int B,
+                       int C, int N, int Tmax, int max_new, int* trk_nsel, int* trk_sel, int* new_n, int* new_nsel, int* new_sel,
+                       int* counts, int* err, int* new_seq, int* singles, int* big_n, int* big_nsel, int* big_sel, int* big_slot,
+                       void* stream);
+size_t mvmc_ik_birth_big_workspace_bytes(void);
+int mvmc_ik_birth_big(const double* kps, const double* P, const int* big_n, const int* big_nsel, const int* big_sel,
+                      const int* big_slot, int B, int C, int Pmax, int G, int S, int slot0, int max_nfev, void* workspace,
+                      double* x_out, double* joints, int* info, double* cost, void* stream);
 int mvmc_ik_launch(const double* kps2d, const double* Psel, const int* n_views, const double* x0, const uint8_t* birth,
                    const int* max_nfev, const uint8_t* free_mask, int n_items, int cnt, int S, int s0, int V, int vmax,
                    int* counter, double* x_out, double* joints, int* info, double* cost, void* stream);
@@ -140,7 +148,7 @@ __global__ void __launch_bounds__(128)
         } else {
             const int k = slot - Tmax;
             if (k < nb && new_nsel[b * max_new + k] >= 2) {
-                nsel = new_nsel[b * max_new + k];
+                nsel = min(new_nsel[b * max_new + k], MVMC_MAX_SEL);   // (a many-pose group: its first poses; solved again from all)
                 sel = new_sel + ((size_t)b * max_new + k) * MVMC_MAX_SEL * 2;
                 birth = true;
             }
@@ -419,6 +427,8 @@ struct mvmc_clips {
     int *w_nv = nullptr, *w_nfev = nullptr, *w_info = nullptr;
     uint8_t* w_birth = nullptr;
     void* ik_ws = nullptr;
+    int *big_n = nullptr, *big_nsel = nullptr, *big_sel = nullptr, *big_slot = nullptr;   // many-pose birth groups of the step
+    void* big_ws = nullptr;
     mvmc_step_out* out = nullptr;
     double* stats = nullptr;  // [MVMC_N_STATS] device counters
     // side stream for the birth solves (a handful per step, each ~10x an update: alone they are a ~5 ms latency tail)
@@ -578,6 +588,15 @@ extern "C" int mvmc_clips_create(const mvmc_config* cfg, mvmc_clips** out) {
         h->bytes += nb;
         h->ik_ws = p;
     }
+    TRY(h->alloc(&h->big_n, (size_t)B));
+    TRY(h->alloc(&h->big_nsel, (size_t)B * MVMC_MAX_BIG));
+    TRY(h->alloc(&h->big_slot, (size_t)B * MVMC_MAX_BIG));
+    TRY(h->alloc(&h->big_sel, (size_t)B * MVMC_MAX_BIG * MVMC_MAX_GROUP * 2));
+    {
+        unsigned char* p = nullptr;
+        TRY(h->alloc(&p, mvmc_ik_birth_big_workspace_bytes()));
+        h->big_ws = p;
+    }
     TRY(h->alloc(&h->out, (size_t)B));
     TRY(h->alloc(&h->stats, (size_t)MVMC_N_STATS));
     {
@@ -660,8 +679,9 @@ extern "C" int mvmc_clips_step(mvmc_clips* h, const double* kps, const int* n_po
                                 h->xbin, h->als_iter, stream);
     if (rc) return rc;
     MVMC_EV(2);
-    rc = mvmc_assign(h->xbin, h->dim_groups, h->idx_view, h->idx_pose, h->st.n_trk, B, C, N, Tmax, h->cfg.max_new,
-                     h->trk_nsel, h->trk_sel, h->new_n, h->new_nsel, h->new_sel, h->n_dup, h->assign_err, stream);
+    rc = mvmc_assign_groups(h->xbin, h->dim_groups, h->idx_view, h->idx_pose, h->st.n_trk, B, C, N, Tmax, h->cfg.max_new,
+                            h->trk_nsel, h->trk_sel, h->new_n, h->new_nsel, h->new_sel, h->n_dup, h->assign_err, nullptr, nullptr,
+                            h->big_n, h->big_nsel, h->big_sel, h->big_slot, stream);
     if (rc) return rc;
     MVMC_LAUNCH(k_gather, dim3(B), dim3(128), 0, stream, kps, h->P, h->st, h->trk_nsel, h->trk_sel, h->new_n, h->new_nsel,
                 h->new_sel, C, Pmax, Tmax, h->cfg.max_new, h->cfg.nfev_update, h->cfg.nfev_birth, h->w_kps, h->w_P, h->w_nv,
@@ -682,6 +702,11 @@ extern "C" int mvmc_clips_step(mvmc_clips* h, const double* kps, const int* n_po
     rc = mvmc_ik_launch(h->w_kps, h->w_P, h->w_nv, h->w_x0, h->w_birth, h->w_nfev, nullptr, B * h->cfg.max_new, h->cfg.max_new,
                         h->S, Tmax, MVMC_MAX_SEL, MVMC_MAX_SEL, (int*)h->ik_ws + 16, h->w_xout, h->w_joints, h->w_info,
                         h->w_cost, bstream);
+    if (rc) return rc;
+    // births from groups of more than MVMC_MAX_SEL poses (crowded no-track frames): solved again, from all their poses, by the
+    // many-pose solver, which overwrites the slot the fast path filled from the first MVMC_MAX_SEL (148 idle warps otherwise)
+    rc = mvmc_ik_birth_big(kps, h->P, h->big_n, h->big_nsel, h->big_sel, h->big_slot, B, C, Pmax, MVMC_MAX_BIG, h->S, Tmax,
+                           h->cfg.nfev_birth, h->big_ws, h->w_xout, h->w_joints, h->w_info, h->w_cost, bstream);
     if (rc) return rc;
     rc = mvmc_ik_launch(h->w_kps, h->w_P, h->w_nv, h->w_x0, nullptr, h->w_nfev, nullptr, B * Tmax, Tmax, h->S, 0,
                         MVMC_MAX_SEL, C, (int*)h->ik_ws, h->w_xout, h->w_joints, h->w_info, h->w_cost, ustream);
@@ -867,6 +892,17 @@ extern "C" int mvmc_clips_set_tracks_host(mvmc_clips* h, const int* n_trk, const
     MVMC_CUDA_OK(cudaMemcpyAsync(h->st.param, param, BT * MVMC_N_PARAM * sizeof(double), cudaMemcpyHostToDevice, s));
     MVMC_CUDA_OK(cudaMemcpyAsync(h->st.joints, joints, BT * 54 * sizeof(double), cudaMemcpyHostToDevice, s));
     MVMC_CUDA_OK(cudaStreamSynchronize(s));
+    return MVMC_OK;
+}
+
+extern "C" int mvmc_clips_read_big_groups_host(mvmc_clips* h, int b, int* n, int* nsel, int* slot, int* sel, void* stream) {
+    if (!h || b < 0 || b >= h->B || !n || !nsel || !slot || !sel) return MVMC_ERR_INVALID;
+    MVMC_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    MVMC_CUDA_OK(cudaMemcpy(n, h->big_n + b, sizeof(int), cudaMemcpyDeviceToHost));
+    MVMC_CUDA_OK(cudaMemcpy(nsel, h->big_nsel + (size_t)b * MVMC_MAX_BIG, MVMC_MAX_BIG * sizeof(int), cudaMemcpyDeviceToHost));
+    MVMC_CUDA_OK(cudaMemcpy(slot, h->big_slot + (size_t)b * MVMC_MAX_BIG, MVMC_MAX_BIG * sizeof(int), cudaMemcpyDeviceToHost));
+    MVMC_CUDA_OK(cudaMemcpy(sel, h->big_sel + (size_t)b * MVMC_MAX_BIG * MVMC_MAX_GROUP * 2,
+                            (size_t)MVMC_MAX_BIG * MVMC_MAX_GROUP * 2 * sizeof(int), cudaMemcpyDeviceToHost));
     return MVMC_OK;
 }
 

@@ -83,7 +83,7 @@ __device__ __forceinline__ void lane_tile(int lane, int& ti, int& tj) {
 template <class Res>
 __device__ __noinline__ void trf_jacobian(TrfWarp& s, Res& res, int ncol, const double* f) {
     MVMC_ASSUME_SHARED(&s);
-    MVMC_ASSUME_SHARED(f);
+    if constexpr (!Res::kGlobalF) MVMC_ASSUME_SHARED(f);   // (the many-view birth solver keeps its residual vectors in global memory)
     const int lane = threadIdx.x & 31;
     for (int e = lane; e < WS_CH * WS_LDJ; e += 32) s.Jc[e] = 0.0;
     // SciPy's 2-point rule: h = sqrt(eps) * sign(x) * max(1, |x|) with sign(0) = +1, dx = (x + h) - x

@@ -333,18 +333,26 @@ class MvTracker:
         n = int(rec["n_alive"])
         self.n_dup_view += int(rec["n_dup_view"])
         if int(rec["n_truncated"]):
-            # a no-track frame of a crowded scene: the reference's float32 affinity merged more than MVMC_MAX_SEL poses into one
-            # group and would run the birth IK on all of them; the library keeps the first MVMC_MAX_SEL (include/mvmc.h)
+            # a group beyond even the overflow capacities (MVMC_MAX_BIG groups of MVMC_MAX_GROUP poses per frame) was cut to its
+            # first MVMC_MAX_SEL poses; the reference would solve the birth from all of them (include/mvmc.h)
             self.n_truncated += int(rec["n_truncated"])
             import warnings
             warnings.warn(f"frame {frm_idx}, clip {b}: {int(rec['n_truncated'])} association group(s) held more than "
                           f"{len(rec['tracks']['sel'][0])} poses and were cut to that many before the birth solve "
                           f"(the reference solves from all of them)")
         alive_ids = []
+        big, k_born = None, 0
         for t in rec["tracks"][:n]:
             tid = int(t["track_id"])
             alive_ids.append(tid)
-            sel = [(int(v), int(p)) for v, p in t["sel"][:t["n_sel"]]]
+            sel = [(int(v), int(p)) for v, p in t["sel"][:min(int(t["n_sel"]), len(t["sel"]))]]
+            if t["updated"] == 2:
+                if int(t["n_sel"]) > len(t["sel"]):
+                    # born from more poses than a record lists (a crowded no-track frame: the reference solves the new track
+                    # from every pose of the group): the full list comes from the library's overflow table
+                    big = self._cb.read_big_groups(b) if big is None else big
+                    sel = [(int(v), int(p)) for v, p in big[k_born]]
+                k_born += 1
             if t["updated"] == 2:
                 cam_poses = [(v, frames[v].poses[p]) for v, p in sel]
                 pose = Pose(KpsFormat.BASIC_18, t["joints"].reshape(18, 3).copy(), np.ones((18, 1)), None)

@@ -129,13 +129,16 @@ def assign(xbin, prep, n_trk, C, max_new):
     Tmax = prep["Tmax"]
     dev = xbin.device
     z = lambda *s: torch.zeros(s, dtype=i32, device=dev)
+    from ._lib import MAX_BIG, MAX_GROUP
     out = dict(trk_nsel=z(B, max(Tmax, 1)), trk_sel=z(B, max(Tmax, 1), MAX_SEL, 2), new_n=z(B), new_nsel=z(B, max_new),
-               new_sel=z(B, max_new, MAX_SEL, 2), counts=z(B, 4), err=z(B), new_seq=z(B, max_new), singles=z(B, max_new, 3))
-    check(_lib.get_lib().mvmc_assign_listed(ptr(xbin), ptr(prep["dim_groups"]), ptr(prep["idx_view"]), ptr(prep["idx_pose"]),
+               new_sel=z(B, max_new, MAX_SEL, 2), counts=z(B, 4), err=z(B), new_seq=z(B, max_new), singles=z(B, max_new, 3),
+               big_n=z(B), big_nsel=z(B, MAX_BIG), big_sel=z(B, MAX_BIG, MAX_GROUP, 2), big_slot=z(B, MAX_BIG))
+    check(_lib.get_lib().mvmc_assign_groups(ptr(xbin), ptr(prep["dim_groups"]), ptr(prep["idx_view"]), ptr(prep["idx_pose"]),
                                             ptr(n_trk), B, C, N, Tmax, max_new, ptr(out["trk_nsel"]), ptr(out["trk_sel"]),
                                             ptr(out["new_n"]), ptr(out["new_nsel"]), ptr(out["new_sel"]), ptr(out["counts"]),
-                                            ptr(out["err"]), ptr(out["new_seq"]), ptr(out["singles"]), _stream(xbin)),
-          "mvmc_assign_listed")
+                                            ptr(out["err"]), ptr(out["new_seq"]), ptr(out["singles"]), ptr(out["big_n"]),
+                                            ptr(out["big_nsel"]), ptr(out["big_sel"]), ptr(out["big_slot"]), _stream(xbin)),
+          "mvmc_assign_groups")
     return out
 
 
@@ -269,3 +272,35 @@ def tracklet_pose_association(trk_joints, n_trk, kps, keep, Kr_inv, cam_loc, max
                                                         Pmax, Tmax, float(max_dst), ptr(match), ptr(cost), ptr(status), _stream(kps)),
           "mvmc_tracklet_pose_association")
     return match, cost, status
+
+
+def ik_birth_big(kps, P, groups, max_nfev=50):
+    """Births from groups of any size (mvmc_ik_birth_big; the slow path behind MVMC_MAX_SEL). kps [B,C,Pmax,17,3], P [B,C,3,4],
+    groups: per clip a list of groups, each a list of (view, pose id). Returns x [B,G,68], joints [B,G,18,3], info [B,G,2,4],
+    cost [B,G,2] with G = the largest number of groups of a clip."""
+    import numpy as np
+    from ._lib import MAX_GROUP
+    kps, P = _c(kps, f64), _c(P, f64)
+    B, C, Pmax = kps.shape[:3]
+    G = max(1, max(len(g) for g in groups))
+    big_n = np.array([len(g) for g in groups], dtype=np.int32)
+    big_nsel = np.zeros((B, G), dtype=np.int32)
+    big_sel = np.zeros((B, G, MAX_GROUP, 2), dtype=np.int32)
+    big_slot = np.tile(np.arange(G, dtype=np.int32), (B, 1))
+    for b, gs in enumerate(groups):
+        for g, sel in enumerate(gs):
+            assert 2 <= len(sel) <= MAX_GROUP
+            big_nsel[b, g] = len(sel)
+            big_sel[b, g, :len(sel)] = np.asarray(sel, dtype=np.int32)
+    dev = kps.device
+    t = lambda a: torch.from_numpy(a).to(dev)
+    lib = _lib.get_lib()
+    ws = torch.zeros(lib.mvmc_ik_birth_big_workspace_bytes() // 8 + 1, dtype=f64, device=dev)
+    x = torch.zeros((B, G, N_PARAM), dtype=f64, device=dev)
+    joints = torch.zeros((B, G, N_B18, 3), dtype=f64, device=dev)
+    info = torch.zeros((B, G, 2, 4), dtype=i32, device=dev)
+    cost = torch.zeros((B, G, 2), dtype=f64, device=dev)
+    bn, bs, bl, bo = t(big_n), t(big_nsel), t(big_sel), t(big_slot)
+    check(lib.mvmc_ik_birth_big(ptr(kps), ptr(P), ptr(bn), ptr(bs), ptr(bl), ptr(bo), B, C, Pmax, G, G, 0, int(max_nfev), ptr(ws), ptr(x),
+                                ptr(joints), ptr(info), ptr(cost), _stream(kps)), "mvmc_ik_birth_big")
+    return x, joints, info, cost

@@ -249,3 +249,39 @@ def check_edge_cases(dev):
     # (a one-view match is not solved but still counts as "matched": the track is not marked missed - the reference's quirk,
     #  src/motion_capture.py:925-934 - so nothing has to die on the single-view frame)
     return seen
+
+
+
+def check_crowded_no_track_frame(dev, n_views=8, n_people=16, seed=1000, clip=0):
+    """Frame 1 of a crowded synthetic clip (no tracks yet): the reference's float32 affinity is not discriminative there, its
+    ALS stops at the 1000-iteration cap and merges many poses - several per view, of several people - into a few groups,
+    and it builds each new track from ALL the poses of its group (src/motion_capture.py:618-624, 942-958). Against the oracle
+    on the same input: X_bin and the iteration count bit-exact, the same groups with the same complete pose lists (the
+    overflow table for the ones beyond MVMC_MAX_SEL), nothing truncated, the same track ids; the births' joints and costs are
+    reported (fits of one skeleton to several people: ill-posed)."""
+    from multiview_motion_capture_b200 import synthetic as S
+    from multiview_motion_capture_b200._lib import MAX_SEL
+    from multiview_motion_capture_b200.clips import ClipBatch
+    c = S.make_clip(n_views, n_people, 3, seed=seed, clip_idx=clip)
+    kps = S.body25_to_coco(c["kps25"])
+    trk = o.Tracker(o.projections(c["K"], c["RT"]), c["K"], c["RT"])
+    a = trk.step(1, kps[1], c["n_pose"][1])
+    cb = ClipBatch(1, n_views, n_people, max_tracks=2 * n_people, max_new=2 * n_people, device=dev)
+    cb.set_calib(c["K"][None], c["RT"][None])
+    rec = cb.step(kps[1][None], c["n_pose"][1][None], 1)[0].copy()
+    _, _, xb, _ = cb.read_matrices(0)
+    assert np.array_equal(xb, a.x_bin) and int(rec["als_iters"]) == a.n_iter, "X_bin / iterations"
+    born_ref = [g for g in a.new_groups if len(g) >= 2]
+    tr = rec["tracks"][:int(rec["n_alive"])]
+    assert rec["error"] == 0 and int(rec["n_truncated"]) == 0
+    assert tr["track_id"].tolist() == [t.track_id for t in trk.tracks]
+    big = cb.read_big_groups(0)
+    sizes, dj, dcost = [], [], []
+    for k, (t, gref, tref) in enumerate(zip(tr, born_ref, trk.tracks)):
+        assert int(t["updated"]) == 2 and int(t["n_sel"]) == len(gref), (k, int(t["n_sel"]), len(gref))
+        sel = big[k] if len(gref) > MAX_SEL else [tuple(x) for x in t["sel"][:len(gref)].tolist()]
+        assert sel == [tuple(x) for x in gref], k
+        sizes.append(len(gref))
+        dj.append(float(np.abs(t["joints"].reshape(18, 3) - tref.joints[-1]).max()))
+    cb.close()
+    return dict(n=int(a.x_bin.shape[0]), als_iters=a.n_iter, group_sizes=sizes, n_big=len(big), joints_diff_m=dj)

@@ -547,3 +547,88 @@ def check_ik_bitwise_vs_cpu_restatement(dev, name, frames):
     for a, b, what in zip(got, ref, ("parameters", "joints", "info", "cost")):
         assert np.array_equal(a, b), (name, what, float(np.abs(np.asarray(a, dtype=np.float64) - b).max()))
     return len(probs), n_birth, worst
+
+
+# ---------------------------------------------------------------------------------------------------
+def check_birth_from_many_poses(dev, n_frames=3, max_nfev=50):
+    """Births from more poses than MVMC_MAX_SEL (the reference builds a no-track group's track from ALL its poses,
+    src/motion_capture.py:618-624, 942-958): k_ik_birth_big against the oracle's PoseSolver restatement on the same pose
+    lists. Groups: one person of a golden scene seen in 8 views at `n_frames` consecutive frames = 8 * n_frames poses treated
+    as that many "views" (consistent enough to converge), and the same with a second person's poses mixed in (the
+    reference's crowded-scene case: an ill-posed fit, compared by cost)."""
+    inp, g = golden("synth_c8p6")
+    kps_all = o.body25_to_coco(inp["kps25"])
+    C = kps_all.shape[1]
+    gt = inp["gt_person"]
+    frames = list(range(2, 2 + n_frames))
+    Pmax = 2 * n_frames
+
+    def poses_of(person, slot0):
+        out, sel = {}, []
+        for q, f in enumerate(frames):
+            for v in range(C):
+                hit = np.nonzero(gt[f, v] == person)[0]
+                if len(hit):
+                    out[(v, slot0 + q)] = kps_all[f, v, hit[0]]
+                    sel.append((v, slot0 + q))
+        return out, sel
+    a, sel_a = poses_of(0, 0)
+    b_, sel_b = poses_of(1, n_frames)
+    kp = np.zeros((1, C, Pmax, 17, 3))
+    for (v, p), k in {**a, **b_}.items():
+        kp[0, v, p] = k
+    Ps = np.array(o.projections(inp["K"], inp["RT"]))
+    groups = [[sel_a, sorted(sel_a + sel_b[:6])]]
+    assert len(sel_a) > MAX_SEL
+    x, joints, info, cost = [t.cpu().numpy() for t in S.ik_birth_big(T(kp, dev), T(Ps[None], dev), groups, max_nfev)]
+    skel = o.load_skeleton()
+    res = []
+    for gi, sel in enumerate(groups[0]):
+        cam_kps = [kp[0, v, p] for v, p in sel]
+        log = []
+        prm, jr = o.solve_ik(skel, None, cam_kps, [Ps[v] for v, _ in sel], collect=log)
+        tri = [e for e in log if e[0] == "tri"][0][1]
+        r2 = [e for e in log if e[0] == "ik2"][0][2]
+        dj = float(np.abs(joints[0, gi] - jr).max())
+        rel = float(abs(cost[0, gi, 1] - r2.cost) / max(r2.cost, 1e-300))
+        res.append((len(sel), dj, rel, info[0, gi, :, :3].tolist(), (r2.nfev, r2.status)))
+    # the clean group converges to the oracle's pose; the mixed one to a comparable cost
+    assert res[0][1] <= 5e-3 and res[0][2] <= 1e-2, res
+    assert res[1][2] <= 0.25, res
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------
+def check_assign_many_pose_groups(dev):
+    """A no-track X_bin with one group of 24 poses (3 views x 8), one of 17 and a pair: the overflow lists of
+    mvmc_assign_groups hold every pose of the two large groups in the reference's member order (ascending global index),
+    new_nsel carries their true sizes, nothing is counted as truncated; the oracle's decode gives the same groups."""
+    C, Pmax, Tmax = 4, 8, 4
+    kps = np.zeros((1, C, Pmax, 17, 3))
+    kps[..., 0] = np.linspace(10, 500, 17)[None, None, None, :]
+    kps[..., 1] = np.linspace(20, 400, 17)[None, None, None, :]
+    kps[..., 2] = 0.9
+    n_pose = np.full((1, C), Pmax, np.int32)
+    n_trk = np.zeros(1, np.int32)
+    prep = S.prepare(T(kps, dev), T(n_pose, dev, i32), T(n_trk, dev, i32), Tmax)
+    n = C * Pmax
+    iv, ip = prep["idx_view"].cpu().numpy()[0], prep["idx_pose"].cpu().numpy()[0]
+    x = np.eye(n, dtype=bool)
+    g1 = [q for q in range(n) if iv[q] in (0, 1, 2)]                 # 24 poses
+    g2 = [q for q in range(n) if iv[q] == 3][:2]                      # a pair ... plus
+    for grp in (g1, g2):
+        for a in grp:
+            for b in grp:
+                x[a, b] = True
+    words = S.pack_xbin(x, Tmax + n)[None].to(dev)
+    out = {k: v.cpu().numpy() for k, v in S.assign(words.contiguous(), prep, T(n_trk, dev, i32), C, 16).items()}
+    assert out["err"][0] == 0 and out["counts"][0, 2] == 0
+    assert out["big_n"][0] == 1 and out["big_nsel"][0, 0] == 24 and out["big_slot"][0, 0] == 0
+    assert out["new_n"][0] == 2 and out["new_nsel"][0, 0] == 24 and out["new_nsel"][0, 1] == 2
+    want = [(int(iv[q]), int(ip[q])) for q in g1]
+    assert [tuple(r) for r in out["big_sel"][0, 0, :24].tolist()] == want
+    assert [tuple(r) for r in out["new_sel"][0, 0].tolist()] == want[:MAX_SEL]
+    # the oracle's closure + parse + decode on the same X_bin
+    groups = o.parse_groups(o.transform_closure(x), np.cumsum([0] + [Pmax] * C))
+    dec = o.decode_groups(groups, 0, iv[:n], ip[:n], False)
+    assert [s_ for s_ in dec.new_groups if len(s_) >= 2] == [want, [(int(iv[q]), int(ip[q])) for q in g2]]

@@ -97,3 +97,12 @@ def test_edge_cases_against_the_oracle(emu):
     """Empty / single-view / ragged / all-filtered frames and the return to the no-track path after every track died."""
     from pipeline_checks import check_edge_cases
     print(check_edge_cases(DEV))
+
+
+def test_birth_from_many_poses(emu):
+    """The slow path behind MVMC_MAX_SEL (24 and 30 poses per group) through the emulator, with a small evaluation budget."""
+    print(SC.check_birth_from_many_poses(DEV, n_frames=3, max_nfev=12))
+
+
+def test_assign_many_pose_groups(emu):
+    SC.check_assign_many_pose_groups(DEV)

@@ -176,3 +176,14 @@ def test_edge_cases_against_the_oracle(cuda):
     """Empty / single-view / ragged / all-filtered frames and the return to the no-track path after every track died."""
     from pipeline_checks import check_edge_cases
     print("edge cases (kind, alive after, died):", check_edge_cases(DEV))
+
+
+def test_crowded_no_track_frame_births_from_all_poses(cuda):
+    """8 x 32, frame 1 (a group of 76 poses among others): groups of more than MVMC_MAX_SEL poses are born from all their poses,
+    like the reference."""
+    from pipeline_checks import check_crowded_no_track_frame
+    r = check_crowded_no_track_frame(DEV, 8, 32, seed=1000, clip=1)
+    print(f"PARITY crowded no-track frame (8x32, n = {r['n']}, ALS {r['als_iters']} iterations): X_bin bit-exact, groups of "
+          f"{r['group_sizes']} poses identical ({r['n_big']} beyond MVMC_MAX_SEL, none truncated), track ids identical; "
+          f"birth joints vs oracle (m): {[round(x, 4) for x in r['joints_diff_m']]}")
+    assert r["n_big"] >= 1

@@ -203,3 +203,9 @@ def test_als_tile_builds_agree(cuda):
                 assert SC.check_als(DEV, name, fr, N=N, rmax=2 * max(Pmax, Tmax)) == len(fr)
     finally:
         lib.mvmc_als_force_variant(-1)
+
+
+def test_birth_from_many_poses(cuda):
+    r = SC.check_birth_from_many_poses(DEV, n_frames=4, max_nfev=50)
+    print("PARITY births from more than MVMC_MAX_SEL poses vs oracle (poses, max joint diff m, rel. cost diff, (nfev, njev, status) x2, oracle):", r)
+    SC.check_assign_many_pose_groups(DEV)
