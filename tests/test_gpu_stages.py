@@ -206,6 +206,6 @@ def test_als_tile_builds_agree(cuda):
 
 
 def test_birth_from_many_poses(cuda):
-    r = SC.check_birth_from_many_poses(DEV, n_frames=4, max_nfev=50)
+    r = SC.check_birth_from_many_poses(DEV, n_frames=3, max_nfev=50)
     print("PARITY births from more than MVMC_MAX_SEL poses vs oracle (poses, max joint diff m, rel. cost diff, (nfev, njev, status) x2, oracle):", r)
     SC.check_assign_many_pose_groups(DEV)
