@@ -100,3 +100,51 @@ def test_two_ranks_equal_single_process(tmp_path, emu):
         upd = ref[c]["tracks"][:int(ref[c]["n_alive"])]
         upd = upd[upd["updated"] > 0]
         assert np.array_equal(a[:, 1], upd["track_id"]) and np.array_equal(a[:, 6:74], upd["param"]) and np.array_equal(a[:, 74:], upd["joints"])
+
+
+class _FakeBatch:
+    """Stands in for a ClipBatch: pack_records writes a pattern that depends on (rank, step)."""
+    def __init__(self, B, rank):
+        self.B, self.rank, self.step = B, rank, 0
+
+    def pack_records(self, cap, clip0=0, rec=None, count=None):
+        rec.zero_()
+        rec[:, 0, 5] = 2.0                                   # one solved track per clip
+        rec[:, 0, 6] = 1000.0 * self.rank + self.step        # a "parameter"
+        count.fill_(1)
+        self.step += 1
+        return rec, count
+
+
+def _gather_worker(rank, world, port, out_dir):
+    sys.path[:0] = [ROOT]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        seen = []
+        g = sharding.RecordGatherer(_FakeBatch(3, rank), cap=2, device="cpu", consume=lambda r: seen.append(r[:, :, 0, 6].clone()))
+        for _ in range(5):
+            g.submit()
+        g.finish()
+        recs, used = g.last()
+        if rank == 0:
+            np.save(os.path.join(out_dir, "seen.npy"), torch.stack(seen).numpy())
+            np.save(os.path.join(out_dir, "used.npy"), used.numpy())
+        else:
+            assert seen == []
+    finally:
+        dist.destroy_process_group()
+
+
+def test_record_gatherer_async_double_buffered(tmp_path):
+    """sharding.RecordGatherer over gloo, world size 2: every step's records of both ranks reach rank 0 exactly once, in
+    order, through the two alternating buffers."""
+    world = 2
+    port = 29700 + (os.getpid() % 2000)
+    mp.spawn(_gather_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    seen = np.load(tmp_path / "seen.npy")          # [steps, world, B]
+    assert seen.shape == (5, 2, 3)
+    for s in range(5):
+        for r in range(2):
+            assert (seen[s, r] == 1000.0 * r + s).all(), (s, r, seen[s, r])
+    assert (np.load(tmp_path / "used.npy") == 1).all()
