@@ -830,7 +830,12 @@ __device__ __forceinline__ void admm_pass(AdmmPass& ps, double* ring, const doub
 #ifndef AL_CTAS_
 #define AL_CTAS_ (512 / AL_THREADS_)
 #endif
+#if defined(AL_MAXREG_) && !defined(MVMC_EMU)
+// (a register cap below 65536 / (CTAs x threads): leaves room on the SM for a co-resident IK solver warp)
+__global__ void __maxnreg__(AL_MAXREG_)
+#else
 __global__ void __launch_bounds__(AL_THREADS, AL_CTAS_)
+#endif
     k_als(const AL_GRID_CONSTANT AlsMaps maps, const double* __restrict__ sim, const int* __restrict__ dim_groups, int n_groups,
           const int* __restrict__ f32_first_iter, const double* __restrict__ rand_stream, const int* __restrict__ order,
           int N, int rmax, double* __restrict__ ws, uint32_t* __restrict__ xbin, int* __restrict__ n_iter_out, double alpha,
