@@ -15,11 +15,11 @@ LIB = os.path.join(LIBDIR, "libmvmc.so")
 SOURCES = ["affinity.cu", "als.cu", "assign.cu", "ik.cu", "ingest.cu", "matchers.cu", "pipeline.cu"]
 # ik.cu: no implicit FMA contraction (every fused operation in the solver is an explicit fma()), so that the CPU build of
 # the same sources (tests/emu, g++ -ffp-contract=off) reproduces the GPU's results bit for bit (parity of I4)
-# als.cu: k_als capped at 112 registers per thread (no spills to speak of): two 8-warp CTAs then leave 8192 registers of an SM free,
-# exactly one IK solver warp, so IK work of another clip group can run beside a full ALS wave instead of waiting for it
-PER_FILE_FLAGS = {"ik.cu": ["-fmad=false"], "als.cu": ["-DAL_MAXREG_=112"]}
+# (als.cu also takes -DAL_MAXREG_=112, which caps k_als at 112 registers with no spills to speak of and leaves room for one IK
+#  solver warp per SM beside two ALS CTAs: measured 1-2 % slower alone and no better overlapped - 4 691 vs 4 765 frames/s - so off)
+PER_FILE_FLAGS = {"ik.cu": ["-fmad=false"]}
 # the same source built again with other tile shapes (see als.cu: AL_VARIANT)
-VARIANTS = [("als.cu", "als_small.o", ["-DAL_VARIANT=small", "-DAL_FM_=3", "-DAL_THREADS_=128", "-DAL_MAXREG_=112"])]
+VARIANTS = [("als.cu", "als_small.o", ["-DAL_VARIANT=small", "-DAL_FM_=3", "-DAL_THREADS_=128"])]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
