@@ -221,9 +221,9 @@ def check_edge_cases(dev, full=True):
         return k, n
 
     seen = []
-    steps = [("normal", 3), ("empty", 4), ("normal", 5), ("one_view", 6), ("ragged", 7)]
+    steps = [("normal", 3), ("one_view", 4), ("ragged", 5), ("empty", 6)]
     if full:
-        steps += [("filtered", 8), ("normal", 8)]
+        steps += [("normal", 7), ("filtered", 8), ("normal", 8)]      # (re-births after everything died: 50-evaluation solves)
     for step, (kind, f) in enumerate(steps):
         k, n = frame(kind, f)
         fi = 100 + step

@@ -68,7 +68,7 @@ def test_warm_started_tracked_frames_bit_exact(name):
     oracle seeded the same way reproduces every matrix, ALS iteration count, assignment, id and parameter bit for bit."""
     _, g = golden(name)
     # (bounded for the CPU tier: ~4 s per 8 x 32 oracle frame; the GPU tier replays every frame of these goldens)
-    last = min(int(g["last_frame"]), int(g["first_frame"]) + {"warm_c8p32": 1, "warm_c8p16": 2, "warm_c8p12": 3}.get(name, 99))
+    last = min(int(g["last_frame"]), int(g["first_frame"]) + {"warm_c8p32": 0, "warm_c8p16": 1, "warm_c8p12": 2}.get(name, 99))
     _free_run(name, last)
 
 
