@@ -240,8 +240,9 @@ struct IkRes {
         }
         __syncwarp();
     }
-    // per column: perturbed chain; the 16 observed joint positions go to the scratch S[(slot*3+c)*WS_NC + col] (aliases s.A)
-    __device__ void fd_prepare(TrfWarp& s, int ncol) {
+    // per column: perturbed chain; the 16 observed joint positions go to the scratch S[(slot*3+c)*TW::NC + col] (aliases s.A)
+    template <class TW>
+    __device__ void fd_prepare(TW& s, int ncol) {
         const int lane = threadIdx.x & 31;
         double* S = s.A;
         local_rots(s.x, Rloc);
@@ -250,10 +251,11 @@ struct IkRes {
             const bool on = c < ncol;
             const int prm = on ? s.act[c] : -1;
             const double xp = on ? s.w[c] : 0.0;
-            fk_store(s.x, Rloc, prm, xp, S + c, WS_NC, true, on);
+            fk_store(s.x, Rloc, prm, xp, S + c, TW::NC, true, on);
         }
     }
-    __device__ __forceinline__ void fd_chunk(TrfWarp& s, int ncol, int ch, const double* f) {
+    template <class TW>
+    __device__ __forceinline__ void fd_chunk(TW& s, int ncol, int ch, const double* f) {
         MVMC_ASSUME_SHARED(&s);
         MVMC_ASSUME_SHARED(f);
         MVMC_ASSUME_SHARED(obs);
@@ -271,7 +273,7 @@ struct IkRes {
                 const int q = q0 + qq;
                 const double* o = obs + (v * MVMC_N_IKJ + q) * 3;
                 double pu, pv, pw;
-                project3(Pv, S[(q * 3) * WS_NC + c], S[(q * 3 + 1) * WS_NC + c], S[(q * 3 + 2) * WS_NC + c], pu, pv, pw);
+                project3(Pv, S[(q * 3) * TW::NC + c], S[(q * 3 + 1) * TW::NC + c], S[(q * 3 + 2) * TW::NC + c], pu, pv, pw);
                 const double inv = 1.0 / (1e-5 + pw);
                 const double ru = DMUL(DSUB(DMUL(pu, inv), o[0]), o[2]);
                 const double rv = DMUL(DSUB(DMUL(pv, inv), o[1]), o[2]);
@@ -491,23 +493,37 @@ __device__ __forceinline__ void mid_spine(const double* k, double* o) {
 
 // ---- per-warp shared memory of the solver kernels ----
 // (the staging copy of the 18-point observations and the triangulated points exist only in the kernels that give birth)
+// The update-only instance is trimmed so that six one-warp CTAs fit an SM: a 50-column solver workspace (the pose model has
+// at most 49 live columns; the 54-column triangulation refine exists only where births do) and no buffer of its own for the
+// trial residuals - a trial is evaluated while the J chunk is idle, so they live there (trf_solve_warp copies an accepted
+// trial into f before the next Jacobian is formed).
+constexpr int IK_UPDATE_NC = 50;
 template <int VMAX, bool BIRTH>
 struct IkBirthSh {
     double obs18[VMAX * 18 * 3];
     double p3[18 * 4];
+    double fn_[32 * VMAX];
+    TrfWarp t;
+    static constexpr int NC = TrfWarp::NC;
+    __device__ __forceinline__ double* fn() { return fn_; }
 };
 template <int VMAX>
-struct IkBirthSh<VMAX, false> {};
+struct IkBirthSh<VMAX, false> {
+    TrfWarpT<IK_UPDATE_NC> t;
+    static constexpr int NC = IK_UPDATE_NC;
+    __device__ __forceinline__ double* fn() { return t.Jc; }
+    static_assert(32 * VMAX <= WS_CH * WS_LDJ, "the trial residuals must fit the J chunk");
+};
 template <int VMAX, bool BIRTH = true>
 struct alignas(16) IkWarpSh : IkBirthSh<VMAX, BIRTH> {
-    TrfWarp t;
-    double f[32 * VMAX], fn[32 * VMAX];
+    double f[32 * VMAX];
     double obs16[VMAX * MVMC_N_IKJ * 3];
     double P[VMAX * 12];
     double posb[MVMC_N_IKJ * 3];
     double Rloc[MVMC_N_B18 * 9];
 };
-static_assert(5 * (sizeof(IkWarpSh<8, false>) + 1024) <= 228 * 1024, "five update-solver CTAs must fit the 228 KB of an SM");
+constexpr int IK_UPDATE_CTAS = 6;   // resident update-solver CTAs per SM
+static_assert(IK_UPDATE_CTAS * (sizeof(IkWarpSh<8, false>) + 1024) <= 228 * 1024, "six update-solver CTAs must fit the 228 KB of an SM");
 
 // Triangulate K (<= 18) joints from nv views (+ optional refine_nfev-evaluation TRF refine); result in sh.p3 [K][4].
 template <int VMAX>
@@ -525,7 +541,7 @@ __device__ void warp_triangulate(IkWarpSh<VMAX>& sh, const double* obs /*[nv][K]
     }
     __syncwarp();
     TriRes tr{obs, sh.P, nv, K};
-    trf_solve_warp(sh.t, tr, 3 * K, 3 * K, 0.0, false, refine_nfev, sh.f, sh.fn);
+    trf_solve_warp(sh.t, tr, 3 * K, 3 * K, 0.0, false, refine_nfev, sh.f, sh.fn());
     __syncwarp();
     for (int e = lane; e < 3 * K; e += 32) sh.p3[(e / 3) * 4 + (e % 3)] = sh.t.x[e];
     __syncwarp();
@@ -533,7 +549,8 @@ __device__ void warp_triangulate(IkWarpSh<VMAX>& sh, const double* obs /*[nv][K]
 
 // active-column list of one IK stage: optimised (free_mask) parameters in [0, npar) that can move a joint.
 // returns ncol; n_opt / x2_dead / has_dead describe the optimised-but-dead parameters (they enter SciPy's norms).
-__device__ int ik_columns(TrfWarp& t, const uint8_t* free_mask, int npar, int& n_opt, double& x2_dead, bool& has_dead) {
+template <class TW>
+__device__ int ik_columns(TW& t, const uint8_t* free_mask, int npar, int& n_opt, double& x2_dead, bool& has_dead) {
     const int lane = threadIdx.x & 31;
     int ncol = 0;
     n_opt = 0;
@@ -938,10 +955,10 @@ __global__ void __launch_bounds__(32)
             r[stage].njev = 1;
             r[stage].status = 0;
             r[stage].cost = 0.0;
-            if (ncol > WS_NC) {
+            if (ncol > Sh::NC) {
                 r[stage].status = -2;
             } else if (ncol > 0) {
-                r[stage] = trf_solve_warp(sh.t, res, ncol, n_opt, x2_dead, has_dead, nfev_cap, sh.f, sh.fn);
+                r[stage] = trf_solve_warp(sh.t, res, ncol, n_opt, x2_dead, has_dead, nfev_cap, sh.f, sh.fn());
             }
             __syncwarp();
         }
@@ -1142,8 +1159,9 @@ static int ensure_skeleton() {
     return MVMC_OK;
 }
 
-// persistent grid: 148 SMs x 4 resident one-warp CTAs
-constexpr int IK_MAX_GRID = 148 * 5;   // persistent one-warp CTAs: five update solvers per SM
+// persistent one-warp CTAs: as many as are resident at once (six update solvers per SM; the kernels with the birth staging
+// or the 3D targets hold fewer - their surplus CTAs find the work counter exhausted)
+constexpr int IK_MAX_GRID = 148 * IK_UPDATE_CTAS;
 static int ik_grid(int M) { return M < IK_MAX_GRID ? M : IK_MAX_GRID; }
 
 extern "C" size_t mvmc_ik_workspace_bytes(int M, int V) {

@@ -45,14 +45,22 @@ constexpr double kDblMax = 1.79769313486231570e308;
 #define DDIV(a, b) __ddiv_rn((a), (b))
 #endif
 
-struct alignas(16) TrfWarp {
-    double A[WS_NC * WS_LDA];       // J^T J, then the Householder vectors; aliased by the FD scratch while J is formed
+// NC = the most live columns the instance is laid out for (A and the FD scratch are NC wide; the vectors keep WS_NC slots).
+// The track-update solver never has more than 49 live columns: its instance is TrfWarpT<50>, 5 KB smaller, which - with the
+// trial residual vector parked in the idle J chunk - lets a sixth solver CTA fit on an SM.
+template <int NC_>
+struct alignas(16) TrfWarpT {
+    static constexpr int NC = NC_;
+    static constexpr int LDA = NC_ | 1;   // row stride of A (odd: conflict-free column walks with 64-bit accesses)
+    double A[NC * LDA];             // J^T J, then the Householder vectors; aliased by the FD scratch while J is formed
     double Jc[WS_CH * WS_LDJ];      // current chunk of J, row major
     double x[MVMC_N_PARAM], xn[MVMC_N_PARAM];
     double g[WS_NC], gt[WS_NC], p[WS_NC], pt[WS_NC], d[WS_NC], e[WS_NC], tau[WS_NC], w[WS_NC], u[WS_NC], dx[WS_NC];
     double sc[8];
     int act[WS_NC];                 // parameter index behind each Jacobian column
 };
+typedef TrfWarpT<WS_NC> TrfWarp;
+static_assert(TrfWarp::LDA == WS_LDA, "WS_LDA is the stride of the full-width instance");
 
 struct TrfResult {
     int nfev, njev, status;
@@ -78,10 +86,11 @@ __device__ __forceinline__ void lane_tile(int lane, int& ti, int& tj) {
 //   int  n_chunks() const;               J is produced chunk by chunk (<= WS_CH rows each)
 //   int  chunk_rows(int c) const;        rows of chunk c;  row index of its first row = chunk_row0(c)
 //   void eval(const double* x, double* f);                 all residuals at x (x, f in shared memory)
-//   void fd_prepare(TrfWarp& s, int ncol);                 per column: perturb, evaluate the model, park the state in s.A
-//   void fd_chunk(TrfWarp& s, int ncol, int c, const double* f);   fill s.Jc[r][col] = (r'(x + h e_col) - f) / dx for chunk c
-template <class Res>
-__device__ __noinline__ void trf_jacobian(TrfWarp& s, Res& res, int ncol, const double* f) {
+//   void fd_prepare(TW& s, int ncol);                      per column: perturb, evaluate the model, park the state in s.A
+//   void fd_chunk(TW& s, int ncol, int c, const double* f);        fill s.Jc[r][col] = (r'(x + h e_col) - f) / dx for chunk c
+template <class TW, class Res>
+__device__ __noinline__ void trf_jacobian(TW& s, Res& res, int ncol, const double* f) {
+    constexpr int LDA = TW::LDA;
     MVMC_ASSUME_SHARED(&s);
     if constexpr (!Res::kGlobalF) MVMC_ASSUME_SHARED(f);   // (the many-view birth solver keeps its residual vectors in global memory)
     const int lane = threadIdx.x & 31;
@@ -140,7 +149,7 @@ __device__ __noinline__ void trf_jacobian(TrfWarp& s, Res& res, int ncol, const 
         __syncwarp();
     }
     // the FD scratch (aliasing A) is dead from here on
-    for (int e = lane; e < WS_NC * WS_LDA; e += 32) s.A[e] = 0.0;
+    for (int e = lane; e < TW::NC * LDA; e += 32) s.A[e] = 0.0;
     __syncwarp();
     if (tile_on) {
 #pragma unroll
@@ -148,8 +157,10 @@ __device__ __noinline__ void trf_jacobian(TrfWarp& s, Res& res, int ncol, const 
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int r = 8 * ti + i, c = 8 * tj + j;
-                s.A[r * WS_LDA + c] = acc[i][j];
-                s.A[c * WS_LDA + r] = acc[i][j];   // (on diagonal tiles both orders are written with the same products)
+                if (TW::NC == WS_NC || (r < TW::NC && c < TW::NC)) {   // (the last tiles of a narrower instance hang over its edge)
+                    s.A[r * LDA + c] = acc[i][j];
+                    s.A[c * LDA + r] = acc[i][j];   // (on diagonal tiles both orders are written with the same products)
+                }
             }
     }
     if (lane < ncol) s.g[lane] = g0;
@@ -160,16 +171,18 @@ __device__ __noinline__ void trf_jacobian(TrfWarp& s, Res& res, int ncol, const 
 
 // A (n x n, symmetric, full storage) -> tridiagonal T = Q^T A Q: d[0..n), e[0..n-1); reflector k is stored in
 // A[k+2.., k] (v[k+1] = 1 implicit) with s.tau[k]. LAPACK dsytd2 (lower) arithmetic, one warp.
-__device__ __noinline__ void warp_tridiagonalise(TrfWarp& s, int n) {
+template <class TW>
+__device__ __noinline__ void warp_tridiagonalise(TW& s, int n) {
+    constexpr int LDA = TW::LDA;
     MVMC_ASSUME_SHARED(&s);
     const int lane = threadIdx.x & 31;
     for (int k = 0; k + 1 < n; k++) {
         const int r0 = k + 1 + lane, r1 = r0 + 32;
-        const double a0 = r0 < n ? s.A[r0 * WS_LDA + k] : 0.0;
-        const double a1 = r1 < n ? s.A[r1 * WS_LDA + k] : 0.0;
+        const double a0 = r0 < n ? s.A[r0 * LDA + k] : 0.0;
+        const double a1 = r1 < n ? s.A[r1 * LDA + k] : 0.0;
         const double alpha = __shfl_sync(MVMC_FULL, a0, 0);
         const double xn2 = warp_sum(fma(a1, a1, lane == 0 ? 0.0 : a0 * a0));
-        if (lane == 0) s.d[k] = s.A[k * WS_LDA + k];
+        if (lane == 0) s.d[k] = s.A[k * LDA + k];
         if (xn2 == 0.0) {
             if (lane == 0) {
                 s.tau[k] = 0.0;
@@ -185,11 +198,11 @@ __device__ __noinline__ void warp_tridiagonalise(TrfWarp& s, int n) {
         const double v1 = a1 * scal;
         if (r0 < n) {
             s.u[r0] = v0;
-            if (lane != 0) s.A[r0 * WS_LDA + k] = v0;
+            if (lane != 0) s.A[r0 * LDA + k] = v0;
         }
         if (r1 < n) {
             s.u[r1] = v1;
-            s.A[r1 * WS_LDA + k] = v1;
+            s.A[r1 * LDA + k] = v1;
         }
         if (lane == 0) {
             s.tau[k] = tau;
@@ -199,12 +212,12 @@ __device__ __noinline__ void warp_tridiagonalise(TrfWarp& s, int n) {
         // w = tau * A22 v
         double w0 = 0.0, w1 = 0.0;
         if (r0 < n) {
-            const double* row = s.A + r0 * WS_LDA;
+            const double* row = s.A + r0 * LDA;
 #pragma unroll 4
             for (int c = k + 1; c < n; c++) w0 = fma(row[c], s.u[c], w0);
         }
         if (r1 < n) {
-            const double* row = s.A + r1 * WS_LDA;
+            const double* row = s.A + r1 * LDA;
 #pragma unroll 4
             for (int c = k + 1; c < n; c++) w1 = fma(row[c], s.u[c], w1);
         }
@@ -219,26 +232,28 @@ __device__ __noinline__ void warp_tridiagonalise(TrfWarp& s, int n) {
         __syncwarp();
         // A22 -= v w^T + w v^T
         if (r0 < n) {
-            double* row = s.A + r0 * WS_LDA;
+            double* row = s.A + r0 * LDA;
 #pragma unroll 4
             for (int c = k + 1; c < n; c++) row[c] = fma(-w0, s.u[c], fma(-v0, s.w[c], row[c]));
         }
         if (r1 < n) {
-            double* row = s.A + r1 * WS_LDA;
+            double* row = s.A + r1 * LDA;
 #pragma unroll 4
             for (int c = k + 1; c < n; c++) row[c] = fma(-w1, s.u[c], fma(-v1, s.w[c], row[c]));
         }
         __syncwarp();
     }
     if (lane == 0) {
-        s.d[n - 1] = s.A[(n - 1) * WS_LDA + (n - 1)];
+        s.d[n - 1] = s.A[(n - 1) * LDA + (n - 1)];
         if (n >= 1) s.e[n - 1] = 0.0;
     }
     __syncwarp();
 }
 
 // y <- H_k y for k = 0..n-3 (forward = true: y <- Q^T y) or k = n-3..0 (y <- Q y). y in shared memory.
-__device__ __noinline__ void warp_apply_q(const TrfWarp& s, int n, double* y, bool transpose) {
+template <class TW>
+__device__ __noinline__ void warp_apply_q(const TW& s, int n, double* y, bool transpose) {
+    constexpr int LDA = TW::LDA;
     MVMC_ASSUME_SHARED(&s);
     MVMC_ASSUME_SHARED(y);
     const int lane = threadIdx.x & 31;
@@ -247,8 +262,8 @@ __device__ __noinline__ void warp_apply_q(const TrfWarp& s, int n, double* y, bo
         const double tau = s.tau[k];
         if (tau == 0.0) continue;  // uniform
         const int r0 = k + 1 + lane, r1 = r0 + 32;
-        const double v0 = r0 < n ? (lane == 0 ? 1.0 : s.A[r0 * WS_LDA + k]) : 0.0;
-        const double v1 = r1 < n ? s.A[r1 * WS_LDA + k] : 0.0;
+        const double v0 = r0 < n ? (lane == 0 ? 1.0 : s.A[r0 * LDA + k]) : 0.0;
+        const double v1 = r1 < n ? s.A[r1 * LDA + k] : 0.0;
         const double y0 = r0 < n ? y[r0] : 0.0;
         const double y1 = r1 < n ? y[r1] : 0.0;
         const double dot = tau * warp_sum(fma(v1, y1, v0 * y0));
@@ -289,7 +304,8 @@ __device__ __forceinline__ void pcr_neigh(double v0, double v1, int s, int lane,
 }
 
 // factor + solve: b0/b1 = right-hand side rows (lane, lane+32) -> y0/y1
-__device__ __forceinline__ void pcr_solve(const TrfWarp& s, int n, double alpha, double floor_, double& r0, double& r1,
+template <class TW>
+__device__ __forceinline__ void pcr_solve(const TW& s, int n, double alpha, double floor_, double& r0, double& r1,
                                           PcrFactors& F) {
     const int lane = threadIdx.x & 31;
     const int i0 = lane, i1 = lane + 32;
@@ -360,7 +376,8 @@ __device__ __forceinline__ void pcr_resolve(const PcrFactors& F, double& r0, dou
 // SciPy solve_lsq_trust_region in the Q basis. In: s.d, s.e, s.gt (= Q^T g), delta, alpha (warm start), full_rank.
 // Out: s.pt (step in the Q basis, already rescaled), returns alpha; sc[1] = ||p||, sc[2] = predicted reduction.
 // Every lane computes the same scalars (butterfly reductions), so the control flow is warp uniform.
-__device__ __noinline__ double trf_subproblem(TrfWarp& s, int n, double delta, double alpha, bool full_rank) {
+template <class TW>
+__device__ __noinline__ double trf_subproblem(TW& s, int n, double delta, double alpha, bool full_rank) {
     MVMC_ASSUME_SHARED(&s);
     const int lane = threadIdx.x & 31;
     const int i0 = lane, i1 = lane + 32;
@@ -455,8 +472,8 @@ __device__ __noinline__ double trf_subproblem(TrfWarp& s, int n, double delta, d
 // s.x holds the full parameter vector; s.act[0..ncol) the optimised parameters that can move a residual
 // ("live" columns); n_opt = number of optimised parameters including structurally dead ones (they only enter
 // SciPy's norms of x and its m >= n rank test); x2_dead = sum of squares of the dead optimised parameters.
-template <class Res>
-__device__ TrfResult trf_solve_warp(TrfWarp& s, Res& res, int ncol, int n_opt, double x2_dead, bool has_dead, int max_nfev,
+template <class TW, class Res>
+__device__ TrfResult trf_solve_warp(TW& s, Res& res, int ncol, int n_opt, double x2_dead, bool has_dead, int max_nfev,
                                     double* f, double* fn) {
     const int lane = threadIdx.x & 31;
     const int m = res.m();
@@ -482,7 +499,7 @@ __device__ TrfResult trf_solve_warp(TrfWarp& s, Res& res, int ncol, int n_opt, d
         if (status != -1 || nfev == max_nfev) break;
         // zero columns of J?  (exactly zero diagonal of J^T J)
         int zc = 0;
-        for (int c = lane; c < ncol; c += 32) zc |= (s.A[c * WS_LDA + c] == 0.0) ? 1 : 0;
+        for (int c = lane; c < ncol; c += 32) zc |= (s.A[c * TW::LDA + c] == 0.0) ? 1 : 0;
         zc = warp_sum_i(zc);
         const bool full_rank = (m >= n_opt) && !has_dead && zc == 0;
         for (int c = lane; c < ncol; c += 32) s.gt[c] = s.g[c];
