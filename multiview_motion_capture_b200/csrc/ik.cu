@@ -160,30 +160,24 @@ __device__ __noinline__ void fk_store(const double* x, const double* Rloc, int p
         }
     };
     emit(0, pr[0], pr[1], pr[2]);
-    // Everything a joint reads from memory is requested before the previous joint's position is stored (`out` may be any
-    // memory as far as the compiler knows, so it never moves a load above one of those stores itself): the bone length of
-    // joint j + 1 (a constant-bank index, then x) while joint j is worked on, joint j's local rotation at the top of its
-    // iteration. The walk is one dependent chain per lane; these two loads were most of its length.
-    double len_next = getx(57 + c_skel.side_to_full[1]);
 #pragma unroll 1
     for (int j = 1; j < MVMC_N_B18; j++) {
         const int sel = c_fk_psel[j];
-        const double len = len_next;
-        double m[9];
-#pragma unroll
-        for (int q = 0; q < 9; q++) m[q] = j == jo ? mo[q] : Rloc[j * 9 + q];   // (a leaf's slot is read and never used)
-        if (j + 1 < MVMC_N_B18) len_next = getx(57 + c_skel.side_to_full[j + 1]);
         double Rp[9], pp[3];
 #pragma unroll
         for (int q = 0; q < 9; q++) Rp[q] = sel == 0 ? Gc[q] : (sel == 1 ? Gr[q] : Gn[q]);
 #pragma unroll
         for (int q = 0; q < 3; q++) pp[q] = sel == 0 ? pc[q] : (sel == 1 ? pr[q] : pn[q]);
+        const double len = getx(57 + c_skel.side_to_full[j]);
         const double o0 = c_skel.dirs[j][0] * len, o1 = c_skel.dirs[j][1] * len, o2 = c_skel.dirs[j][2] * len;
         double pj[3];
 #pragma unroll
         for (int r = 0; r < 3; r++) pj[r] = fma(Rp[r * 3 + 2], o2, fma(Rp[r * 3 + 1], o1, fma(Rp[r * 3], o0, pp[r])));
         emit(j, pj[0], pj[1], pj[2]);
         if (!c_skel.leaf[j]) {   // uniform branch
+            double m[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) m[q] = j == jo ? mo[q] : Rloc[j * 9 + q];
 #pragma unroll
             for (int r = 0; r < 3; r++)
 #pragma unroll
@@ -274,10 +268,6 @@ struct IkRes {
         for (int e = 0; e < 12; e++) Pv[e] = P[v * 12 + e];
         for (int c = lane; c < ncol; c += 32) {
             const double rdx = s.tau[c];   // 1 / dx, formed once per Jacobian
-            // the eight entries of the column are formed before the first is stored: the compiler cannot prove that a store
-            // into the J chunk leaves the parked positions, the observations and f alone, so stores between the four joints
-            // would serialise their loads and their reciprocals
-            double jv[8];
 #pragma unroll
             for (int qq = 0; qq < 4; qq++) {
                 const int q = q0 + qq;
@@ -288,11 +278,9 @@ struct IkRes {
                 const double ru = DMUL(DSUB(DMUL(pu, inv), o[0]), o[2]);
                 const double rv = DMUL(DSUB(DMUL(pv, inv), o[1]), o[2]);
                 const int row = (v * MVMC_N_IKJ + q) * 2;
-                jv[2 * qq] = DMUL(DSUB(ru, f[row]), rdx);
-                jv[2 * qq + 1] = DMUL(DSUB(rv, f[row + 1]), rdx);
+                s.Jc[(2 * qq) * WS_LDJ + c] = DMUL(DSUB(ru, f[row]), rdx);
+                s.Jc[(2 * qq + 1) * WS_LDJ + c] = DMUL(DSUB(rv, f[row + 1]), rdx);
             }
-#pragma unroll
-            for (int e = 0; e < 8; e++) s.Jc[e * WS_LDJ + c] = jv[e];
         }
     }
 };

@@ -209,76 +209,37 @@ __device__ __noinline__ void warp_tridiagonalise(TW& s, int n) {
             s.e[k] = beta;
         }
         __syncwarp();
-        // w = tau * A22 v. Both rows of a lane in one loop: two independent accumulation chains (a dependent DFMA is 8
-        // cycles) with one broadcast load of u[c] between them; each row's sum keeps its order.
+        // w = tau * A22 v
         double w0 = 0.0, w1 = 0.0;
-        const bool on0 = r0 < n, on1 = r1 < n;
-        const double* row0 = s.A + (on0 ? r0 : k + 1) * LDA;
-        const double* row1 = s.A + (on1 ? r1 : k + 1) * LDA;
-        if (__any_sync(MVMC_FULL, on1)) {
+        if (r0 < n) {
+            const double* row = s.A + r0 * LDA;
 #pragma unroll 4
-            for (int c = k + 1; c < n; c++) {
-                const double uc = s.u[c];
-                w0 = fma(row0[c], uc, w0);
-                w1 = fma(row1[c], uc, w1);
-            }
-        } else {
-#pragma unroll 4
-            for (int c = k + 1; c < n; c++) w0 = fma(row0[c], s.u[c], w0);
+            for (int c = k + 1; c < n; c++) w0 = fma(row[c], s.u[c], w0);
         }
-        if (!on0) w0 = 0.0;
-        if (!on1) w1 = 0.0;
+        if (r1 < n) {
+            const double* row = s.A + r1 * LDA;
+#pragma unroll 4
+            for (int c = k + 1; c < n; c++) w1 = fma(row[c], s.u[c], w1);
+        }
         w0 *= tau;
         w1 *= tau;
-        const double wv = warp_sum(fma(w1, v1, on0 ? w0 * v0 : 0.0));
+        const double wv = warp_sum(fma(r1 < n ? w1 : 0.0, v1, r0 < n ? w0 * v0 : 0.0));
         const double kk = -0.5 * tau * wv;
         w0 = fma(kk, v0, w0);
         w1 = fma(kk, v1, w1);
-        if (on0) s.w[r0] = w0;
-        if (on1) s.w[r1] = w1;
+        if (r0 < n) s.w[r0] = w0;
+        if (r1 < n) s.w[r1] = w1;
         __syncwarp();
-        // A22 -= v w^T + w v^T, four columns at a time: every load of the block is issued before its first store (the
-        // compiler cannot prove that a store into a row of A leaves u and w alone, so an element-by-element loop waits
-        // out a full shared-memory round trip per element)
-        {
-            double* a0p = s.A + (on0 ? r0 : k + 1) * LDA;
-            double* a1p = s.A + (on1 ? r1 : k + 1) * LDA;
-            const bool any1 = __any_sync(MVMC_FULL, on1);
-            int c = k + 1;
-            for (; c + 4 <= n; c += 4) {
-                double uu[4], ww[4], x0[4], x1[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    uu[q] = s.u[c + q];
-                    ww[q] = s.w[c + q];
-                    x0[q] = a0p[c + q];
-                }
-                if (any1) {
-#pragma unroll
-                    for (int q = 0; q < 4; q++) x1[q] = a1p[c + q];
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++) x0[q] = fma(-w0, uu[q], fma(-v0, ww[q], x0[q]));
-                if (any1) {
-#pragma unroll
-                    for (int q = 0; q < 4; q++) x1[q] = fma(-w1, uu[q], fma(-v1, ww[q], x1[q]));
-                }
-                if (on0) {
-#pragma unroll
-                    for (int q = 0; q < 4; q++) a0p[c + q] = x0[q];
-                }
-                if (on1) {
-#pragma unroll
-                    for (int q = 0; q < 4; q++) a1p[c + q] = x1[q];
-                }
-            }
-            for (; c < n; c++) {
-                const double uc = s.u[c], wc = s.w[c];
-                const double y0 = fma(-w0, uc, fma(-v0, wc, a0p[c]));
-                const double y1 = fma(-w1, uc, fma(-v1, wc, a1p[c]));
-                if (on0) a0p[c] = y0;
-                if (on1) a1p[c] = y1;
-            }
+        // A22 -= v w^T + w v^T
+        if (r0 < n) {
+            double* row = s.A + r0 * LDA;
+#pragma unroll 4
+            for (int c = k + 1; c < n; c++) row[c] = fma(-w0, s.u[c], fma(-v0, s.w[c], row[c]));
+        }
+        if (r1 < n) {
+            double* row = s.A + r1 * LDA;
+#pragma unroll 4
+            for (int c = k + 1; c < n; c++) row[c] = fma(-w1, s.u[c], fma(-v1, s.w[c], row[c]));
         }
         __syncwarp();
     }
@@ -296,33 +257,19 @@ __device__ __noinline__ void warp_apply_q(const TW& s, int n, double* y, bool tr
     MVMC_ASSUME_SHARED(&s);
     MVMC_ASSUME_SHARED(y);
     const int lane = threadIdx.x & 31;
-    // reflector q + 1 (tau and the two entries of v this lane owns) is fetched before y is written for reflector q: the
-    // compiler cannot move those loads above the stores to y itself
-    auto fetch = [&](int q, double& tau, double& v0, double& v1) {
-        const int k = transpose ? q : n - 3 - q;
-        const int r0 = k + 1 + lane, r1 = r0 + 32;
-        tau = s.tau[k];
-        v0 = r0 < n ? (lane == 0 ? 1.0 : s.A[r0 * LDA + k]) : 0.0;
-        v1 = r1 < n ? s.A[r1 * LDA + k] : 0.0;
-    };
-    double tau = 0.0, v0 = 0.0, v1 = 0.0;
-    if (n > 2) fetch(0, tau, v0, v1);
     for (int q = 0; q + 2 < n; q++) {
         const int k = transpose ? q : n - 3 - q;
+        const double tau = s.tau[k];
+        if (tau == 0.0) continue;  // uniform
         const int r0 = k + 1 + lane, r1 = r0 + 32;
+        const double v0 = r0 < n ? (lane == 0 ? 1.0 : s.A[r0 * LDA + k]) : 0.0;
+        const double v1 = r1 < n ? s.A[r1 * LDA + k] : 0.0;
         const double y0 = r0 < n ? y[r0] : 0.0;
         const double y1 = r1 < n ? y[r1] : 0.0;
-        double tau_n = 0.0, v0_n = 0.0, v1_n = 0.0;
-        if (q + 3 < n) fetch(q + 1, tau_n, v0_n, v1_n);
-        if (tau != 0.0) {  // uniform
-            const double dot = tau * warp_sum(fma(v1, y1, v0 * y0));
-            if (r0 < n) y[r0] = fma(-dot, v0, y0);
-            if (r1 < n) y[r1] = fma(-dot, v1, y1);
-        }
+        const double dot = tau * warp_sum(fma(v1, y1, v0 * y0));
+        if (r0 < n) y[r0] = fma(-dot, v0, y0);
+        if (r1 < n) y[r1] = fma(-dot, v1, y1);
         __syncwarp();
-        tau = tau_n;
-        v0 = v0_n;
-        v1 = v1_n;
     }
 }
 
